@@ -1,0 +1,321 @@
+"""ctypes binding of libaxisafe_b200.so (include/axisafe_b200.h) + torch device buffers.
+
+PyTorch is used only for device memory (``torch.empty(..., device='cuda')``,
+``.data_ptr()``), streams and ``torch.distributed``; every numerical kernel is in
+the shared library.  There is deliberately no CPU fallback: a missing library or a
+missing GPU raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, '_lib', 'libaxisafe_b200.so')
+_lib = None
+
+_c_int_p = ctypes.c_void_p
+_SIGNATURES = {
+    'axs_version': (ctypes.c_int, []),
+    'axs_strerror': (ctypes.c_char_p, [ctypes.c_int]),
+    'axs_max_small_n2': (ctypes.c_int, []),
+    'axs_element_matrices': (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p] * 6),
+    'axs_assemble_operators': (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p] * 5 +
+                               [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5),
+    'axs_build_S': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 6 + [ctypes.c_int] +
+                    [ctypes.c_void_p] * 2),
+    'axs_eig_worksize': (ctypes.c_longlong, [ctypes.c_int, ctypes.c_int]),
+    'axs_eig_sweep': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 6 + [ctypes.c_int] +
+                      [ctypes.c_void_p] * 4 + [ctypes.c_longlong, ctypes.c_void_p]),
+    'axs_reduce': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 6 + [ctypes.c_int] +
+                   [ctypes.c_void_p] * 2 + [ctypes.c_longlong, ctypes.c_void_p]),
+    'axs_hqr': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 3 + [ctypes.c_longlong, ctypes.c_void_p]),
+    'axs_modes': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 2 + [ctypes.c_int] +
+                  [ctypes.c_void_p] * 3 + [ctypes.c_longlong, ctypes.c_void_p]),
+    'axs_get_reduction': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 4),
+    'axs_track_worksize': (ctypes.c_longlong, [ctypes.c_int, ctypes.c_int]),
+    'axs_track_pairs': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 3 + [ctypes.c_int] +
+                        [ctypes.c_void_p] * 3 + [ctypes.c_longlong, ctypes.c_void_p]),
+    'axs_track_scan': (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p]),
+    'axs_apply_order': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 6),
+}
+EXPORTED = tuple(_SIGNATURES)
+
+
+def lib():
+    """Load (once) and return the shared library; raise if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('axisafe_b200: CUDA library not built (%s). Run '
+                               '`python -c "import __graft_entry__ as g; g.build()"` '
+                               'or axisym-safe-python_b200/build.py; there is no CPU fallback.' % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def torch_cuda():
+    """Return the torch module after checking that a CUDA device is usable."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('axisafe_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    return torch
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().axs_strerror(code).decode()
+        raise RuntimeError('%s failed: %s (code %d)' % (what, msg, code))
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(torch):
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def to_device(array, torch, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(array))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+# ------------------------------------------------------------------------ kernel 1a
+class DeviceElements(object):
+    """Element matrices resident on the GPU + the tables needed to scatter them."""
+
+    def __init__(self, out, edesc_i, offsets, sizes):
+        self.out, self.edesc_i, self.offsets, self.sizes = out, edesc_i, offsets, sizes
+
+
+def element_matrices(elements):
+    """Run axs_element_matrices for a list of element objects (elements.py classes).
+
+    Installs the results on the objects (``_load``) and returns a DeviceElements.
+    """
+    from . import shape_functions as sf
+    torch = torch_cuda()
+    L = lib()
+    tables, table_off, cache = [], {}, 0
+    desc_i, desc_d, nodes, offsets, sizes = [], [], [], [], []
+    node_off = out_off = 0
+    for el in elements:
+        (kind, family, pml, m), dbl = el._descriptor()
+        if m > 64:
+            raise ValueError('element with %d nodes exceeds the kernel limit of 64' % m)
+        key = (family, m)
+        if key not in table_off:
+            ksi, w = (sf.build_GLJ_quadrature if family == 1 else sf.build_GLL_quadrature)(m)
+            D = (sf.lagrange_GLJ if family == 1 else sf.lagrange_poly)(ksi)[1]
+            table_off[key] = cache
+            block = np.concatenate([ksi, w, D.ravel()])
+            tables.append(block)
+            cache += len(block)
+        nd = (3 if kind == 0 else 1) * m
+        desc_i.append([kind, family, pml, m, table_off[key], node_off, out_off, 0])
+        desc_d.append(list(dbl) + [0.0] * (12 - len(dbl)))
+        nodes.append(np.asarray(el.nodes_at, dtype=np.float64))
+        offsets.append(out_off)
+        sizes.append(nd)
+        node_off += m
+        out_off += 10 * nd * nd
+    d_i = to_device(np.array(desc_i, dtype=np.int32), torch)
+    d_d = to_device(np.array(desc_d, dtype=np.float64), torch)
+    d_t = to_device(np.concatenate(tables), torch)
+    d_n = to_device(np.concatenate(nodes), torch)
+    out = torch.empty(out_off, dtype=torch.complex128, device='cuda')
+    check(L.axs_element_matrices(len(elements), _ptr(d_i), _ptr(d_d), _ptr(d_t), _ptr(d_n), _ptr(out),
+                                 _stream(torch)), 'axs_element_matrices')
+    host = out.cpu().numpy()
+    for el, off, nd in zip(elements, offsets, sizes):
+        el._load(host[off:off + 10 * nd * nd].reshape(10, nd, nd).copy())
+    return DeviceElements(out, d_i, offsets, sizes)
+
+
+# ------------------------------------------------------------------------ kernel 1b
+class DeviceOperators(object):
+    """Banded operators of the quadratic pencil, resident in HBM."""
+
+    def __init__(self, N, hb, K0s, Cb, Mb, K1c, K6d):
+        self.N, self.hb = N, hb
+        self.K0s, self.Cb, self.Mb, self.K1c, self.K6d = K0s, Cb, Mb, K1c, K6d
+
+    def band_to_dense(self, t):
+        """Host dense N x N copy of one banded operator (tests / debugging)."""
+        W = 2 * self.hb + 1
+        band = t.cpu().numpy().reshape(self.N, W)
+        dense = np.zeros([self.N, self.N], complex)
+        for r in range(self.N):
+            for c in range(max(0, r - self.hb), min(self.N, r + self.hb + 1)):
+                dense[r, c] = band[r, c - r + self.hb]
+        return dense
+
+
+def assemble_operators(mesh, order, dev_elem):
+    """Scatter the element matrices into the banded operators (axs_assemble_operators)."""
+    torch = torch_cuda()
+    L = lib()
+    N = mesh.no_of_dofs
+    lm_all, lm_off, hb = [], [], 0
+    for el in order:
+        obj = mesh.elements[el]
+        reduced = iter(mesh.LM[el])
+        full = [-1 if i in obj._dropped else next(reduced) for i in range(obj._full_dofs)]
+        live = [g for g in full if g >= 0]
+        if live:
+            hb = max(hb, max(live) - min(live))
+        lm_off.append(len(lm_all))
+        lm_all.extend(full)
+    K1c = None
+    if mesh.is_coupled and mesh.K1_coupling is not None and mesh.K1_coupling.nnz:
+        coo = mesh.K1_coupling.tocoo()
+        hb = max(hb, int(np.max(np.abs(coo.row - coo.col))))
+    W = 2 * hb + 1
+    if mesh.is_coupled and mesh.K1_coupling is not None and mesh.K1_coupling.nnz:
+        band = np.zeros([N, W], complex)
+        np.add.at(band, (coo.row, coo.col - coo.row + hb), coo.data)
+        K1c = to_device(band, torch)
+    tclass = np.array([0 if t == 1 else 1 for t in mesh.Tdiag], dtype=np.int32)
+    d_lm = to_device(np.array(lm_all, dtype=np.int32), torch)
+    d_off = to_device(np.array(lm_off, dtype=np.int32), torch)
+    d_tc = to_device(tclass, torch)
+    K0s = torch.zeros(N * W, dtype=torch.complex128, device='cuda')
+    Cb = torch.zeros_like(K0s)
+    Mb = torch.zeros_like(K0s)
+    K6d = torch.zeros(N, dtype=torch.complex128, device='cuda')
+    check(L.axs_assemble_operators(len(order), _ptr(dev_elem.edesc_i), _ptr(dev_elem.out), _ptr(d_lm),
+                                   _ptr(d_off), _ptr(d_tc), int(mesh.n), N, hb, _ptr(K0s), _ptr(Cb),
+                                   _ptr(Mb), _ptr(K6d), _stream(torch)), 'axs_assemble_operators')
+    return DeviceOperators(N, hb, K0s, Cb, Mb, K1c, K6d)
+
+
+# ------------------------------------------------------------------- kernels 1c, 2, 3
+def build_S(ops, omega):
+    """Dense S(w) batch [nf, n2, n2] (column-major per matrix) as a device tensor."""
+    torch = torch_cuda()
+    n2 = 2 * ops.N
+    S = torch.empty(len(omega) * n2 * n2, dtype=torch.complex128, device='cuda')
+    check(lib().axs_build_S(ops.N, ops.hb, _ptr(ops.K0s), _ptr(ops.Cb), _ptr(ops.Mb), _ptr(ops.K1c),
+                            _ptr(ops.K6d), _ptr(omega), len(omega), _ptr(S), _stream(torch)), 'axs_build_S')
+    return S
+
+
+class EigWorkspace(object):
+    def __init__(self, N, nf):
+        torch = torch_cuda()
+        self.N, self.nf = N, nf
+        self.bytes = int(lib().axs_eig_worksize(N, nf))
+        self.buf = torch.empty(self.bytes, dtype=torch.uint8, device='cuda')
+
+
+def eig_sweep(ops, omega, want_modes=True, work=None):
+    """axs_eig_sweep: returns (k [nf, n2], psi [nf, n2, n2] or None, info [nf], workspace)."""
+    torch = torch_cuda()
+    nf, n2 = len(omega), 2 * ops.N
+    work = work or EigWorkspace(ops.N, nf)
+    k = torch.empty(nf * n2, dtype=torch.complex128, device='cuda')
+    psi = torch.empty(nf * n2 * n2, dtype=torch.complex128, device='cuda') if want_modes else None
+    info = torch.zeros(nf, dtype=torch.int32, device='cuda')
+    check(lib().axs_eig_sweep(ops.N, ops.hb, _ptr(ops.K0s), _ptr(ops.Cb), _ptr(ops.Mb), _ptr(ops.K1c),
+                              _ptr(ops.K6d), _ptr(omega), nf, _ptr(k), _ptr(psi), _ptr(info),
+                              _ptr(work.buf), work.bytes, _stream(torch)), 'axs_eig_sweep')
+    return k, psi, info, work
+
+
+def reduce_dense(S, N, nf, work=None):
+    """axs_reduce on an explicit dense batch (parity tests)."""
+    torch = torch_cuda()
+    work = work or EigWorkspace(N, nf)
+    check(lib().axs_reduce(N, 0, None, None, None, None, None, None, nf, _ptr(S), _ptr(work.buf),
+                           work.bytes, _stream(torch)), 'axs_reduce')
+    return work
+
+
+def hqr(N, nf, work):
+    torch = torch_cuda()
+    n2 = 2 * N
+    k = torch.empty(nf * n2, dtype=torch.complex128, device='cuda')
+    info = torch.zeros(nf, dtype=torch.int32, device='cuda')
+    check(lib().axs_hqr(N, nf, _ptr(k), _ptr(info), _ptr(work.buf), work.bytes, _stream(torch)), 'axs_hqr')
+    return k, info
+
+
+def modes(ops, nf, k, work):
+    torch = torch_cuda()
+    n2 = 2 * ops.N
+    psi = torch.empty(nf * n2 * n2, dtype=torch.complex128, device='cuda')
+    check(lib().axs_modes(ops.N, ops.hb, _ptr(ops.Cb), _ptr(ops.K6d), nf, _ptr(k), _ptr(psi),
+                          _ptr(work.buf), work.bytes, _stream(torch)), 'axs_modes')
+    return psi
+
+
+def get_reduction(N, nf, work):
+    torch = torch_cuda()
+    n2 = 2 * N
+    scale = torch.empty(nf * n2, dtype=torch.float64, device='cuda')
+    H = torch.empty(nf * n2 * n2, dtype=torch.complex128, device='cuda')
+    check(lib().axs_get_reduction(N, nf, _ptr(work.buf), _ptr(scale), _ptr(H), _stream(torch)),
+          'axs_get_reduction')
+    return scale.cpu().numpy().reshape(nf, n2), H.cpu().numpy().reshape(nf, n2, n2).transpose(0, 2, 1)
+
+
+def track_pairs(ops, psi, npairs, scratch=None):
+    """axs_track_pairs: (arg [npairs, n2] int32, amax [npairs, n2] float64) device tensors."""
+    torch = torch_cuda()
+    n2 = 2 * ops.N
+    need = int(lib().axs_track_worksize(ops.N, npairs))
+    if scratch is None or scratch.numel() * scratch.element_size() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device='cuda')
+    arg = torch.empty(npairs * n2, dtype=torch.int32, device='cuda')
+    amax = torch.empty(npairs * n2, dtype=torch.float64, device='cuda')
+    check(lib().axs_track_pairs(ops.N, ops.hb, _ptr(ops.Cb), _ptr(ops.K6d), _ptr(psi), npairs, _ptr(arg),
+                                _ptr(amax), _ptr(scratch), need, _stream(torch)), 'axs_track_pairs')
+    return arg, amax
+
+
+def track_scan(arg, amax, nf, n2):
+    """Reference column order per frequency (solver.py:159-182) from the arg-max tables.
+
+    ``arg``/``amax`` are host arrays [nf-1, n2].  The hot loop is the C function
+    axs_track_scan; frequencies where some tracked mode has round(|biorth|, 2) <= 0.9
+    take the reference's fix-up with the very same Python set expression, so the
+    (CPython-specific) iteration order of ``set`` is reproduced exactly.
+    """
+    arg = np.ascontiguousarray(arg, dtype=np.int32)
+    amax = np.ascontiguousarray(amax, dtype=np.float64)
+    order = np.zeros([nf, n2], dtype=np.int32)
+    L = lib()
+    start = 0
+    while True:
+        i = L.axs_track_scan(arg.ctypes.data, amax.ctypes.data, nf, n2, start, order.ctypes.data)
+        if i >= nf:
+            return order
+        prev = order[i - 1]
+        new_order = arg[i - 1][prev].copy()
+        valid = np.round(amax[i - 1][prev], 2) > 0.9
+        valid_entries = np.delete(new_order, np.where(valid == False))   # noqa: E712 (as the reference)
+        unassigned = list(set(range(n2)) - set(valid_entries))
+        j = 0
+        for ii in range(n2):
+            if not valid[ii]:
+                new_order[ii] = unassigned[j]
+                j += 1
+        order[i] = new_order
+        start = i + 1
+
+
+def apply_order(n2, nf, order, k, psi):
+    torch = torch_cuda()
+    d_order = order if hasattr(order, 'data_ptr') else to_device(np.ascontiguousarray(order, dtype=np.int32), torch)
+    k_out = torch.empty_like(k)
+    psi_out = torch.empty_like(psi) if psi is not None else None
+    check(lib().axs_apply_order(n2, nf, _ptr(d_order), _ptr(k), _ptr(psi), _ptr(k_out), _ptr(psi_out),
+                                _stream(torch)), 'axs_apply_order')
+    return k_out, psi_out

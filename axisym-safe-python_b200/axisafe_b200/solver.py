@@ -1,0 +1,203 @@
+"""Per-frequency SAFE dispersion sweep on the GPU.
+
+Host-side mirror of the reference's ``axisafe/solver.py`` ``WaveElementAxisym``
+(same constructor, ``solve(f, no_of_waves='full', central_wavespeed=0)``, result
+attributes ``k, psi_hat, w, B, T, K2_hat..., evaluated, k_ready``) with the loop body
+of solver.py:119-182 replaced by batched sm_100a kernels:
+
+    reference (per frequency, serial)                     here (all frequencies at once)
+    ---------------------------------------------------   --------------------------------
+    A(w), S = Binv A          solver.py:121-134           k_reduce (S built in-kernel)
+    scipy.linalg.eig (zgeev)  solver.py:136               k_reduce + k_hqr + k_modes
+    vec^T B vec normalisation solver.py:142               fused into k_modes
+    biorth = psi^T B psi, argmax   solver.py:157-161      k_bpsi + k_track_gemm
+    permutation bookkeeping   solver.py:159-182           axs_track_scan (host, integers)
+    reorder val / vec         solver.py:176-182           k_apply_order
+
+The frequency axis is embarrassingly parallel; under ``torch.distributed``
+(one process per GPU) every rank solves a contiguous block of frequencies plus a
+one-frequency halo for the tracking pair at the block boundary, and only the
+eigenvalue / arg-max tables are all-gathered (NCCL).  No CPU fallback.
+"""
+from __future__ import print_function
+
+import numpy as np
+import scipy.sparse as sps
+
+
+class _LazyModes(object):
+    """Device-resident ``psi_hat`` block that is copied to the host on first use."""
+
+    def __init__(self, tensor, shape, first, total):
+        self.tensor, self.shape, self.first, self.total = tensor, shape, first, total
+        self.host = None
+
+    def materialise(self):
+        if self.host is None:
+            block = self.tensor.cpu().numpy().reshape(self.shape)
+            if self.shape[0] == self.total:
+                self.host = block
+            else:
+                # sharded sweep: frequencies owned by other ranks stay zero on this rank
+                full = np.zeros((self.total,) + tuple(self.shape[1:]), complex)
+                full[self.first:self.first + self.shape[0]] = block
+                self.host = full
+        return self.host
+
+
+class WaveElementAxisym(object):
+    """Axisymmetric wave element: dispersion curves of a layered waveguide (ref solver.py:24-55)."""
+
+    def __init__(self, mesh):
+        self.Mesh = mesh
+        self.evaluated = False
+        self.k_ready = None
+        self.k = None
+        self._psi = None
+        self.er = None
+        self.K2_hat = self.K3_hat = self.KF_hat = self.KFt_hat = None
+        self.T = None
+        self.B = None
+        self.w = None
+        self.e_p = self.e_k = self.p = self.en_vel = None
+        self.propagating_indices = None
+        self.info = None                 # per-frequency count of unconverged eigenvalues
+        self.order = None                # tracked column order per frequency
+        self.local_range = None          # (first, last+1) frequencies solved by this rank
+        self.timings = {}
+
+    # psi_hat lives on the GPU until somebody reads it ------------------------------------
+    @property
+    def psi_hat(self):
+        if isinstance(self._psi, _LazyModes):
+            return self._psi.materialise()
+        return self._psi
+
+    @psi_hat.setter
+    def psi_hat(self, value):
+        self._psi = value
+
+    @property
+    def psi_hat_device(self):
+        """Tracked mode shapes of this rank's frequency block as a CUDA tensor [nf_local, 2N, 2N]."""
+        if isinstance(self._psi, _LazyModes):
+            return self._psi.tensor.view(self._psi.shape)
+        return None
+
+    def t_transform(self):
+        """K_hat = T K conj(T) / (-i) for the skew matrices (ref solver.py:59-74)."""
+        T = sps.diags(self.Mesh.Tdiag, offsets=0)
+        hat = lambda K: T.dot(K).dot(T.conj()) / (-1j)
+        self.K2_hat, self.K3_hat = hat(self.Mesh.K2), hat(self.Mesh.K3)
+        self.KF_hat, self.KFt_hat = hat(self.Mesh.KF), hat(self.Mesh.KFt)
+        self.T = T
+
+    # ------------------------------------------------------------------------- the sweep
+    def solve(self, f, no_of_waves='full', central_wavespeed=0, distributed='auto'):
+        """All wavenumbers and mode shapes at every frequency of ``f`` (ref solver.py:76-184).
+
+        ``no_of_waves`` other than 'full' (the reference's sparse shift-invert mode,
+        solver.py:137-140) is outside the accelerated path and raises.
+        ``distributed``: 'auto' shards the frequency axis over the ranks of an initialised
+        ``torch.distributed`` process group; False forces a single-GPU sweep.
+        """
+        from . import _native
+        print('Calculating dispersion curves...')
+        if no_of_waves != 'full':
+            raise NotImplementedError('only the dense "full" solution (scipy.linalg.eig path) is accelerated')
+        torch = _native.torch_cuda()
+        mesh = self.Mesh
+        ops = mesh._device_ops
+        if ops is None:
+            raise RuntimeError('Mesh.assemble_matrices(n) must be called before solve()')
+        self.t_transform()
+        n = mesh.n
+        f = np.asarray(f, dtype=float)
+        self.w = 2 * np.pi * f
+        N, n2, nf = mesh.no_of_dofs, 2 * mesh.no_of_dofs, len(f)
+        self.B = sps.bmat([[None, mesh.K6.tocsr()],
+                           [mesh.K6.tocsr(), n * mesh.K4.tocsr() + self.K3_hat.tocsr()]])
+        if n2 > _native.lib().axs_max_small_n2():
+            raise NotImplementedError('2N = %d exceeds the shared-memory eigen kernels (2N <= %d)'
+                                      % (n2, _native.lib().axs_max_small_n2()))
+
+        rank, world = 0, 1
+        if distributed in ('auto', True):
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                rank, world = dist.get_rank(), dist.get_world_size()
+        bounds = [(nf * r) // world for r in range(world + 1)]
+        lo, hi = bounds[rank], bounds[rank + 1]
+        halo = 1 if lo > 0 else 0
+        self.local_range = (lo, hi)
+
+        # host -> device: this rank's angular frequencies (with the halo point in front)
+        omega = torch.from_numpy(self.w[lo - halo:hi].copy()).cuda()
+        nloc = hi - lo + halo
+        k_nat, psi_nat, info, work = _native.eig_sweep(ops, omega, want_modes=True)
+        if nloc > 1:
+            arg, amax = _native.track_pairs(ops, psi_nat, nloc - 1, scratch=work.buf)
+        else:
+            arg = torch.empty(0, dtype=torch.int32, device='cuda')
+            amax = torch.empty(0, dtype=torch.float64, device='cuda')
+        k_loc = k_nat.view(nloc, n2)[halo:]
+        info_loc = info[halo:]
+        if world > 1:
+            k_all, arg_all, amax_all, info_all = _gather_blocks(torch, bounds, rank, n2, k_loc,
+                                                                arg.view(-1, n2), amax.view(-1, n2), info_loc)
+        else:
+            k_all, arg_all, amax_all, info_all = k_loc, arg.view(-1, n2), amax.view(-1, n2), info_loc
+        # device -> host: the small tables
+        k_host = k_all.cpu().numpy().reshape(nf, n2)
+        arg_h = arg_all.cpu().numpy().reshape(max(nf - 1, 0), n2)
+        amax_h = amax_all.cpu().numpy().reshape(max(nf - 1, 0), n2)
+        self.info = info_all.cpu().numpy()
+        if self.info.any():
+            bad = int(np.count_nonzero(self.info))
+            raise np.linalg.LinAlgError('eig algorithm (QR) did not converge at %d frequencies' % bad)
+        self.order = _native.track_scan(arg_h, amax_h, nf, n2)
+        self.k = np.take_along_axis(k_host, self.order.astype(np.int64), axis=1)
+        # reorder this rank's mode shapes on the device; they are copied out lazily
+        order_loc = np.ascontiguousarray(self.order[lo:hi])
+        psi_loc = psi_nat.view(nloc, n2 * n2)[halo:].reshape(-1)
+        _, psi_sorted = _native.apply_order(n2, hi - lo, order_loc, k_nat.view(nloc, n2)[halo:].reshape(-1),
+                                            psi_loc)
+        self._psi = _LazyModes(psi_sorted, (hi - lo, n2, n2), lo, nf)
+        self.evaluated = True
+        self.k_ready = 0
+
+
+def _gather_blocks(torch, bounds, rank, n2, k_loc, arg_loc, amax_loc, info_loc):
+    """All-gather the per-rank eigenvalue / tracking tables (NCCL); blocks are padded to equal size."""
+    import torch.distributed as dist
+    world = len(bounds) - 1
+    size = max(bounds[r + 1] - bounds[r] for r in range(world))
+    nf = bounds[-1]
+
+    dev = k_loc.device
+
+    def gather(t, rows, dtype):
+        pad = torch.zeros(size, n2, dtype=dtype, device=dev) if t.dim() == 2 else \
+            torch.zeros(size, dtype=dtype, device=dev)
+        pad[:rows] = t[:rows]
+        out = [torch.empty_like(pad) for _ in range(world)]
+        if dtype.is_complex:
+            dist.all_gather([torch.view_as_real(o) for o in out], torch.view_as_real(pad))
+        else:
+            dist.all_gather(out, pad)
+        return out
+
+    nk = bounds[rank + 1] - bounds[rank]
+    ks = gather(k_loc.reshape(nk, n2), nk, torch.complex128)
+    infos = gather(info_loc, nk, torch.int32)
+    # rank r > 0 owns pairs (lo-1, lo) .. (hi-2, hi-1) = nk pairs; rank 0 owns nk - 1 pairs
+    npairs = arg_loc.shape[0]
+    args = gather(arg_loc, npairs, torch.int32)
+    amaxs = gather(amax_loc, npairs, torch.float64)
+    k_all = torch.cat([ks[r][:bounds[r + 1] - bounds[r]] for r in range(world)])
+    info_all = torch.cat([infos[r][:bounds[r + 1] - bounds[r]] for r in range(world)])
+    counts = [(bounds[r + 1] - bounds[r]) - (1 if r == 0 else 0) for r in range(world)]
+    arg_all = torch.cat([args[r][:counts[r]] for r in range(world)])
+    amax_all = torch.cat([amaxs[r][:counts[r]] for r in range(world)])
+    assert arg_all.shape[0] == nf - 1
+    return k_all, arg_all, amax_all, info_all

@@ -1,0 +1,240 @@
+// extern "C" entry points of libaxisafe_b200.so (include/axisafe_b200.h).
+#include "common.cuh"
+#include "../../include/axisafe_b200.h"
+#include <string.h>
+#include <stdio.h>
+
+extern "C" {
+int axs_launch_element_matrices(int, const int*, const double*, const double*, const double*, cplx*, cudaStream_t);
+int axs_launch_scatter(int, const int*, const cplx*, const int*, const int*, const int*, int, int, int,
+                       cplx*, cplx*, cplx*, cplx*, cudaStream_t);
+int axs_launch_build_S(int, int, const cplx*, const cplx*, const cplx*, const cplx*, const cplx*,
+                       const double*, int, cplx*, cudaStream_t);
+int axs_launch_reduce(int, int, const cplx*, const cplx*, const cplx*, const cplx*, const cplx*,
+                      const double*, int, const cplx*, AxsWork, cudaStream_t);
+int axs_launch_hqr(int, int, cplx*, int*, AxsWork, cudaStream_t);
+int axs_launch_modes(int, int, const cplx*, const cplx*, int, const cplx*, cplx*, AxsWork, cudaStream_t);
+int axs_launch_unpack(int, int, AxsWork, cplx*, cudaStream_t);
+int axs_launch_track(int, int, const cplx*, const cplx*, const cplx*, int, cplx*, int*, double*, cudaStream_t);
+int axs_launch_apply_order(int, int, const int*, const cplx*, const cplx*, cplx*, cplx*, cudaStream_t);
+}
+
+#define AXS_ERR_TOO_LARGE 100001
+
+extern "C" int axs_version(void) { return 100; }
+
+extern "C" const char* axs_strerror(int code)
+{
+    static __thread char buf[96];
+    if (code == 0) return "success";
+    if (code == AXS_ERR_TOO_LARGE) return "problem size 2N exceeds the shared-memory eigen path (axs_max_small_n2)";
+    if (code < 0) { snprintf(buf, sizeof buf, "invalid argument %d", -code); return buf; }
+    return cudaGetErrorString((cudaError_t)code);
+}
+
+extern "C" int axs_max_small_n2(void) { return AXS_MAX_SMALL_N2; }
+
+extern "C" int axs_element_matrices(int n_elem, const int* edesc_i, const double* edesc_d,
+                                    const double* tables, const double* nodes, axs_cplx* out, void* stream)
+{
+    if (n_elem <= 0) return -1;
+    if (!edesc_i) return -2;
+    if (!edesc_d) return -3;
+    if (!tables) return -4;
+    if (!nodes) return -5;
+    if (!out) return -6;
+    return axs_launch_element_matrices(n_elem, edesc_i, edesc_d, tables, nodes, (cplx*)out, (cudaStream_t)stream);
+}
+
+extern "C" int axs_assemble_operators(int n_elem, const int* edesc_i, const axs_cplx* elem, const int* lm,
+                                      const int* lm_off, const int* tclass, int n_circ, int N, int hb,
+                                      axs_cplx* K0s, axs_cplx* Cb, axs_cplx* Mb, axs_cplx* K6d, void* stream)
+{
+    if (n_elem <= 0) return -1;
+    if (!edesc_i) return -2;
+    if (!elem) return -3;
+    if (!lm) return -4;
+    if (!lm_off) return -5;
+    if (!tclass) return -6;
+    if (n_circ < 0) return -7;
+    if (N <= 0) return -8;
+    if (hb < 0) return -9;
+    if (!K0s) return -10;
+    if (!Cb) return -11;
+    if (!Mb) return -12;
+    if (!K6d) return -13;
+    return axs_launch_scatter(n_elem, edesc_i, (const cplx*)elem, lm, lm_off, tclass, n_circ, N, hb,
+                              (cplx*)K0s, (cplx*)Cb, (cplx*)Mb, (cplx*)K6d, (cudaStream_t)stream);
+}
+
+static int check_ops(int N, int hb, const void* K0s, const void* Cb, const void* Mb, const void* K6d)
+{
+    if (N <= 0) return -1;
+    if (hb < 0) return -2;
+    if (!K0s) return -3;
+    if (!Cb) return -4;
+    if (!Mb) return -5;
+    if (!K6d) return -7;
+    return 0;
+}
+
+extern "C" int axs_build_S(int N, int hb, const axs_cplx* K0s, const axs_cplx* Cb, const axs_cplx* Mb,
+                           const axs_cplx* K1c, const axs_cplx* K6d, const double* omega, int nf,
+                           axs_cplx* S, void* stream)
+{
+    int rc = check_ops(N, hb, K0s, Cb, Mb, K6d);
+    if (rc) return rc;
+    if (!omega) return -8;
+    if (nf <= 0) return -9;
+    if (!S) return -10;
+    return axs_launch_build_S(N, hb, (const cplx*)K0s, (const cplx*)Cb, (const cplx*)Mb, (const cplx*)K1c,
+                              (const cplx*)K6d, omega, nf, (cplx*)S, (cudaStream_t)stream);
+}
+
+extern "C" long long axs_eig_worksize(int N, int nf)
+{
+    if (N <= 0 || nf <= 0) return 0;
+    return axs_work_layout(2 * N, nf, nullptr, nullptr);
+}
+
+extern "C" int axs_reduce(int N, int hb, const axs_cplx* K0s, const axs_cplx* Cb, const axs_cplx* Mb,
+                          const axs_cplx* K1c, const axs_cplx* K6d, const double* omega, int nf,
+                          const axs_cplx* S_in, void* work, long long work_bytes, void* stream)
+{
+    if (N <= 0) return -1;
+    if (2 * N > AXS_MAX_SMALL_N2) return AXS_ERR_TOO_LARGE;
+    if (!S_in) {
+        int rc = check_ops(N, hb, K0s, Cb, Mb, K6d);
+        if (rc) return rc;
+        if (!omega) return -8;
+    }
+    if (nf <= 0) return -9;
+    if (!work) return -11;
+    if (work_bytes < axs_eig_worksize(N, nf)) return -12;
+    AxsWork wk;
+    axs_work_layout(2 * N, nf, work, &wk);
+    return axs_launch_reduce(N, hb, (const cplx*)K0s, (const cplx*)Cb, (const cplx*)Mb, (const cplx*)K1c,
+                             (const cplx*)K6d, omega, nf, (const cplx*)S_in, wk, (cudaStream_t)stream);
+}
+
+extern "C" int axs_hqr(int N, int nf, axs_cplx* k, int* info, void* work, long long work_bytes, void* stream)
+{
+    if (N <= 0) return -1;
+    if (2 * N > AXS_MAX_SMALL_N2) return AXS_ERR_TOO_LARGE;
+    if (nf <= 0) return -2;
+    if (!k) return -3;
+    if (!info) return -4;
+    if (!work) return -5;
+    if (work_bytes < axs_eig_worksize(N, nf)) return -6;
+    AxsWork wk;
+    axs_work_layout(2 * N, nf, work, &wk);
+    return axs_launch_hqr(2 * N, nf, (cplx*)k, info, wk, (cudaStream_t)stream);
+}
+
+extern "C" int axs_modes(int N, int hb, const axs_cplx* Cb, const axs_cplx* K6d, int nf,
+                         const axs_cplx* k, axs_cplx* psi, void* work, long long work_bytes, void* stream)
+{
+    if (N <= 0) return -1;
+    if (2 * N > AXS_MAX_SMALL_N2) return AXS_ERR_TOO_LARGE;
+    if (hb < 0) return -2;
+    if (!Cb) return -3;
+    if (!K6d) return -4;
+    if (nf <= 0) return -5;
+    if (!k) return -6;
+    if (!psi) return -7;
+    if (!work) return -8;
+    if (work_bytes < axs_eig_worksize(N, nf)) return -9;
+    AxsWork wk;
+    axs_work_layout(2 * N, nf, work, &wk);
+    return axs_launch_modes(N, hb, (const cplx*)Cb, (const cplx*)K6d, nf, (const cplx*)k, (cplx*)psi, wk,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int axs_eig_sweep(int N, int hb, const axs_cplx* K0s, const axs_cplx* Cb, const axs_cplx* Mb,
+                             const axs_cplx* K1c, const axs_cplx* K6d, const double* omega, int nf,
+                             axs_cplx* k, axs_cplx* psi, int* info, void* work, long long work_bytes,
+                             void* stream)
+{
+    int rc = axs_reduce(N, hb, K0s, Cb, Mb, K1c, K6d, omega, nf, nullptr, work, work_bytes, stream);
+    if (rc) return rc;
+    if (!k) return -10;
+    if (!info) return -12;
+    rc = axs_hqr(N, nf, k, info, work, work_bytes, stream);
+    if (rc) return rc;
+    if (psi) rc = axs_modes(N, hb, Cb, K6d, nf, k, psi, work, work_bytes, stream);
+    return rc;
+}
+
+extern "C" int axs_get_reduction(int N, int nf, const void* work, double* scale, axs_cplx* H, void* stream)
+{
+    if (N <= 0) return -1;
+    if (nf <= 0) return -2;
+    if (!work) return -3;
+    AxsWork wk;
+    axs_work_layout(2 * N, nf, (void*)work, &wk);
+    if (scale)
+        AXS_CUDA_OK(cudaMemcpyAsync(scale, wk.scale, (size_t)nf * 2 * N * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (H) return axs_launch_unpack(2 * N, nf, wk, (cplx*)H, (cudaStream_t)stream);
+    return 0;
+}
+
+extern "C" long long axs_track_worksize(int N, int npairs)
+{
+    if (N <= 0 || npairs <= 0) return 0;
+    return (long long)(npairs + 1) * 4 * N * N * (long long)sizeof(cplx);
+}
+
+extern "C" int axs_track_pairs(int N, int hb, const axs_cplx* Cb, const axs_cplx* K6d, const axs_cplx* psi,
+                               int npairs, int* arg, double* amax, void* work, long long work_bytes,
+                               void* stream)
+{
+    if (N <= 0) return -1;
+    if (2 * N > 192) return AXS_ERR_TOO_LARGE;
+    if (hb < 0) return -2;
+    if (!Cb) return -3;
+    if (!K6d) return -4;
+    if (!psi) return -5;
+    if (npairs <= 0) return -6;
+    if (!arg) return -7;
+    if (!amax) return -8;
+    if (!work) return -9;
+    if (work_bytes < axs_track_worksize(N, npairs)) return -10;
+    return axs_launch_track(N, hb, (const cplx*)Cb, (const cplx*)K6d, (const cplx*)psi, npairs, (cplx*)work,
+                            arg, amax, (cudaStream_t)stream);
+}
+
+extern "C" int axs_track_scan(const int* h_arg, const double* h_amax, int nf, int n2, int start, int* h_order)
+{
+    if (start <= 0) {
+        for (int r = 0; r < n2; ++r) h_order[r] = r;
+        start = 1;
+    }
+    for (int i = start; i < nf; ++i) {
+        const int* a = h_arg + (long long)(i - 1) * n2;
+        const double* m = h_amax + (long long)(i - 1) * n2;
+        const int* prev = h_order + (long long)(i - 1) * n2;
+        int* cur = h_order + (long long)i * n2;
+        bool all_valid = true;
+        for (int r = 0; r < n2; ++r) {
+            const int src = prev[r];
+            cur[r] = a[src];
+            // np.round(x, 2) > 0.9   (numpy: rint(x * 100) / 100)
+            if (!(rint(m[src] * 100.0) / 100.0 > 0.9)) all_valid = false;
+        }
+        if (!all_valid) return i;      // caller applies the reference's set-based fix-up to row i
+    }
+    return nf;
+}
+
+extern "C" int axs_apply_order(int n2, int nf, const int* order, const axs_cplx* k, const axs_cplx* psi,
+                               axs_cplx* k_out, axs_cplx* psi_out, void* stream)
+{
+    if (n2 <= 0) return -1;
+    if (nf <= 0) return -2;
+    if (!order) return -3;
+    if (!k) return -4;
+    if (!k_out) return -6;
+    return axs_launch_apply_order(n2, nf, order, (const cplx*)k, (const cplx*)psi, (cplx*)k_out,
+                                  (cplx*)psi_out, (cudaStream_t)stream);
+}

@@ -1,0 +1,629 @@
+// Kernels 2 + 3 of the SAFE sweep, shared-memory ("small", 2N <= 166) instance:
+// one CTA per frequency point.  Together they replace scipy.linalg.eig (LAPACK zgeev,
+// solver.py:136) and the B-normalisation (solver.py:142).
+//
+//   k_reduce   S(w) built straight from the banded operators (never round-trips HBM as a
+//              separate batch), zgebal-style power-of-2 scaling (Gauss-Seidel sweeps on a
+//              fp32 |a_ij|^2 table in shared memory), unblocked Householder reduction to
+//              Hessenberg form with the two-sided update fused into 2 passes over the
+//              L2-resident work matrix (one read pass for w = A v, y = A^H v, one
+//              read-modify-write pass for the rank-2 update).
+//   k_hqr      explicit single-shift (Wilkinson) QR on the packed Hessenberg matrix held in
+//              shared memory: systolic column wavefront for the left rotations (one thread
+//              per column keeps its running element in a register), row-parallel right
+//              rotations; standard + Ahues-Tisseur deflation; exceptional shifts.
+//   k_modes    eigenvectors by one step of inverse iteration on the Hessenberg matrix, done
+//              as a bottom-up pivoted LU (column operations) fused with the back
+//              substitution, so the per-mode state is O(n): 32 modes per warp, state in
+//              shared memory; then back-transformation through the Householder reflectors,
+//              un-balancing, B-normalisation psi = v / sqrt(2k u^T K6 u + u^T C u) and the
+//              store in the reference psi_hat layout.
+#include "common.cuh"
+
+#define EPS_D 2.220446049250313e-16
+#define SMALL_D (2.2250738585072014e-308 / EPS_D)
+
+__device__ __forceinline__ cplx band_get(const cplx* __restrict__ B, int W, int hb, int r, int c) {
+    int d = c - r;
+    return (d < -hb || d > hb) ? mk(0, 0) : B[(long long)r * W + d + hb];
+}
+
+__device__ __forceinline__ cplx companion_entry(int N, int hb, const cplx* K0s, const cplx* Cb,
+                                                const cplx* Mb, const cplx* K1c, const cplx* K6d,
+                                                double w, int r, int c)
+{
+    const int W = 2 * hb + 1;
+    if (r >= N) return mk((r - N == c) ? 1.0 : 0.0, 0.0);
+    cplx num;
+    if (c < N) {
+        if (c - r < -hb || c - r > hb) return mk(0, 0);
+        num = band_get(Cb, W, hb, r, c);
+    } else {
+        int cc = c - N;
+        if (cc - r < -hb || cc - r > hb) return mk(0, 0);
+        num = band_get(K0s, W, hb, r, cc);
+        num = cfma(mk(-w * w, 0), band_get(Mb, W, hb, r, cc), num);
+        if (K1c) num = cfma(mk(0, w), band_get(K1c, W, hb, r, cc), num);
+    }
+    return cneg(cdiv(num, K6d[r]));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sumf(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ cplx warp_csum(cplx v) {
+    v.x = warp_sum(v.x); v.y = warp_sum(v.y);
+    return v;
+}
+
+// =========================================================================================
+// k_reduce
+// =========================================================================================
+#define RED_THREADS 256
+#define RED_WARPS (RED_THREADS / 32)
+#define RED_ROWS 6                      // ceil(AXS_MAX_SMALL_N2 / 32)
+
+__global__ void __launch_bounds__(RED_THREADS, 1)
+k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ Cb,
+         const cplx* __restrict__ Mb, const cplx* __restrict__ K1c, const cplx* __restrict__ K6d,
+         const double* __restrict__ omega, const cplx* __restrict__ S_in, AxsWork wk)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = 2 * N;
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    cplx* A = wk.A + (long long)f * n * n;
+
+    // shared layout
+    cplx* v = (cplx*)smem_raw;                       // [n]
+    cplx* wv = v + n;                                // [n]
+    cplx* y = wv + n;                                // [n]
+    cplx* wpart = y + n;                             // [RED_WARPS][n]
+    double* d = (double*)(wpart + RED_WARPS * n);    // [n]
+    double* red = d + n;                             // [RED_WARPS * 2 + 8]
+    float* d2 = (float*)(red + RED_WARPS * 2 + 8);   // [n] d^2
+    float* di2 = d2 + n;                             // [n] 1/d^2
+    float* Wn = di2 + n;                             // [n*n] |a_ij|^2 (fp32 is enough to pick powers of 2)
+
+    // ---- phase A: build S(w) (or copy the given dense matrix) --------------------------
+    const double w = omega ? omega[f] : 0.0;
+    const cplx* Sf = S_in ? S_in + (long long)f * n * n : nullptr;
+    for (int idx = tid; idx < n * n; idx += RED_THREADS) {
+        int c = idx / n, r = idx - c * n;
+        cplx val = Sf ? Sf[idx] : companion_entry(N, hb, K0s, Cb, Mb, K1c, K6d, w, r, c);
+        A[idx] = val;
+        Wn[idx] = (float)val.x * (float)val.x + (float)val.y * (float)val.y;
+    }
+    for (int i = tid; i < n; i += RED_THREADS) { d[i] = 1.0; d2[i] = 1.0f; di2[i] = 1.0f; }
+    __syncthreads();
+
+    // ---- phase B: balancing (scaling only), LAPACK zgebal loop, one warp ---------------
+    if (warp == 0) {
+        for (int sweep = 0; sweep < 40; ++sweep) {
+            bool noconv = false;
+            for (int i = 0; i < n; ++i) {
+                float cs = 0.f, rs = 0.f;
+                for (int kk = lane; kk < n; kk += 32) {
+                    cs += Wn[kk + i * n] * di2[kk];
+                    rs += Wn[i + kk * n] * d2[kk];
+                }
+                cs = warp_sumf(cs); rs = warp_sumf(rs);
+                double c = sqrt((double)cs) * d[i];
+                double r = sqrt((double)rs) / d[i];
+                if (c == 0.0 || r == 0.0) continue;
+                double g = r * 0.5, fsc = 1.0, s = c + r;
+                int guard = 0;
+                while (c < g && guard < 200) { fsc *= 2.0; c *= 2.0; r *= 0.5; g *= 0.5; ++guard; }
+                g = c * 0.5;
+                while (g >= r && guard < 400) { fsc *= 0.5; c *= 0.5; g *= 0.5; r *= 2.0; ++guard; }
+                if (c + r >= 0.95 * s) continue;
+                noconv = true;
+                if (lane == 0) {
+                    double dn = d[i] * fsc;
+                    d[i] = dn;
+                    d2[i] = (float)(dn * dn);
+                    di2[i] = (float)(1.0 / (dn * dn));
+                }
+                __syncwarp();
+            }
+            if (!noconv) break;
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * n; idx += RED_THREADS) {
+        int c = idx / n, r = idx - c * n;
+        double sc = d[c] / d[r];                    // exact: powers of two
+        cplx a = A[idx];
+        A[idx] = mk(a.x * sc, a.y * sc);
+    }
+    for (int i = tid; i < n; i += RED_THREADS) wk.scale[(long long)f * n + i] = d[i];
+    __syncthreads();
+
+    // ---- phase C: Householder reduction to Hessenberg form ------------------------------
+    for (int k = 0; k < n - 2; ++k) {
+        // reflector from column k, rows k+1..n-1  (zlarfg)
+        const cplx* colk = A + (long long)k * n;
+        double part = 0.0;
+        for (int i = k + 2 + tid; i < n; i += RED_THREADS) part += cabs2(colk[i]);
+        part = warp_sum(part);
+        if (lane == 0) red[warp] = part;
+        __syncthreads();
+        double xnorm2 = 0.0;
+        for (int q = 0; q < RED_WARPS; ++q) xnorm2 += red[q];
+        const cplx alpha = colk[k + 1];
+        cplx tau = mk(0, 0);
+        double beta = 0.0;
+        if (!(xnorm2 == 0.0 && alpha.y == 0.0)) {
+            beta = -copysign(sqrt(cabs2(alpha) + xnorm2), alpha.x);
+            tau = mk((beta - alpha.x) / beta, -alpha.y / beta);
+            cplx sc = cdiv(mk(1.0, 0.0), mk(alpha.x - beta, alpha.y));
+            for (int i = k + 1 + tid; i < n; i += RED_THREADS) {
+                cplx vi = (i == k + 1) ? mk(1.0, 0.0) : cmul(colk[i], sc);
+                v[i] = vi;
+                if (i > k + 1) A[(long long)k * n + i] = vi;      // keep the reflector for the back-transformation
+            }
+        } else {
+            if (tid == 0) wk.tau[(long long)f * n + k] = tau;
+            __syncthreads();
+            continue;                                             // uniform: nothing to do
+        }
+        __syncthreads();                                          // every thread has read alpha
+        if (tid == 0) {
+            A[(long long)k * n + k + 1] = mk(beta, 0.0);
+            wk.tau[(long long)f * n + k] = tau;
+        }
+
+        // pass 1: w = A[:, k+1:] v   and   y_j = v^H A[k+1:, j]
+        cplx wacc[RED_ROWS];
+#pragma unroll
+        for (int q = 0; q < RED_ROWS; ++q) wacc[q] = mk(0, 0);
+        for (int j = k + 1 + warp; j < n; j += RED_WARPS) {
+            const cplx* colj = A + (long long)j * n;
+            const cplx vj = v[j];
+            cplx yacc = mk(0, 0);
+#pragma unroll
+            for (int q = 0; q < RED_ROWS; ++q) {
+                int i = lane + 32 * q;
+                if (i < n) {
+                    cplx a = colj[i];
+                    wacc[q] = cfma(a, vj, wacc[q]);
+                    if (i > k) yacc = cfmac(a, v[i], yacc);       // a * conj(v_i)
+                }
+            }
+            yacc = warp_csum(yacc);
+            if (lane == 0) y[j] = yacc;
+        }
+#pragma unroll
+        for (int q = 0; q < RED_ROWS; ++q) {
+            int i = lane + 32 * q;
+            if (i < n) wpart[warp * n + i] = wacc[q];
+        }
+        __syncthreads();
+        for (int i = tid; i < n; i += RED_THREADS) {
+            cplx s = mk(0, 0);
+            for (int q = 0; q < RED_WARPS; ++q) s = cadd(s, wpart[q * n + i]);
+            wv[i] = s;
+        }
+        __syncthreads();
+        // alpha2 = v^H w[k+1:]
+        cplx ap = mk(0, 0);
+        for (int i = k + 1 + tid; i < n; i += RED_THREADS) ap = cfmac(wv[i], v[i], ap);
+        ap = warp_csum(ap);
+        if (lane == 0) { red[2 * warp] = ap.x; red[2 * warp + 1] = ap.y; }
+        __syncthreads();
+        cplx al = mk(0, 0);
+        for (int q = 0; q < RED_WARPS; ++q) { al.x += red[2 * q]; al.y += red[2 * q + 1]; }
+        const cplx tal = cmul(tau, al);
+        const cplx ctau = cconj(tau);
+        // pass 2: A[i,j] -= tau w_i conj(v_j)  (all i)  and  -= conj(tau) v_i z_j (i > k),
+        //         z_j = y_j - tau alpha conj(v_j)
+        for (int j = k + 1 + warp; j < n; j += RED_WARPS) {
+            cplx* colj = A + (long long)j * n;
+            const cplx cvj = cconj(v[j]);
+            const cplx tcv = cmul(tau, cvj);
+            const cplx zj = cmul(ctau, csub(y[j], cmul(tal, cvj)));
+#pragma unroll
+            for (int q = 0; q < RED_ROWS; ++q) {
+                int i = lane + 32 * q;
+                if (i < n) {
+                    cplx a = colj[i];
+                    a = cfms(wv[i], tcv, a);
+                    if (i > k) a = cfms(v[i], zj, a);
+                    colj[i] = a;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase D: packed copies of H -----------------------------------------------------
+    cplx* Hc = wk.Hc + (long long)f * hcol_size(n);
+    cplx* Hr = wk.Hr + (long long)f * hrow_size(n);
+    for (int idx = tid; idx < n * n; idx += RED_THREADS) {
+        int c = idx / n, r = idx - c * n;
+        if (r <= c + 1) {
+            cplx a = A[idx];
+            Hc[hcol_off(c) + r] = a;
+            Hr[hrow_off(r, n) + c - hrow_first(r)] = a;
+        }
+    }
+}
+
+static size_t reduce_smem(int n) {
+    return (size_t)(3 + RED_WARPS) * n * sizeof(cplx) + (size_t)n * sizeof(double)
+           + (RED_WARPS * 2 + 8) * sizeof(double) + (size_t)2 * n * sizeof(float)
+           + (size_t)n * n * sizeof(float);
+}
+
+// =========================================================================================
+// k_hqr
+// =========================================================================================
+__device__ __forceinline__ cplx& HC(cplx* H, int i, int j) { return H[hcol_off(j) + i]; }
+
+__device__ cplx wilkinson_shift(cplx* H, int i) {
+    // eigenvalue of the trailing 2x2 closer to H(i,i)  (zlahqr)
+    cplx t = HC(H, i, i);
+    cplx u2 = cmul(csqrt_(HC(H, i - 1, i)), csqrt_(HC(H, i, i - 1)));
+    double s = cabs1(u2);
+    if (s != 0.0) {
+        cplx x = cscale(csub(HC(H, i - 1, i - 1), t), 0.5);
+        double sx = cabs1(x);
+        s = fmax(s, sx);
+        cplx xs = cscale(x, 1.0 / s), us = cscale(u2, 1.0 / s);
+        cplx yv = cscale(csqrt_(cadd(cmul(xs, xs), cmul(us, us))), s);
+        if (sx > 0.0) {
+            cplx xn = cscale(x, 1.0 / sx);
+            if (xn.x * yv.x + xn.y * yv.y < 0.0) yv = cneg(yv);
+        }
+        t = csub(t, cmul(u2, cdiv(u2, cadd(x, yv))));
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(192, 1)
+k_hqr(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* __restrict__ info)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int hsz = hcol_size(n);
+    cplx* H = (cplx*)smem_raw;          // packed column-major Hessenberg
+    cplx* ra = H + hsz;                 // [n] rotation a_k
+    cplx* rb = ra + n;                  // [n] rotation b_k
+    __shared__ int s_l;
+    __shared__ cplx s_shift;
+
+    const cplx* Hg = Hc_all + (long long)f * hsz;
+    for (int i = tid; i < hsz; i += blockDim.x) H[i] = Hg[i];
+    cplx* eig = eig_all + (long long)f * n;
+    __syncthreads();
+
+    int u = n - 1, its = 0, failed = 0;
+    const int itmax = 60;
+    while (u >= 0) {
+        // ---- deflation scan (parallel over subdiagonal entries) -------------------------
+        if (tid == 0) s_l = 0;
+        __syncthreads();
+        if (tid >= 1 && tid <= u) {
+            const int k = tid;
+            const cplx hkk1 = HC(H, k, k - 1);
+            const double sub = cabs1(hkk1);
+            bool neg = false;
+            if (sub <= SMALL_D) neg = true;
+            else {
+                const cplx hkk = HC(H, k, k), hk1k1 = HC(H, k - 1, k - 1);
+                double tst = cabs1(hk1k1) + cabs1(hkk);
+                if (tst == 0.0) {
+                    if (k - 2 >= 0) tst += cabs1(HC(H, k - 1, k - 2));
+                    if (k + 1 <= n - 1) tst += cabs1(HC(H, k + 1, k));
+                }
+                if (sub <= EPS_D * tst) {
+                    const double up = cabs1(HC(H, k - 1, k));
+                    const double ab = fmax(sub, up), ba = fmin(sub, up);
+                    const double dd = cabs1(csub(hk1k1, hkk));
+                    const double aa = fmax(cabs1(hkk), dd), bb = fmin(cabs1(hkk), dd);
+                    const double s = aa + ab;
+                    if (ba * (ab / s) <= fmax(SMALL_D, EPS_D * (bb * (aa / s)))) neg = true;
+                }
+            }
+            if (neg) atomicMax(&s_l, k);
+        }
+        __syncthreads();
+        const int l = s_l;
+        if (l > 0 && tid == 0) HC(H, l, l - 1) = mk(0, 0);
+        if (l == u) {
+            if (tid == 0) eig[u] = HC(H, u, u);
+            --u; its = 0;
+            __syncthreads();
+            continue;
+        }
+        ++its;
+        if (its > itmax) {                 // give up on this eigenvalue: report and move on
+            if (tid == 0) eig[u] = HC(H, u, u);
+            ++failed; --u; its = 0;
+            __syncthreads();
+            continue;
+        }
+        // ---- shift ------------------------------------------------------------------------
+        if (tid == 0) {
+            cplx sg;
+            if (its % 20 == 10) sg = cadd(HC(H, l, l), mk(0.75 * fabs(HC(H, l + 1, l).x), 0));
+            else if (its % 20 == 0) sg = cadd(HC(H, u, u), mk(0.75 * fabs(HC(H, u, u - 1).x), 0));
+            else sg = wilkinson_shift(H, u);
+            s_shift = sg;
+        }
+        __syncthreads();
+        const cplx sg = s_shift;
+
+        // ---- left rotations: systolic wavefront, thread j owns column j --------------------
+        const bool mine = (tid >= l && tid <= u);
+        cplx carry = mk(0, 0);
+        if (mine) {
+            carry = HC(H, l, tid);
+            if (tid == l) carry = csub(carry, sg);
+        }
+        for (int k = l; k < u; ++k) {
+            if (tid == k) {
+                const cplx g = HC(H, k + 1, k);
+                const double r2 = cabs2(carry) + cabs2(g);
+                cplx a = mk(1, 0), b = mk(0, 0);
+                double r = 0.0;
+                if (r2 > 0.0) {
+                    const double ir = rsqrt(r2);
+                    a = mk(carry.x * ir, -carry.y * ir);
+                    b = mk(g.x * ir, -g.y * ir);
+                    r = r2 * ir;
+                }
+                ra[k] = a; rb[k] = b;
+                HC(H, k, k) = mk(r, 0.0);
+            }
+            __syncthreads();
+            if (tid > k && tid <= u) {
+                const cplx a = ra[k], b = rb[k];
+                cplx low = HC(H, k + 1, tid);
+                if (tid == k + 1) low = csub(low, sg);
+                // [top; bot] = [[a, b], [-conj(b), conj(a)]] [carry; low]
+                const cplx top = cfma(a, carry, cmul(b, low));
+                const cplx bot = csub(cmulc(low, a), cmulc(carry, b));
+                HC(H, k, tid) = top;
+                carry = bot;
+            }
+        }
+        if (tid == u) HC(H, u, u) = carry;
+        __syncthreads();
+
+        // ---- right rotations: thread i owns row i -----------------------------------------
+        if (mine) {
+            const int i = tid;
+            int kk = (i - 1 >= l) ? i - 1 : l;
+            cplx left = (i - 1 >= l) ? mk(0, 0) : HC(H, i, l);
+            for (int k = kk; k < u; ++k) {
+                const cplx right = HC(H, i, k + 1);
+                const cplx a = ra[k], b = rb[k];
+                // [newl, newr] = [left, right] * [[conj(a), -b], [conj(b), a]]
+                cplx newl = cfmac(left, a, cmulc(right, b));
+                const cplx newr = csub(cmul(right, a), cmul(left, b));
+                if (k == i) newl = cadd(newl, sg);
+                HC(H, i, k) = newl;
+                left = newr;
+            }
+            if (i == u) left = cadd(left, sg);
+            HC(H, i, u) = left;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) info[f] = failed;
+}
+
+static size_t hqr_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(cplx); }
+
+// =========================================================================================
+// k_modes
+// =========================================================================================
+// grid = (ceil(n/32), nf), block = 32: one warp = 32 modes of one frequency.
+__global__ void __launch_bounds__(32, 1)
+k_modes(int N, int hb, const cplx* __restrict__ Cb, const cplx* __restrict__ K6d,
+        const cplx* __restrict__ eig_all, cplx* __restrict__ psi_all, AxsWork wk)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = 2 * N;
+    const int f = blockIdx.y, lane = threadIdx.x;
+    const int mode = blockIdx.x * 32 + lane;
+    const bool live = mode < n;
+
+    cplx* mul = (cplx*)smem_raw;              // [n][32]
+    cplx* z = mul + (size_t)n * 32;           // [n][32]   (becomes x, then v)
+    cplx* rowbuf = z + (size_t)n * 32;        // [2][n]
+    unsigned char* swp = (unsigned char*)(rowbuf + 2 * n);   // [n][32]
+
+    const cplx* Hr = wk.Hr + (long long)f * hrow_size(n);
+    const cplx* A = wk.A + (long long)f * n * n;
+    const cplx* tau = wk.tau + (long long)f * n;
+    const double* dsc = wk.scale + (long long)f * n;
+    const cplx lam = eig_all[(long long)f * n + (live ? mode : n - 1)];
+
+    // ||H||_1-ish magnitude for the pivot floor: use the largest |entry| of the first row
+    // block instead of a full norm (cheap, same order of magnitude after balancing)
+    double hmax = 0.0;
+    for (int i = lane; i < hrow_size(n); i += 32) hmax = fmax(hmax, cabs1(Hr[i]));
+    for (int o = 16; o > 0; o >>= 1) hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+    const double tiny = fmax(EPS_D * hmax, SMALL_D);
+
+    // stage row n-1
+    {
+        const int k = n - 1, first = hrow_first(k), off = hrow_off(k, n);
+        for (int c = first + lane; c < n; c += 32) rowbuf[c] = Hr[off + c - first];
+    }
+    __syncwarp();
+    for (int k = n - 1; k >= 0; --k) {
+        cplx* row = rowbuf + (size_t)((n - 1 - k) & 1) * n;
+        cplx* nxt = rowbuf + (size_t)((n - k) & 1) * n;
+        // prefetch row k-1 into registers (stored after the compute loop)
+        cplx pre[RED_ROWS];
+        int pfirst = 0;
+        if (k > 0) {
+            pfirst = hrow_first(k - 1);
+            const int off = hrow_off(k - 1, n);
+#pragma unroll
+            for (int q = 0; q < RED_ROWS; ++q) {
+                int c = pfirst + lane + 32 * q;
+                if (c < n) pre[q] = Hr[off + c - pfirst];
+            }
+        }
+        cplx carry = row[n - 1];
+        if (k == n - 1) carry = csub(carry, lam);
+        cplx acc = mk(1.0, 0.0);
+        for (int j = n - 2; j >= k; --j) {
+            cplx a = row[j];
+            if (j == k) a = csub(a, lam);
+            const bool s = swp[j * 32 + lane] != 0;
+            cplx a2 = s ? carry : a;
+            const cplx c2 = s ? a : carry;
+            a2 = cfms(mul[j * 32 + lane], c2, a2);
+            acc = cfms(c2, z[(j + 1) * 32 + lane], acc);
+            carry = a2;
+        }
+        cplx rkk;
+        if (k > 0) {
+            const cplx a = row[k - 1];
+            const bool s = cabs1(a) > cabs1(carry);
+            const cplx a2 = s ? carry : a;
+            cplx c2 = s ? a : carry;
+            if (cabs1(c2) < tiny) c2 = mk(tiny, 0.0);
+            mul[(k - 1) * 32 + lane] = cdiv(a2, c2);
+            swp[(k - 1) * 32 + lane] = s ? 1 : 0;
+            rkk = c2;
+        } else {
+            rkk = carry;
+            if (cabs1(rkk) < tiny) rkk = mk(tiny, 0.0);
+        }
+        z[k * 32 + lane] = cdiv(acc, rkk);
+        if (k > 0) {
+#pragma unroll
+            for (int q = 0; q < RED_ROWS; ++q) {
+                int c = pfirst + lane + 32 * q;
+                if (c < n) nxt[c] = pre[q];
+            }
+        }
+        __syncwarp();
+    }
+    // x = W z : apply the column operations to the vector, first to last
+    {
+        cplx xj = z[lane];
+        for (int j = 0; j < n - 1; ++j) {
+            cplx xj1 = cfms(mul[j * 32 + lane], xj, z[(j + 1) * 32 + lane]);
+            if (swp[j * 32 + lane]) { z[j * 32 + lane] = xj1; /* xj stays */ }
+            else { z[j * 32 + lane] = xj; xj = xj1; }
+        }
+        z[(n - 1) * 32 + lane] = xj;
+    }
+    // scale to unit max-norm (keeps the later dot products in range)
+    {
+        double mx = 0.0;
+        for (int i = 0; i < n; ++i) mx = fmax(mx, cabs1(z[i * 32 + lane]));
+        const double inv = mx > 0.0 ? 1.0 / mx : 1.0;
+        for (int i = 0; i < n; ++i) z[i * 32 + lane] = cscale(z[i * 32 + lane], inv);
+    }
+    // back-transformation  y = H_0 H_1 ... H_{n-3} x ,  H_k = I - tau_k v_k v_k^H
+    cplx* vb = rowbuf;                       // reuse: [2][n]
+    for (int kk = n - 3; kk >= 0; --kk) {
+        cplx* vv = vb + (size_t)(kk & 1) * n;
+        for (int i = kk + 2 + lane; i < n; i += 32) vv[i] = A[(long long)kk * n + i];
+        __syncwarp();
+        const cplx t = tau[kk];
+        if (t.x == 0.0 && t.y == 0.0) continue;
+        cplx dot = z[(kk + 1) * 32 + lane];
+        for (int i = kk + 2; i < n; ++i) dot = cfmac(z[i * 32 + lane], vv[i], dot);   // conj(v_i) x_i
+        const cplx td = cmul(t, dot);
+        z[(kk + 1) * 32 + lane] = csub(z[(kk + 1) * 32 + lane], td);
+        for (int i = kk + 2; i < n; ++i) z[i * 32 + lane] = cfms(td, vv[i], z[i * 32 + lane]);
+    }
+    // undo the balancing, B-normalise on the lower half u = v[N:], write psi
+    for (int i = 0; i < n; ++i) z[i * 32 + lane] = cscale(z[i * 32 + lane], dsc[i]);
+    {
+        double mx = 0.0;
+        for (int i = N; i < n; ++i) mx = fmax(mx, cabs1(z[i * 32 + lane]));
+        const double inv = mx > 0.0 ? 1.0 / mx : 1.0;
+        for (int i = N; i < n; ++i) z[i * 32 + lane] = cscale(z[i * 32 + lane], inv);
+    }
+    const int W = 2 * hb + 1;
+    cplx s6 = mk(0, 0), sc = mk(0, 0);
+    for (int r = 0; r < N; ++r) {
+        const cplx ur = z[(N + r) * 32 + lane];
+        s6 = cfma(cmul(ur, ur), K6d[r], s6);
+        cplx cu = mk(0, 0);
+        const int c0 = max(0, r - hb), c1 = min(N - 1, r + hb);
+        for (int c = c0; c <= c1; ++c) cu = cfma(Cb[(long long)r * W + c - r + hb], z[(N + c) * 32 + lane], cu);
+        sc = cfma(ur, cu, sc);
+    }
+    const cplx nrm = cadd(cscale(cmul(lam, s6), 2.0), sc);
+    const cplx inv = cdiv(mk(1.0, 0.0), csqrt_(nrm));
+    if (live) {
+        cplx* psi = psi_all + (long long)f * n * n;
+        for (int r = 0; r < N; ++r) {
+            const cplx u = cmul(z[(N + r) * 32 + lane], inv);
+            psi[(long long)(N + r) * n + mode] = u;
+            psi[(long long)r * n + mode] = cmul(lam, u);
+        }
+    }
+}
+
+static size_t modes_smem(int n) {
+    return (size_t)2 * n * 32 * sizeof(cplx) + (size_t)2 * n * sizeof(cplx) + (size_t)n * 32;
+}
+
+// =========================================================================================
+// debug accessor: dense H and scale factors out of the workspace
+// =========================================================================================
+__global__ void k_unpack_H(int n, AxsWork wk, cplx* __restrict__ Hd)
+{
+    const int f = blockIdx.y;
+    const cplx* Hc = wk.Hc + (long long)f * hcol_size(n);
+    cplx* out = Hd + (long long)f * n * n;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += gridDim.x * blockDim.x) {
+        int c = idx / n, r = idx - c * n;
+        out[idx] = (r <= c + 1) ? Hc[hcol_off(c) + r] : mk(0, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------ launchers
+extern "C" int axs_launch_reduce(int N, int hb, const cplx* K0s, const cplx* Cb, const cplx* Mb,
+                                 const cplx* K1c, const cplx* K6d, const double* omega, int nf,
+                                 const cplx* S_in, AxsWork wk, cudaStream_t st)
+{
+    const int n = 2 * N;
+    size_t smem = reduce_smem(n);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_reduce<<<nf, RED_THREADS, smem, st>>>(N, hb, K0s, Cb, Mb, K1c, K6d, omega, S_in, wk);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, cudaStream_t st)
+{
+    size_t smem = hqr_smem(n);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int threads = ((n + 31) / 32) * 32;
+    if (threads < 64) threads = 64;
+    k_hqr<<<nf, threads, smem, st>>>(n, wk.Hc, eig, info);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int axs_launch_modes(int N, int hb, const cplx* Cb, const cplx* K6d, int nf,
+                                const cplx* eig, cplx* psi, AxsWork wk, cudaStream_t st)
+{
+    const int n = 2 * N;
+    size_t smem = modes_smem(n);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_modes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_modes<<<dim3((n + 31) / 32, nf), 32, smem, st>>>(N, hb, Cb, K6d, eig, psi, wk);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int axs_launch_unpack(int n, int nf, AxsWork wk, cplx* Hd, cudaStream_t st)
+{
+    k_unpack_H<<<dim3(32, nf), 256, 0, st>>>(n, wk, Hd);
+    return (int)cudaGetLastError();
+}

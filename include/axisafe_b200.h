@@ -1,0 +1,143 @@
+/*
+ * axisafe_b200.h - C ABI of the B200-native SAFE dispersion sweep.
+ *
+ * The reference (michalkalkowski/axisym-safe-python) is pure Python and has no
+ * FFI; its boundary for this path is the Python call surface
+ *     Mesh.assemble_matrices(n)            axisafe/mesh.py:290
+ *     WaveElementAxisym.solve(f)           axisafe/solver.py:76
+ * The entry points below are what a ctypes binding inside those two methods
+ * calls (see INTEGRATION.md for the stub).  Each one cites the reference code
+ * it replaces.
+ *
+ * Conventions
+ *   - every pointer is a CUDA DEVICE pointer unless the name starts with h_;
+ *   - complex numbers are interleaved (re, im) IEEE doubles ("cplx");
+ *   - the caller allocates every buffer, nothing is retained between calls;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *     calls are asynchronous on that stream;
+ *   - return 0 on success, -k if argument k (1-based) is invalid, >0 = CUDA
+ *     error code (cudaError_t) - decode either with axs_strerror().
+ *   - per-frequency convergence failures do not fail the call: info[f] holds
+ *     the number of eigenvalues that did not converge (0 = ok).
+ */
+#ifndef AXISAFE_B200_H
+#define AXISAFE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { double re, im; } axs_cplx;
+
+int         axs_version(void);
+const char* axs_strerror(int code);
+
+/* Largest dense problem size (2N) handled by the shared-memory eigen kernels. */
+int axs_max_small_n2(void);
+
+/* ---- kernel 1a: Gauss-Lobatto quadrature of the element matrices ------------------
+ * Replaces the per-element Python loops Element.calculate_matrices()
+ *   elements.py:148-229 (SLAX6) :293-330 (ALAX6) :447-586 (SLAX6_core)
+ *   :683-737 (ALAX6_core) :810-894 (SLAX6_PML) :962-1007 (ALAX6_PML)
+ * driven from mesh.py:488-489.  One warp per element.
+ *   edesc_i[e][8] : kind(0 solid,1 fluid), family(0 GLL,1 GLJ), pml(0 none,1 exp,2 poly),
+ *                   m (nodes), table_off, nodes_off, out_off, reserved
+ *   edesc_d[e][12]: lambda, mu, eta, rho, c_p^2, pml_start, pml_thk, pml_a, pml_b, 0,0,0
+ *   tables        : per element at table_off: ksi[m], w[m], D[m*m] (D[a*m+q] = l_a'(ksi_q))
+ *   nodes         : radii of the element's nodes at nodes_off
+ *   out           : per element at out_off (in cplx): 10 matrices nd x nd row-major,
+ *                   nd = 3m (solid) or m (fluid), order K1 K2 K3 K4 K5 K6 KF1 KF2 KF3 M
+ *                   (full size, axis conditions NOT applied; M of non-PML solids carries the
+ *                   reference's per-point complex64 rounding, elements.py:99,:217,:397,:529)
+ */
+int axs_element_matrices(int n_elem, const int* edesc_i, const double* edesc_d,
+                         const double* tables, const double* nodes,
+                         axs_cplx* out, void* stream);
+
+/* ---- kernel 1b: scatter-assembly + T-transform into banded operators --------------
+ * Replaces mesh.py:518-619 (scatter), solver.py:59-74 (T-transform) and the static
+ * parts of solver.py:115-133:
+ *     K0s = K1 + n^2 K5 + n K2hat      Cb = n K4 + K3hat     Mb = M    K6d = diag(K6)
+ * with Khat[r,c] = i T_r conj(T_c) K[r,c].  Banded row-major, width W = 2*hb+1,
+ * entry (r,c) at [r*W + c-r+hb].  Output buffers must be zeroed by the caller.
+ *   lm[e] at lm_off[e] : local->global DOF map over the FULL element DOFs, -1 = dropped
+ *   tclass[N]          : 0 if Tdiag = 1, 1 if Tdiag = i
+ */
+int axs_assemble_operators(int n_elem, const int* edesc_i, const axs_cplx* elem,
+                           const int* lm, const int* lm_off, const int* tclass,
+                           int n_circ, int N, int hb,
+                           axs_cplx* K0s, axs_cplx* Cb, axs_cplx* Mb, axs_cplx* K6d,
+                           void* stream);
+
+/* ---- kernel 1c: frequency-batched dense companion matrix ---------------------------
+ * Replaces solver.py:115-134 (B, Binv = spla.inv(B), A(w), S = Binv A):
+ *     S(w) = [[-K6^-1 Cb, -K6^-1 (K0s - w^2 Mb + i w K1c)], [I, 0]]
+ * S is [nf][n2][n2] column-major, n2 = 2N.  K1c is banded like K0s (may be NULL).
+ */
+int axs_build_S(int N, int hb, const axs_cplx* K0s, const axs_cplx* Cb, const axs_cplx* Mb,
+                const axs_cplx* K1c, const axs_cplx* K6d, const double* omega, int nf,
+                axs_cplx* S, void* stream);
+
+/* ---- kernels 2+3: batched dense eigen-solve of S(w) --------------------------------
+ * Replaces val, vec = scipy.linalg.eig(S) (LAPACK zgeev, solver.py:136) and the
+ * B-normalisation solver.py:142:
+ *   stage A  build S(w), zgebal-style scaling, Householder Hessenberg   (axs_reduce)
+ *   stage B  explicit single-shift QR on the Hessenberg matrix          (axs_hqr)
+ *   stage C  inverse iteration, back-transformation, psi = v/sqrt(v^T B v) (axs_modes)
+ * axs_eig_sweep runs A, B, C for nf frequencies.  Workspace: axs_eig_worksize() bytes.
+ *   k    [nf][n2]          eigenvalues in the solver's native order
+ *   psi  [nf][n2][n2]      row-major, psi[f][r][j] = component r of mode j, rows [0,N) = k*u,
+ *                          rows [N,2N) = u (same layout as psi_hat, solver.py:106-109);
+ *                          may be NULL (eigenvalues only)
+ *   info [nf]
+ */
+long long axs_eig_worksize(int N, int nf);
+int axs_eig_sweep(int N, int hb, const axs_cplx* K0s, const axs_cplx* Cb, const axs_cplx* Mb,
+                  const axs_cplx* K1c, const axs_cplx* K6d, const double* omega, int nf,
+                  axs_cplx* k, axs_cplx* psi, int* info, void* work, long long work_bytes,
+                  void* stream);
+
+/* The three stages separately (used by the parity tests; same workspace layout).
+ * axs_reduce accepts an explicit dense input S_in ([nf][n2][n2] column-major) instead of
+ * the banded operators when S_in != NULL.  */
+int axs_reduce(int N, int hb, const axs_cplx* K0s, const axs_cplx* Cb, const axs_cplx* Mb,
+               const axs_cplx* K1c, const axs_cplx* K6d, const double* omega, int nf,
+               const axs_cplx* S_in, void* work, long long work_bytes, void* stream);
+int axs_hqr(int N, int nf, axs_cplx* k, int* info, void* work, long long work_bytes, void* stream);
+int axs_modes(int N, int hb, const axs_cplx* Cb, const axs_cplx* K6d, int nf,
+              const axs_cplx* k, axs_cplx* psi, void* work, long long work_bytes, void* stream);
+/* Debug/parity accessors into the workspace: copy scale factors D [nf][n2] (double) and the
+ * Hessenberg matrix H [nf][n2][n2] (dense column-major, zeros below the subdiagonal). */
+int axs_get_reduction(int N, int nf, const void* work, double* scale, axs_cplx* H, void* stream);
+
+/* ---- mode tracking ------------------------------------------------------------------
+ * Replaces the two dense products of solver.py:157 and the row arg-max of :159-161:
+ * for pair p (p = 0..npairs-1) with psi_prev = psi[p], psi_cur = psi[p+1],
+ *     P = psi_prev^T (B psi_cur),  B = [[0, K6], [K6, Cb]]
+ *     arg[p][a] = argmax_b |P[a,b]|,   amax[p][a] = max_b |P[a,b]|
+ * psi holds npairs+1 consecutive frequencies in the solver's native (unsorted) order; the
+ * workspace (axs_track_worksize bytes) receives Y = B psi.  The sequential permutation scan (solver.py:159-182) is
+ * axs_track_scan (host).
+ */
+long long axs_track_worksize(int N, int npairs);
+int axs_track_pairs(int N, int hb, const axs_cplx* Cb, const axs_cplx* K6d,
+                    const axs_cplx* psi, int npairs, int* arg, double* amax,
+                    void* work, long long work_bytes, void* stream);
+
+/* HOST function.  Composes the per-pair arg-max tables into the reference's column order:
+ * order[0] = identity (or h_order[start-1] when start > 0), order[i][r] =
+ * arg[i-1][order[i-1][r]]; rows with round(amax,2) <= 0.9 need the reference's Python-set
+ * fix-up: the function stops there and returns that frequency index (caller fills
+ * order[i] and resumes with start = i+1).  Returns nf when done.  */
+int axs_track_scan(const int* h_arg, const double* h_amax, int nf, int n2, int start,
+                   int* h_order);
+
+/* Column gather after tracking: k_out[f][c] = k[f][order[f][c]],
+ * psi_out[f][r][c] = psi[f][r][order[f][c]]  (solver.py:176-182). psi/psi_out may be NULL. */
+int axs_apply_order(int n2, int nf, const int* order, const axs_cplx* k, const axs_cplx* psi,
+                    axs_cplx* k_out, axs_cplx* psi_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,117 @@
+"""TEST INFRASTRUCTURE ONLY - generate tests/golden/*.npz from the UNMODIFIED reference.
+
+Run inside the build container (needs /root/reference):
+    OPENBLAS_NUM_THREADS=1 python oracle/make_golden.py
+Every fixture holds, for one case of ``axisafe_b200.cases``:
+  * mesh book-keeping (node radii, IEN, LM, Tdiag, element types, dof domains),
+  * the reference's global matrices K1..K6, M, KF, KFt, KFz, K1_coupling (COO triplets),
+  * per-element matrices of every element (K_1..K_6, K_F, K_Ft, K_Fz, M, H vectors),
+  * S(w) at three frequencies rebuilt exactly as solver.py:115-134,
+  * untracked scipy.linalg.eig eigenvalues of those S,
+  * the reference's tracked ``k`` for the whole sweep and ``psi_hat`` (lower halves) at the
+    same three frequencies,
+  * energy_ratio / k_propagating outputs.
+The case inputs are taken from axisafe_b200.cases; the script asserts that the reference's own
+suggest_PML_parameters gives the same layer definitions.
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.linalg as la
+import scipy.sparse as sps
+import scipy.sparse.linalg as spla
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'axisym-safe-python_b200'))
+
+from oracle import refshim  # noqa: E402
+
+CASES = [('pipe_soil_pml', 0, {}), ('free_steel_pipe', 0, {'nf': 60}), ('free_steel_pipe', 1, {'nf': 60}),
+         ('aristegui', 0, {'nf': 40}), ('muggleton_submerged', 0, {'nf': 40}),
+         ('muggleton_buried', 0, {'nf': 25}), ('gravenkamp', 0, {'nf': 30}), ('gravenkamp', 1, {'nf': 30}),
+         ('gravenkamp', 2, {'nf': 30}), ('nguyen', 0, {'nf': 30}), ('nguyen', 1, {'nf': 30}),
+         ('pipe_soil_pml', 1, {'nf': 20})]
+KPROP = {'pipe_soil_pml': (15, 0.935), 'aristegui': (100, 0.9), 'muggleton_submerged': (15, 0.8),
+         'muggleton_buried': (15, 0.935), 'gravenkamp': (350, 0.97), 'nguyen': (200, 0.9)}
+
+
+def coo(m):
+    m = m.tocoo()
+    return np.array(m.row, np.int32), np.array(m.col, np.int32), np.array(m.data)
+
+
+def reference_S(solver, mesh, n, w):
+    """S(w) exactly as the reference builds it (solver.py:115-134)."""
+    B = sps.bmat([[None, mesh.K6.tocsr()], [mesh.K6.tocsr(), n * mesh.K4.tocsr() + solver.K3_hat.tocsr()]])
+    Binv = spla.inv(B.tocsc())
+    low = mesh.K1.tocsr() + n ** 2 * mesh.K5.tocsr() + n * solver.K2_hat.tocsr() - w ** 2 * mesh.M.tocsr()
+    if mesh.is_coupled:
+        low = low + 1j * w * mesh.K1_coupling.tocsr()
+    A = sps.bmat([[mesh.K6.tocsr(), None], [None, -low]])
+    return Binv.dot(A.tocsc()).toarray()
+
+
+def main():
+    ref = refshim.load()
+    from axisafe_b200 import cases
+    outdir = os.path.join(ROOT, 'tests', 'golden')
+    os.makedirs(outdir, exist_ok=True)
+    for name, n, kw in CASES:
+        c = cases.ALL[name](n=n, **kw)
+        with refshim.quiet():
+            mesh = ref.mesh.Mesh()
+            mesh.create(c['sets'], c['fmax'], PML=c['PML'], PML_props=c['PML_props'])
+            mesh.assemble_matrices(n)
+            sol = ref.solver.WaveElementAxisym(mesh)
+            sol.solve(c['f'])
+            er = kready = pidx = None
+            if c['PML'] != 0:
+                sol.energy_ratio()
+                sol.k_propagating(*KPROP[name])
+                er, kready, pidx = sol.er, sol.k_ready, sol.propagating_indices
+        N = mesh.no_of_dofs
+        pick = sorted({0, len(c['f']) // 3, len(c['f']) - 1})
+        S = np.array([reference_S(sol, mesh, n, sol.w[i]) for i in pick])
+        with refshim.quiet():
+            ev = np.array([la.eig(s)[0] for s in S])
+        data = dict(f=c['f'], n=n, N=N, pick=np.array(pick), S=S, eig_untracked=ev, k=sol.k,
+                    psi_low=np.array([sol.psi_hat[i][N:] for i in pick]),
+                    Tdiag=np.array(mesh.Tdiag), node_r=np.array([mesh.glob_nodes[k][0] for k in sorted(mesh.glob_nodes)]),
+                    solid_dofs=np.array(mesh.dof_domains['solid'], np.int32),
+                    fluid_dofs=np.array(mesh.dof_domains['fluid'], np.int32),
+                    etypes=np.array([mesh.element_types[e] for e in sorted(mesh.IEN)]),
+                    is_coupled=bool(mesh.is_coupled))
+        for e in sorted(mesh.IEN):
+            data['IEN_%d' % e] = np.array(mesh.IEN[e], np.int32)
+            data['LM_%d' % e] = np.array(mesh.LM[e], np.int32)
+            el = mesh.elements[e]
+            for attr in ('K_1', 'K_2', 'K_3', 'K_4', 'K_5', 'K_6', 'K_F', 'K_Ft', 'K_Fz', 'M',
+                         'Hs0', 'Hs1', 'Hf0', 'Hf1'):
+                if getattr(el, attr, None) is not None and (len(mesh.IEN) <= 4):
+                    data['el%d_%s' % (e, attr)] = np.asarray(getattr(el, attr))
+        for g in ('K1', 'K2', 'K3', 'K4', 'K5', 'K6', 'M', 'KF', 'KFt', 'KFz', 'K1_coupling'):
+            m = getattr(mesh, g)
+            if m is not None:
+                r, cc, d = coo(m.tocsr())     # duplicates summed, like every consumer does
+                data['G_%s_r' % g], data['G_%s_c' % g], data['G_%s_d' % g] = r, cc, d
+        if er is not None:
+            data['er'], data['k_ready'], data['prop_idx'] = er, kready, np.array(pidx)
+            data['kprop_args'] = np.array(KPROP[name])
+        path = os.path.join(outdir, '%s_n%d.npz' % (name, n))
+        np.savez_compressed(path, **data)
+        print('%-28s N=%3d nf=%3d  %6.0f KB' % (os.path.basename(path), N, len(c['f']), os.path.getsize(path) / 1024))
+        # the case builder must reproduce the reference's own PML suggestion
+    with refshim.quiet():
+        mine = __import__('axisafe_b200.mesh', fromlist=['x']).suggest_PML_parameters
+        lam = ref.misc.young2lame(156e9, 0.2)
+        args = (0.11, 3, list(lam) + [7800, 0.0], list(ref.misc.cLcS2lame(200, 100, 1500)) + [1500, 0.], 1e3, 20e3)
+        a, b = ref.mesh.suggest_PML_parameters(*args, att=1), mine(*args, att=1)
+    assert all(x == y for x, y in zip(a, b)), (a, b)
+    np.savez(os.path.join(outdir, 'suggest_pml.npz'), args_scalar=np.array([0.11, 3, 1e3, 20e3]), out=np.array(a))
+    print('suggest_PML_parameters: identical', a)
+
+
+if __name__ == '__main__':
+    main()

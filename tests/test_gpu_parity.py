@@ -1,0 +1,268 @@
+"""GPU parity tests: every CUDA stage against the CPU oracle / the reference fixtures.
+
+All calls go through the C-ABI of libaxisafe_b200.so (ctypes, axisafe_b200/_native.py).
+"""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, CASE_IDS, load_golden, golden_dense, make_case
+from oracle import safe_oracle as so
+from test_oracle_golden import tracked_agreement
+
+pytestmark = pytest.mark.gpu
+
+
+def _mesh(c):
+    import axisafe_b200 as ax
+    m = ax.mesh.Mesh()
+    m.create(c['sets'], c['fmax'], PML=c['PML'], PML_props=c['PML_props'])
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.assemble_matrices(c['n'])
+    return m
+
+
+# ------------------------------------------------------------------ kernel 1a (elements)
+@pytest.mark.parametrize('n', [0, 1, 2])
+@pytest.mark.parametrize('m', [4, 5, 9, 14, 23])
+def test_element_matrices_vs_oracle(m, n):
+    """Every element class x circumferential order x element order (SURVEY.md test pyramid ii)."""
+    import axisafe_b200 as ax
+    E = ax.elements
+    lam, mu = ax.misc.young2lame(156e9, 0.2)
+    solid, water, pml = [lam, mu, 7800, 0.03], [2.25e9, 1000, 0], [0.1, 0.01, 6 + 7j]
+    gll = 0.1 + 0.01 * (so.gll(m)[0] + 1) / 2
+    glj = 0.1 * (so.glj(m)[0] + 1) / 2
+    glj[0] = 0.0
+    cases = [('SLAX6', E.SLAX6(gll, n), gll, solid, None), ('ALAX6', E.ALAX6(gll, n), gll, water, None),
+             ('SLAX6_core', E.SLAX6_core(glj, n), glj, solid, None),
+             ('ALAX6_core', E.ALAX6_core(glj, n), glj, water, None),
+             ('SLAX6_PML', E.SLAX6_PML(gll, n, pml), gll, solid, pml),
+             ('ALAX6_PML', E.ALAX6_PML(gll, n, pml), gll, water, pml)]
+    for name, el, nodes, mat, p in cases:
+        el.add_properties(mat)
+        el.calculate_matrices()
+        ref = so.element_matrices(name, nodes, mat, n, p)
+        for key in ('K_1', 'K_2', 'K_3', 'K_4', 'K_5', 'K_6', 'K_F', 'K_Ft', 'K_Fz', 'M'):
+            a, b = np.asarray(getattr(el, key)), ref[key]
+            assert a.shape == b.shape, (name, key, a.shape, b.shape)
+            assert np.abs(a - b).max() <= 2e-12 * max(np.abs(b).max(), 1e-300), (name, key)
+        if name in ('SLAX6', 'SLAX6_core'):
+            assert el.M.dtype == np.complex64
+            assert np.array_equal(np.diag(el.M), np.diag(ref['M'])), name   # fp32 rounding, bit exact
+        for key in ('Hs0', 'Hs1', 'Hf0', 'Hf1'):
+            if key in ref:
+                assert np.allclose(getattr(el, key), ref[key], rtol=1e-15, atol=0), (name, key)
+
+
+# --------------------------------------------------- kernels 1a+1b against the reference
+@pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
+def test_global_matrices_vs_reference(name, n, kw):
+    g = load_golden(name, n)
+    c = make_case(name, n, kw)
+    m = _mesh(c)
+    for key in ('K1', 'K2', 'K3', 'K4', 'K5', 'K6', 'M', 'KF', 'KFt', 'KFz'):
+        ref = golden_dense(g, key)
+        got = getattr(m, key).toarray()
+        assert np.abs(got - ref).max() <= 2e-12 * max(np.abs(ref).max(), 1e-300), key
+    ref_M = golden_dense(g, 'M')
+    sol = [d for d in g['solid_dofs'] if ref_M[d, d] == np.complex64(ref_M[d, d])]
+    assert np.array_equal(m.M.toarray()[sol, sol], ref_M[sol, sol])       # complex64 quirk, exact
+    if bool(g['is_coupled']):
+        ref = golden_dense(g, 'K1_coupling')
+        assert np.abs(m.K1_coupling.toarray() - ref).max() <= 1e-12 * np.abs(ref).max()
+    # banded device operators against the oracle's dense ones
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), n)
+    op = so.operators(G, n)
+    ops = m._device_ops
+    for dev, key in ((ops.K0s, 'K0s'), (ops.Cb, 'C'), (ops.Mb, 'M')):
+        got = ops.band_to_dense(dev)
+        assert np.abs(got - op[key]).max() <= 2e-12 * max(np.abs(op[key]).max(), 1e-300), key
+    assert np.abs(ops.K6d.cpu().numpy() - np.diag(op['K6'])).max() <= 2e-12 * np.abs(op['K6']).max()
+    if ops.K1c is not None:
+        assert np.abs(ops.band_to_dense(ops.K1c) - op['K1c']).max() <= 1e-12 * np.abs(op['K1c']).max()
+
+
+@pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
+def test_S_batch_vs_reference(name, n, kw):
+    import torch
+    from axisafe_b200 import _native
+    g = load_golden(name, n)
+    c = make_case(name, n, kw)
+    m = _mesh(c)
+    w = 2 * np.pi * c['f'][g['pick']]
+    S = _native.build_S(m._device_ops, torch.from_numpy(w).cuda())
+    n2 = 2 * m.no_of_dofs
+    S = S.cpu().numpy().reshape(len(w), n2, n2).transpose(0, 2, 1)       # column-major -> [r, c]
+    for j in range(len(w)):
+        assert np.abs(S[j] - g['S'][j]).max() <= 1e-11 * np.abs(g['S'][j]).max()
+
+
+# --------------------------------------------------------------------- kernels 2 + 3
+def _stages(name, n, kw, S=None):
+    import torch
+    from axisafe_b200 import _native
+    g = load_golden(name, n)
+    c = make_case(name, n, kw)
+    m = _mesh(c)
+    ops = m._device_ops
+    N = m.no_of_dofs
+    pick = g['pick']
+    w = 2 * np.pi * c['f'][pick]
+    omega = torch.from_numpy(w).cuda()
+    return g, c, m, ops, N, pick, omega, _native
+
+
+@pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
+def test_reduction_is_a_similarity(name, n, kw):
+    """Balancing uses exact powers of two and H = Q^H D^-1 S D Q keeps the spectrum."""
+    import torch
+    g, c, m, ops, N, pick, omega, nat = _stages(name, n, kw)
+    Sd = torch.from_numpy(np.ascontiguousarray(g['S'].transpose(0, 2, 1))).cuda().reshape(-1)
+    work = nat.reduce_dense(Sd, N, len(pick))
+    scale, H = nat.get_reduction(N, len(pick), work)
+    assert np.all(np.log2(scale) == np.round(np.log2(scale)))
+    for j in range(len(pick)):
+        assert np.abs(np.tril(H[j], -2)).max() == 0.0
+        Sb = g['S'][j] * scale[j][None, :] / scale[j][:, None]
+        # Frobenius norm is invariant under the unitary similarity
+        assert abs(np.linalg.norm(H[j]) - np.linalg.norm(Sb)) <= 1e-12 * np.linalg.norm(Sb)
+        assert np.linalg.norm(Sb) <= np.linalg.norm(g['S'][j])           # balancing never hurts
+        ev = np.linalg.eigvals(H[j])
+        tol = so.eig_tolerance(g['S'][j], g['eig_untracked'][j])
+        perm, _ = so.match_eigenvalues(g['eig_untracked'][j], ev)
+        assert np.all(np.abs(g['eig_untracked'][j] - ev[perm]) <= tol)
+
+
+@pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
+def test_eigenvalues_vs_reference_zgeev(name, n, kw):
+    """Solver-level (bijective) parity: GPU eigenvalues of the reference's own S against
+    the untracked scipy.linalg.eig values stored in the fixture; bar 1e-8 relative
+    (conditioning-aware allowance, see so.eig_tolerance)."""
+    import torch
+    g, c, m, ops, N, pick, omega, nat = _stages(name, n, kw)
+    Sd = torch.from_numpy(np.ascontiguousarray(g['S'].transpose(0, 2, 1))).cuda().reshape(-1)
+    work = nat.reduce_dense(Sd, N, len(pick))
+    k, info = nat.hqr(N, len(pick), work)
+    assert not info.cpu().numpy().any()
+    k = k.cpu().numpy().reshape(len(pick), 2 * N)
+    plain = 0
+    for j in range(len(pick)):
+        ref = g['eig_untracked'][j]
+        perm, _ = so.match_eigenvalues(ref, k[j])
+        err = np.abs(ref - k[j][perm])
+        assert np.all(err <= so.eig_tolerance(g['S'][j], ref)), (j, (err / np.abs(ref)).max())
+        plain += int(np.sum(err > 1e-8 * np.abs(ref)))
+    if name in ('pipe_soil_pml', 'free_steel_pipe'):
+        assert plain == 0                     # flagship: plain 1e-8 bar, no allowance needed
+
+
+@pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
+def test_modes_vs_reference(name, n, kw):
+    """Mode shapes (lower half, B-normalised, sign fixed) within 1e-6 of the reference psi_hat."""
+    g, c, m, ops, N, pick, omega, nat = _stages(name, n, kw)
+    k, psi, info, work = nat.eig_sweep(ops, omega)
+    n2 = 2 * N
+    k = k.cpu().numpy().reshape(len(pick), n2)
+    psi = psi.cpu().numpy().reshape(len(pick), n2, n2)
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), n)
+    B = so.operators(G, n)['B']
+    loose = 0
+    for j, i in enumerate(pick):
+        # structure: upper half = k * lower half, psi^T B psi = I
+        assert np.abs(psi[j][:N] - k[j] * psi[j][N:]).max() <= 1e-13 * np.abs(psi[j][:N]).max()
+        gram = psi[j].T @ B @ psi[j]
+        assert np.abs(np.diag(gram) - 1).max() < 1e-9
+        # reference (tracked) columns: match by eigenvalue
+        kref, uref = g['k'][i], g['psi_low'][j]
+        for col in range(n2):
+            cand = np.argmin(np.abs(k[j] - kref[col]))
+            err = so.mode_shape_error(uref[:, [col]], psi[j][N:, [cand]])[0]
+            gap = np.sort(np.abs(kref - kref[col]))[1] / abs(kref[col])
+            if err > 1e-6:
+                # only near-degenerate or ill-conditioned modes may exceed the bar: the reference's
+                # own vectors move by this much under 1e-15 perturbations of S
+                assert gap < 1e-3 or i == 0, (i, col, err, gap)
+                loose += 1
+    assert loose <= 0.08 * n2 * len(pick)
+
+
+# ------------------------------------------------------------------------- tracking
+def test_track_pairs_vs_numpy():
+    import torch
+    name, n, kw = GOLDEN_CASES[0]
+    g, c, m, ops, N, pick, omega, nat = _stages(name, n, kw)
+    w = 2 * np.pi * c['f'][:6]
+    k, psi, info, work = nat.eig_sweep(ops, torch.from_numpy(w).cuda())
+    arg, amax = nat.track_pairs(ops, psi, 5)
+    n2 = 2 * N
+    arg = arg.cpu().numpy().reshape(5, n2)
+    amax = amax.cpu().numpy().reshape(5, n2)
+    psi = psi.cpu().numpy().reshape(6, n2, n2)
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), n)
+    B = so.operators(G, n)['B']
+    for p in range(5):
+        P = np.abs(psi[p].T @ B @ psi[p + 1])
+        assert np.array_equal(arg[p], P.argmax(axis=1))
+        assert np.abs(amax[p] - P.max(axis=1)).max() < 1e-9
+
+
+# ----------------------------------------------------------------------------- API level
+@pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
+def test_solve_api_vs_reference(name, n, kw):
+    """Drop-in call sequence Mesh.create / assemble_matrices / WaveElementAxisym.solve."""
+    import axisafe_b200 as ax
+    g = load_golden(name, n)
+    c = make_case(name, n, kw)
+    m = _mesh(c)
+    sol = ax.solver.WaveElementAxisym(m)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sol.solve(c['f'])
+    assert sol.k.shape == g['k'].shape and sol.k.dtype == np.complex128
+    assert sol.evaluated and sol.k_ready == 0
+    # every eigenvalue of the reference's tracked table is present (level 2)
+    N = m.no_of_dofs
+    for j, i in enumerate(g['pick']):
+        ref = g['eig_untracked'][j]
+        perm, _ = so.match_eigenvalues(ref, sol.k[i])
+        assert np.all(np.abs(ref - sol.k[i][perm]) <= so.eig_tolerance(g['S'][j], ref))
+    cover, frac = tracked_agreement(g['k'], sol.k)
+    assert cover < 1e-5
+    assert frac > 0.8, frac
+    psi = sol.psi_hat
+    assert psi.shape == (len(c['f']), 2 * N, 2 * N)
+    # tracked mode shapes belong to the tracked eigenvalues
+    i = len(c['f']) // 2
+    Gm = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), n)
+    op = so.operators(Gm, n)
+    S = so.S_matrix(op, 2 * np.pi * c['f'][i])
+    res = np.linalg.norm(S @ psi[i] - psi[i] * sol.k[i], axis=0) / (np.linalg.norm(psi[i], axis=0) * np.abs(sol.k[i]))
+    assert np.median(res) < 1e-10
+
+
+def test_full_size_sweep_properties():
+    """cfg1 at the north-star size (2000 points): size-independent properties."""
+    import axisafe_b200 as ax
+    c = make_case('pipe_soil_pml', 0, {'nf': 2000})
+    m = _mesh(c)
+    sol = ax.solver.WaveElementAxisym(m)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sol.solve(c['f'])
+    assert sol.k.shape == (2000, 126) and np.isfinite(sol.k).all()
+    # trace identity: sum of eigenvalues = trace of S = -sum_r C[r,r]/K6[r], frequency independent
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), 0)
+    op = so.operators(G, 0)
+    tr = -np.sum(np.diag(op['C']) / np.diag(op['K6']))
+    assert np.abs(sol.k.sum(axis=1) - tr).max() < 1e-6 * np.abs(sol.k).sum(axis=1).max()
+    # the sweep solved on a sub-grid gives the same spectra (frequencies are independent)
+    sub = ax.solver.WaveElementAxisym(m)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sub.solve(c['f'][::400])
+    for a, i in enumerate(range(0, 2000, 400)):
+        assert so.match_eigenvalues(sub.k[a], sol.k[i])[1] < 1e-12
+    # spot check against the CPU oracle
+    for i in (0, 777, 1999):
+        val, _ = so.eig_normalised(op, 2 * np.pi * c['f'][i])
+        assert so.match_eigenvalues(val, sol.k[i])[1] < 1e-8

@@ -1,0 +1,162 @@
+"""CPU tests: tables, host mesh logic, C-ABI surface, tracking scan (no GPU needed)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, CASE_IDS, ROOT, load_golden, make_case
+
+
+def test_quadrature_invariants():
+    from axisafe_b200 import shape_functions as sf
+    for m in (4, 5, 9, 11, 14, 23, 30):
+        for build, lag in ((sf.build_GLL_quadrature, sf.lagrange_poly),
+                           (sf.build_GLJ_quadrature, sf.lagrange_GLJ)):
+            ksi, w = build(m)
+            assert abs(w.sum() - 2.0) < 1e-13            # SURVEY.md section 4 invariant
+            assert ksi[0] == -1.0 and abs(ksi[-1] - 1.0) < 1e-15 and np.all(np.diff(ksi) > 0)
+            N, D = lag(ksi)
+            assert np.array_equal(N, np.eye(m))
+            assert np.abs(D.sum(axis=0)).max() < 1e-11   # derivative of the constant function
+            assert np.abs(D.T @ ksi - 1).max() < 1e-11   # derivative of x
+    # GLL integrates polynomials of degree 2m-3 exactly, GLJ integrates (1+x) x^k for k <= 2Q-4
+    ksi, w = sf.build_GLL_quadrature(7)
+    assert abs(w @ ksi ** 10 - 2 / 11) < 1e-14
+    ksi, w = sf.build_GLJ_quadrature(7)
+    assert abs(w @ ksi ** 10 - (2 / 11)) < 1e-14          # int (1+x) x^10 = 2/11
+
+
+def test_tables_match_oracle():
+    from axisafe_b200 import shape_functions as sf
+    from oracle import safe_oracle as so
+    for m in (5, 9, 14, 30):
+        k1, w1 = sf.build_GLL_quadrature(m)
+        k2, w2 = so.gll(m)
+        assert np.abs(k1 - k2).max() < 1e-15 and np.abs(w1 - w2).max() < 1e-15
+        assert np.abs(sf.lagrange_poly(k1)[1] - so.dmatrix(k2)).max() < 1e-12 * m * m
+        k1, w1 = sf.build_GLJ_quadrature(m)
+        k2, w2 = so.glj(m)
+        assert np.abs(k1 - k2).max() < 1e-15 and np.abs(w1 - w2).max() < 1e-14
+
+
+def test_misc_and_pml_suggestion():
+    import axisafe_b200 as ax
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'suggest_pml.npz'))
+    lam = ax.misc.young2lame(156e9, 0.2)
+    soil = list(ax.misc.cLcS2lame(200, 100, 1500)) + [1500, 0.]
+    got = ax.mesh.suggest_PML_parameters(0.11, 3, list(lam) + [7800, 0.0], soil, 1e3, 20e3, att=1)
+    assert np.array_equal(np.array(got, float), g['out'])     # bit-identical to the reference
+    assert ax.misc.G_nu2lame(2.0, 0.25) == (2.0, 2.0)
+    E, nu = ax.misc.bulkvel2E(5960., 3260., 7932.)
+    l1, m1 = ax.misc.young2lame(E, nu)
+    l2, m2 = ax.misc.cLcS2lame(5960., 3260., 7932.)
+    assert abs(l1 - l2) < 1e-6 * l2 and abs(m1 - m2) < 1e-6 * m2
+    assert np.allclose(ax.misc.young2C(E, nu), ax.misc.lame2C(l1, m1))
+
+
+@pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
+def test_mesh_numbering_matches_reference(name, n, kw):
+    """Mesh.create + DOF numbering (mesh.py:153-288, :337-464) against the reference's own output."""
+    import axisafe_b200 as ax
+    g = load_golden(name, n)
+    c = make_case(name, n, kw)
+    m = ax.mesh.Mesh()
+    m.create(c['sets'], c['fmax'], PML=c['PML'], PML_props=c['PML_props'])
+    m.n = n
+    m._instantiate_elements(n)
+    m._number_dofs()
+    assert m.no_of_dofs == int(g['N'])
+    assert np.array_equal(np.array([m.glob_nodes[k][0] for k in sorted(m.glob_nodes)]), g['node_r'])
+    for e in sorted(m.IEN):
+        assert np.array_equal(np.array(m.IEN[e]), g['IEN_%d' % e])
+        assert np.array_equal(np.array(m.LM[e]), g['LM_%d' % e])
+    assert np.array_equal(np.array(m.Tdiag), g['Tdiag'])
+    assert list(g['etypes']) == [m.element_types[e] for e in sorted(m.IEN)]
+    assert np.array_equal(np.array(m.dof_domains['solid'], np.int32), g['solid_dofs'])
+    assert np.array_equal(np.array(m.dof_domains['fluid'], np.int32), g['fluid_dofs'])
+    assert m.is_coupled == bool(g['is_coupled'])
+
+
+def test_lubricated_coupling_numbering():
+    """Radial-only contact duplicates the interface node and shares u_r (mesh.py:219-225, :377-404)."""
+    import axisafe_b200 as ax
+    steel = list(ax.misc.cLcS2lame(5960, 3260, 7932)) + [7932, 0.0]
+    sets = [['a', 0.1, 0.01, steel, 'SLAX6', 3], ['b', 0.11, 0.01, steel, 'SLAX6', 3]]
+    m = ax.mesh.Mesh()
+    m.create(sets, 1e4, lubricated_coupling=('a', 'b'))
+    assert m.uncoupled_nodes == [[4, 5]] and m.IEN[2][0] == 5
+    m.n = 0
+    m._instantiate_elements(0)
+    m._number_dofs()
+    assert m.ID[5] == [m.ID[4][0], 12, 13] and m.no_of_dofs == 23
+    assert m.Tdiag[12:14] == [1j, 1j]
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    import axisafe_b200 as ax
+    c = make_case('free_steel_pipe', 0, {'nf': 4})
+    m = ax.mesh.Mesh()
+    m.create(c['sets'], c['fmax'])
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m.assemble_matrices(0)
+
+
+def test_cabi_exports_every_declared_symbol(built_lib):
+    """The shared library loads and exports exactly what include/axisafe_b200.h declares."""
+    import ctypes
+    from axisafe_b200 import _native
+    header = open(os.path.join(ROOT, 'include', 'axisafe_b200.h')).read()
+    declared = sorted(set(re.findall(r'\b(axs_[a-z_0-9S]+)\s*\(', header)))
+    assert declared, 'no declarations parsed'
+    handle = ctypes.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert sorted(_native.EXPORTED) == declared
+    L = _native.lib()
+    assert L.axs_version() >= 100
+    assert L.axs_strerror(0) == b'success' and b'invalid argument 3' in L.axs_strerror(-3)
+    assert L.axs_max_small_n2() >= 166
+    assert L.axs_eig_worksize(63, 10) > 10 * 126 * 126 * 16
+    # argument checking happens before any CUDA call
+    assert L.axs_element_matrices(0, None, None, None, None, None, None) == -1
+    assert L.axs_hqr(63, 4, None, None, None, 0, None) == -3
+    assert L.axs_reduce(200, 1, None, None, None, None, None, None, 1, None, None, 0, None) == 100001
+
+
+def _python_scan(arg, amax, n2):
+    """Straight restatement of solver.py:159-175 on the arg-max tables."""
+    nf = len(arg) + 1
+    order = np.zeros([nf, n2], int)
+    order[0] = np.arange(n2)
+    for i in range(1, nf):
+        prev = order[i - 1]
+        new_order = arg[i - 1][prev].copy()
+        valid = np.round(amax[i - 1][prev], 2) > 0.9
+        valid_entries = np.delete(new_order, np.where(valid == False))  # noqa: E712
+        if not valid.all():
+            unassigned = list(set(range(n2)) - set(valid_entries))
+            j = 0
+            for ii in range(n2):
+                if not valid[ii]:
+                    new_order[ii] = unassigned[j]
+                    j += 1
+        order[i] = new_order
+    return order
+
+
+def test_track_scan_matches_python_semantics(built_lib):
+    from axisafe_b200 import _native
+    rng = np.random.default_rng(1)
+    n2, nf = 30, 200
+    arg = np.array([rng.permutation(n2) for _ in range(nf - 1)], dtype=np.int32)
+    amax = 0.95 + 0.05 * rng.random([nf - 1, n2])
+    for i in rng.choice(nf - 1, 12, replace=False):          # some weak / duplicated matches
+        rows = rng.choice(n2, 3, replace=False)
+        amax[i, rows] = rng.choice([0.2, 0.9049, 0.905, 0.9051, 0.89])
+        arg[i, rows[0]] = arg[i, rows[1]]
+    got = _native.track_scan(arg, amax, nf, n2)
+    assert np.array_equal(got, _python_scan(arg, amax, n2))

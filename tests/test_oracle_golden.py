@@ -1,0 +1,73 @@
+"""Pins oracle/safe_oracle.py (the CPU checker) to fixtures generated from the reference."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, CASE_IDS, load_golden, golden_dense, make_case
+from oracle import safe_oracle as so
+
+
+@pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
+def test_oracle_assembly_vs_reference(name, n, kw):
+    g = load_golden(name, n)
+    c = make_case(name, n, kw)
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), n)
+    assert G['num']['N'] == int(g['N'])
+    assert np.array_equal(G['num']['Tdiag'], g['Tdiag'])
+    for key in ('K1', 'K2', 'K3', 'K4', 'K5', 'K6', 'M', 'KF', 'KFt', 'KFz'):
+        ref = golden_dense(g, key)
+        assert np.abs(G[key] - ref).max() <= 2e-12 * max(np.abs(ref).max(), 1e-300), key
+    # the complex64 mass accumulation of solid non-PML elements is reproduced bit for bit
+    ref_M = golden_dense(g, 'M')
+    sol = g['solid_dofs']
+    exact32 = [d for d in sol if ref_M[d, d] == np.complex64(ref_M[d, d])]
+    assert np.array_equal(G['M'][exact32, exact32], ref_M[exact32, exact32])
+    if bool(g['is_coupled']):
+        ref = golden_dense(g, 'K1_coupling')
+        assert np.abs(G['K1c'] - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
+def test_oracle_S_and_eigenvalues_vs_reference(name, n, kw):
+    g = load_golden(name, n)
+    c = make_case(name, n, kw)
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), n)
+    op = so.operators(G, n)
+    for j, i in enumerate(g['pick']):
+        w = 2 * np.pi * c['f'][i]
+        S = so.S_matrix(op, w)
+        assert np.abs(S - g['S'][j]).max() <= 1e-11 * np.abs(g['S'][j]).max()
+        val, _ = so.eig_normalised(op, w)
+        tol = so.eig_tolerance(g['S'][j], g['eig_untracked'][j])
+        perm, _ = so.match_eigenvalues(g['eig_untracked'][j], val)
+        assert np.all(np.abs(g['eig_untracked'][j] - val[perm]) <= tol)
+
+
+def tracked_agreement(k_ref, k_new, tol=1e-6):
+    """Match columns at the first frequency, then report (coverage error, fraction of equal entries).
+
+    The reference's tracked array is NOT a function of the physics alone: whenever two or more
+    modes fall below the 0.9 biorthogonality threshold at the same frequency they are re-seated in
+    CPython set-iteration order of the solver's *native* column indices (solver.py:163-175), i.e.
+    in LAPACK's deflation order.  Any other eigen-solver (or LAPACK on a 1e-14-perturbed S) seats
+    them differently, so column-wise equality holds for most, not all, entries.
+    """
+    perm, _ = so.match_eigenvalues(k_ref[0], k_new[0])
+    rel = np.abs(k_new[:, perm] - k_ref) / np.maximum(np.abs(k_ref), 1e-300)
+    cover = 0.0
+    for i in range(len(k_ref)):
+        d = np.abs(k_ref[i][:, None] - k_new[i][None, :]).min(axis=1) / np.abs(k_ref[i])
+        cover = max(cover, d.max())
+    return cover, float((rel < tol).mean())
+
+
+@pytest.mark.parametrize('name,n,kw', [GOLDEN_CASES[0], GOLDEN_CASES[2], GOLDEN_CASES[7]],
+                         ids=[CASE_IDS[0], CASE_IDS[2], CASE_IDS[7]])
+def test_oracle_tracked_sweep_vs_reference(name, n, kw):
+    """Full restated sweep (eig + normalisation + tracking) against the reference's tracked k."""
+    g = load_golden(name, n)
+    c = make_case(name, n, kw)
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), n)
+    k, psi = so.solve(G, n, c['f'])
+    cover, frac = tracked_agreement(g['k'], k)
+    assert cover < 1e-6          # every tracked reference eigenvalue is present
+    assert frac > 0.85           # and sits in the same tracked column almost everywhere
