@@ -87,6 +87,21 @@ def to_device(array, torch, dtype=None):
     return t.cuda()
 
 
+def download(tensor):
+    """Device -> host copy into freshly allocated PINNED memory; returns a NumPy view of it.
+
+    torch's caching host allocator recycles the pinned block once the array is dropped, so
+    repeated sweeps do not pay cudaHostAlloc again (psi_hat is 0.5 GB at 2000 x 126 x 126).
+    """
+    torch = torch_cuda()
+    if tensor.numel() * tensor.element_size() < (1 << 20):
+        return tensor.cpu().numpy()
+    stage = torch.empty(tensor.numel(), dtype=tensor.dtype, pin_memory=True)
+    stage.copy_(tensor.reshape(-1), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return stage.numpy()
+
+
 # ------------------------------------------------------------------------ kernel 1a
 class DeviceElements(object):
     """Element matrices resident on the GPU + the tables needed to scatter them."""

@@ -34,7 +34,8 @@ class _LazyModes(object):
 
     def materialise(self):
         if self.host is None:
-            block = self.tensor.cpu().numpy().reshape(self.shape)
+            from . import _native
+            block = _native.download(self.tensor).reshape(self.shape)
             if self.shape[0] == self.total:
                 self.host = block
             else:
@@ -63,6 +64,7 @@ class WaveElementAxisym(object):
         self.propagating_indices = None
         self.info = None                 # per-frequency count of unconverged eigenvalues
         self.order = None                # tracked column order per frequency
+        self.k_native = None             # eigenvalues before tracking (native order)
         self.local_range = None          # (first, last+1) frequencies solved by this rank
         self.timings = {}
 
@@ -155,6 +157,7 @@ class WaveElementAxisym(object):
         if self.info.any():
             bad = int(np.count_nonzero(self.info))
             raise np.linalg.LinAlgError('eig algorithm (QR) did not converge at %d frequencies' % bad)
+        self.k_native = k_host           # untracked spectra, solver's native column order
         self.order = _native.track_scan(arg_h, amax_h, nf, n2)
         self.k = np.take_along_axis(k_host, self.order.astype(np.int64), axis=1)
         # reorder this rank's mode shapes on the device; they are copied out lazily
