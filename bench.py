@@ -102,7 +102,7 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_baseline(points_per_core=12):
+def cpu_baseline(points_per_core=100):
     """Oracle (port of the reference algorithm: S build + zgeev + normalisation + tracking) on
     all host cores: P single-threaded worker processes, contiguous frequency chunks
     ('tuned' variant - zgeev does not scale with BLAS threads at 2N=126)."""
@@ -295,7 +295,7 @@ def reference_arm(args):
         return
     rates = []
     for _ in range(args.warmup + args.steps):
-        rates.append(cpu_baseline(points_per_core=8))
+        rates.append(cpu_baseline(points_per_core=60))
     timed = rates[args.warmup:]
     value = float(np.mean([r['value'] for r in timed]))
     base = dict(timed[-1], value=value)
