@@ -19,6 +19,7 @@
 //              un-balancing, B-normalisation psi = v / sqrt(2k u^T K6 u + u^T C u) and the
 //              store in the reference psi_hat layout.
 #include "common.cuh"
+#include <stdlib.h>
 
 #define EPS_D 2.220446049250313e-16
 #define SMALL_D (2.2250738585072014e-308 / EPS_D)
@@ -68,7 +69,7 @@ __device__ __forceinline__ cplx warp_csum(cplx v) {
 #define RED_WARPS (RED_THREADS / 32)
 #define RED_ROWS 6                      // ceil(AXS_MAX_SMALL_N2 / 32)
 
-__global__ void __launch_bounds__(RED_THREADS, 1)
+__global__ void __launch_bounds__(RED_THREADS, 2)
 k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ Cb,
          const cplx* __restrict__ Mb, const cplx* __restrict__ K1c, const cplx* __restrict__ K6d,
          const double* __restrict__ omega, const cplx* __restrict__ S_in, AxsWork wk)
@@ -178,25 +179,38 @@ k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ C
             wk.tau[(long long)f * n + k] = tau;
         }
 
-        // pass 1: w = A[:, k+1:] v   and   y_j = v^H A[k+1:, j]
+        // pass 1: w = A[:, k+1:] v   and   y_j = v^H A[k+1:, j].  Two columns per warp iteration
+        // with all loads issued first (the matrix lives in L2: latency, not bandwidth, is the cost).
         cplx wacc[RED_ROWS];
 #pragma unroll
         for (int q = 0; q < RED_ROWS; ++q) wacc[q] = mk(0, 0);
-        for (int j = k + 1 + warp; j < n; j += RED_WARPS) {
-            const cplx* colj = A + (long long)j * n;
-            const cplx vj = v[j];
-            cplx yacc = mk(0, 0);
+        for (int j = k + 1 + 2 * warp; j < n; j += 2 * RED_WARPS) {
+            const bool two = (j + 1 < n);
+            const cplx* col0 = A + (long long)j * n;
+            const cplx* col1 = col0 + n;
+            cplx e0[RED_ROWS], e1[RED_ROWS];
 #pragma unroll
             for (int q = 0; q < RED_ROWS; ++q) {
-                int i = lane + 32 * q;
+                const int i = lane + 32 * q;
+                e0[q] = (i < n) ? col0[i] : mk(0, 0);
+                e1[q] = (i < n && two) ? col1[i] : mk(0, 0);
+            }
+            const cplx v0 = v[j], v1 = two ? v[j + 1] : mk(0, 0);
+            cplx y0 = mk(0, 0), y1 = mk(0, 0);
+#pragma unroll
+            for (int q = 0; q < RED_ROWS; ++q) {
+                const int i = lane + 32 * q;
                 if (i < n) {
-                    cplx a = colj[i];
-                    wacc[q] = cfma(a, vj, wacc[q]);
-                    if (i > k) yacc = cfmac(a, v[i], yacc);       // a * conj(v_i)
+                    wacc[q] = cfma(e0[q], v0, cfma(e1[q], v1, wacc[q]));
+                    if (i > k) {
+                        const cplx vi = v[i];
+                        y0 = cfmac(e0[q], vi, y0);
+                        y1 = cfmac(e1[q], vi, y1);
+                    }
                 }
             }
-            yacc = warp_csum(yacc);
-            if (lane == 0) y[j] = yacc;
+            y0 = warp_csum(y0); y1 = warp_csum(y1);
+            if (lane == 0) { y[j] = y0; if (two) y[j + 1] = y1; }
         }
 #pragma unroll
         for (int q = 0; q < RED_ROWS; ++q) {
@@ -222,19 +236,30 @@ k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ C
         const cplx ctau = cconj(tau);
         // pass 2: A[i,j] -= tau w_i conj(v_j)  (all i)  and  -= conj(tau) v_i z_j (i > k),
         //         z_j = y_j - tau alpha conj(v_j)
-        for (int j = k + 1 + warp; j < n; j += RED_WARPS) {
-            cplx* colj = A + (long long)j * n;
-            const cplx cvj = cconj(v[j]);
-            const cplx tcv = cmul(tau, cvj);
-            const cplx zj = cmul(ctau, csub(y[j], cmul(tal, cvj)));
+        for (int j = k + 1 + 2 * warp; j < n; j += 2 * RED_WARPS) {
+            const bool two = (j + 1 < n);
+            cplx* col0 = A + (long long)j * n;
+            cplx* col1 = col0 + n;
+            cplx e0[RED_ROWS], e1[RED_ROWS];
 #pragma unroll
             for (int q = 0; q < RED_ROWS; ++q) {
-                int i = lane + 32 * q;
+                const int i = lane + 32 * q;
+                e0[q] = (i < n) ? col0[i] : mk(0, 0);
+                e1[q] = (i < n && two) ? col1[i] : mk(0, 0);
+            }
+            const cplx cv0 = cconj(v[j]), cv1 = two ? cconj(v[j + 1]) : mk(0, 0);
+            const cplx t0 = cmul(tau, cv0), t1 = cmul(tau, cv1);
+            const cplx z0 = cmul(ctau, csub(y[j], cmul(tal, cv0)));
+            const cplx z1 = two ? cmul(ctau, csub(y[j + 1], cmul(tal, cv1))) : mk(0, 0);
+#pragma unroll
+            for (int q = 0; q < RED_ROWS; ++q) {
+                const int i = lane + 32 * q;
                 if (i < n) {
-                    cplx a = colj[i];
-                    a = cfms(wv[i], tcv, a);
-                    if (i > k) a = cfms(v[i], zj, a);
-                    colj[i] = a;
+                    const cplx wi = wv[i];
+                    cplx a0 = cfms(wi, t0, e0[q]), a1 = cfms(wi, t1, e1[q]);
+                    if (i > k) { const cplx vi = v[i]; a0 = cfms(vi, z0, a0); a1 = cfms(vi, z1, a1); }
+                    col0[i] = a0;
+                    if (two) col1[i] = a1;
                 }
             }
         }
@@ -285,9 +310,11 @@ __device__ cplx wilkinson_shift(cplx* H, int i) {
     return t;
 }
 
+__device__ long long g_dbg[16];
 __global__ void __launch_bounds__(192, 1)
 k_hqr(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* __restrict__ info)
 {
+    long long c_pro = 0, c_left = 0, c_right = 0, n_sw = 0, n_rot = 0, c_t0 = clock64(), c_a;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.x, tid = threadIdx.x;
     const int hsz = hcol_size(n);
@@ -305,6 +332,7 @@ k_hqr(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* _
     int u = n - 1, its = 0, failed = 0;
     const int itmax = 60;
     while (u >= 0) {
+        c_a = clock64();
         // ---- deflation scan (parallel over subdiagonal entries) -------------------------
         if (tid == 0) s_l = 0;
         __syncthreads();
@@ -358,6 +386,7 @@ k_hqr(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* _
         }
         __syncthreads();
         const cplx sg = s_shift;
+        c_pro += clock64() - c_a; c_a = clock64(); n_sw++; n_rot += u - l;
 
         // ---- left rotations: systolic wavefront, thread j owns column j --------------------
         const bool mine = (tid >= l && tid <= u);
@@ -395,6 +424,7 @@ k_hqr(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* _
         }
         if (tid == u) HC(H, u, u) = carry;
         __syncthreads();
+        c_left += clock64() - c_a; c_a = clock64();
 
         // ---- right rotations: thread i owns row i -----------------------------------------
         if (mine) {
@@ -415,11 +445,415 @@ k_hqr(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* _
             HC(H, i, u) = left;
         }
         __syncthreads();
+        c_right += clock64() - c_a;
     }
     if (tid == 0) info[f] = failed;
+    if (tid == 0 && f == 0) { g_dbg[0] = clock64() - c_t0; g_dbg[1] = c_pro; g_dbg[2] = c_left; g_dbg[3] = c_right; g_dbg[4] = n_sw; g_dbg[5] = n_rot; }
 }
 
+extern "C" void axs_debug_counters(long long* out) { cudaMemcpyFromSymbol(out, g_dbg, sizeof(long long) * 16); }
+
 static size_t hqr_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(cplx); }
+
+// -----------------------------------------------------------------------------------------
+// k_hqr_mb: implicit single-shift QR with several bulges chased concurrently ("small-bulge
+// multishift").  A batch takes nb shifts (eigenvalues of the trailing 2x2 diagonal blocks of
+// the active window, closed form), starts bulge b at macro step b*MB_D and advances every
+// live bulge by one position per macro step:
+//     phase R  rows (k, k+1) <- G_k rows,   one thread per (bulge, column)
+//     phase C  cols (k, k+1) <- cols G_k^H, one thread per (bulge, row); the thread that owns
+//              row k+1 also updates row k+2 (the new bulge) and generates G_{k+1}
+// Left and right multiplications commute and bulges are >= 3 rows apart, so the result is
+// exactly that of nb successive single-shift sweeps, at ~1/nb of the barrier-bound latency.
+#define MB_MAX 8
+#define MB_D 3
+#define MB_THREADS 512
+#define MB_ITEMS 3                      // ceil(MB_MAX * (AXS_MAX_SMALL_N2 + 1) / MB_THREADS)
+
+__device__ __forceinline__ void make_rot(cplx x, cplx y, cplx& a, cplx& b, double& r) {
+    const double r2 = cabs2(x) + cabs2(y);
+    if (r2 > 0.0) {
+        const double ir = rsqrt(r2);
+        a = mk(x.x * ir, -x.y * ir);
+        b = mk(y.x * ir, -y.y * ir);
+        r = r2 * ir;
+    } else { a = mk(1, 0); b = mk(0, 0); r = 0.0; }
+}
+
+__global__ void __launch_bounds__(MB_THREADS, 1)
+k_hqr_mb(int n, int bmax, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* __restrict__ info)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int hsz = hcol_size(n);
+    cplx* H = (cplx*)smem_raw;
+    __shared__ int s_l;
+    __shared__ cplx s_shift[MB_MAX];
+    __shared__ cplx s_ra[2][MB_MAX], s_rb[2][MB_MAX];
+    __shared__ double s_rr[2][MB_MAX];
+    __shared__ cplx s_bulge[MB_MAX];
+
+    const cplx* Hg = Hc_all + (long long)f * hsz;
+    for (int i = tid; i < hsz; i += MB_THREADS) H[i] = Hg[i];
+    cplx* eig = eig_all + (long long)f * n;
+    __syncthreads();
+
+    long long c_pro = 0, c_R = 0, c_C = 0, n_b = 0, n_st = 0, c_t0 = clock64(), c_a;
+    int u = n - 1, its = 0, failed = 0;
+    while (u >= 0) {
+        c_a = clock64();
+        // ---- deflation scan ----------------------------------------------------------------
+        if (tid == 0) s_l = 0;
+        __syncthreads();
+        for (int k = 1 + tid; k <= u; k += MB_THREADS) {
+            const double sub = cabs1(HC(H, k, k - 1));
+            bool neg = false;
+            if (sub <= SMALL_D) neg = true;
+            else {
+                const cplx hkk = HC(H, k, k), hk1k1 = HC(H, k - 1, k - 1);
+                double tst = cabs1(hk1k1) + cabs1(hkk);
+                if (tst == 0.0) {
+                    if (k - 2 >= 0) tst += cabs1(HC(H, k - 1, k - 2));
+                    if (k + 1 <= n - 1) tst += cabs1(HC(H, k + 1, k));
+                }
+                if (sub <= EPS_D * tst) {
+                    const double up = cabs1(HC(H, k - 1, k));
+                    const double ab = fmax(sub, up), ba = fmin(sub, up);
+                    const double dd = cabs1(csub(hk1k1, hkk));
+                    const double aa = fmax(cabs1(hkk), dd), bb = fmin(cabs1(hkk), dd);
+                    const double sm = aa + ab;
+                    if (ba * (ab / sm) <= fmax(SMALL_D, EPS_D * (bb * (aa / sm)))) neg = true;
+                }
+            }
+            if (neg) atomicMax(&s_l, k);
+        }
+        __syncthreads();
+        const int l = s_l;
+        if (l > 0 && tid == 0) HC(H, l, l - 1) = mk(0, 0);
+        if (l == u) {
+            if (tid == 0) eig[u] = HC(H, u, u);
+            --u; its = 0;
+            __syncthreads();
+            continue;
+        }
+        ++its;
+        if (its > 120) {
+            if (tid == 0) eig[u] = HC(H, u, u);
+            ++failed; --u; its = 0;
+            __syncthreads();
+            continue;
+        }
+        const int m = u - l + 1;
+        int nb = (m - 2) / MB_D + 1;
+        if (nb > bmax) nb = bmax;
+        // ---- shifts: eigenvalues of the trailing 2x2 diagonal blocks -------------------------
+        if (tid < (nb + 1) / 2) {
+            const int i = u - 2 * tid;
+            const cplx a11 = HC(H, i - 1, i - 1), a12 = HC(H, i - 1, i), a21 = HC(H, i, i - 1), a22 = HC(H, i, i);
+            const cplx hd = cscale(csub(a11, a22), 0.5);
+            const cplx disc = csqrt_(cadd(cmul(hd, hd), cmul(a12, a21)));
+            const cplx mid = cscale(cadd(a11, a22), 0.5);
+            cplx e1 = cadd(mid, disc), e2 = csub(mid, disc);
+            if (cabs1(csub(e2, a22)) < cabs1(csub(e1, a22))) { const cplx tmp = e1; e1 = e2; e2 = tmp; }
+            if (its % 10 == 0) {                         // exceptional shifts against stagnation
+                const double ex = 0.75 * cabs1(HC(H, u, u - 1));
+                e1 = cadd(e1, mk(ex, 0)); e2 = cadd(e2, mk(0, ex));
+            }
+            s_shift[2 * tid] = e1;
+            if (2 * tid + 1 < MB_MAX) s_shift[2 * tid + 1] = e2;
+        }
+        __syncthreads();
+        if (tid == 0) {                                  // rotation that introduces bulge 0
+            cplx a, b; double r;
+            make_rot(csub(HC(H, l, l), s_shift[0]), HC(H, l + 1, l), a, b, r);
+            s_ra[0][0] = a; s_rb[0][0] = b; s_rr[0][0] = r;
+        }
+        __syncthreads();
+        const int nsteps = (m - 1) + (nb - 1) * MB_D;
+        const int CW = m + 1;                            // columns l-1 .. u
+        // per-thread work items are fixed for the whole batch: (bulge, column) for the row
+        // rotations, (bulge, row) for the column rotations; only k = k0 + t moves.
+        int r_k0[MB_ITEMS], r_col[MB_ITEMS], r_off[MB_ITEMS], c_k0[MB_ITEMS], c_row[MB_ITEMS];
+#pragma unroll
+        for (int q = 0; q < MB_ITEMS; ++q) {
+            const int item = tid + q * MB_THREADS;
+            r_k0[q] = c_k0[q] = 1 << 28;                 // "never active"
+            r_col[q] = 0; r_off[q] = 0; c_row[q] = 0;
+            if (item < nb * CW) {
+                const int b = item / CW, col = l - 1 + (item - b * CW);
+                if (col >= l) { r_k0[q] = l - b * MB_D; r_col[q] = col; r_off[q] = hcol_off(col); }
+                // column l-1 never receives a rotation (k-1 >= l whenever the slot is used)
+            }
+            if (item < nb * m) {
+                const int b = item / m;
+                c_k0[q] = l - b * MB_D; c_row[q] = l + (item - b * m);
+            }
+        }
+        c_pro += clock64() - c_a; n_b++; n_st += nsteps;
+        for (int t = 0; t < nsteps; ++t) {
+            const int cur = t & 1, nxt = cur ^ 1;
+            c_a = clock64();
+            // ---- phase R: row rotations ---------------------------------------------------------
+#pragma unroll
+            for (int q = 0; q < MB_ITEMS; ++q) {
+                const int k = r_k0[q] + t, col = r_col[q];
+                if (k >= l && k <= u - 1 && col >= k - 1 && k < (1 << 27)) {
+                    const int b = (l - r_k0[q]) / MB_D;
+                    cplx* pk = H + r_off[q] + k;
+                    if (col == k - 1) { *pk = mk(s_rr[cur][b], 0.0); }
+                    else {
+                        const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
+                        const cplx p = pk[0], qv = pk[1];
+                        pk[0] = cfma(ga, p, cmul(gb, qv));
+                        pk[1] = csub(cmulc(qv, ga), cmulc(p, gb));
+                    }
+                }
+            }
+            __syncthreads();
+            c_R += clock64() - c_a; c_a = clock64();
+            // ---- phase C: column rotations, next rotation ---------------------------------------
+#pragma unroll
+            for (int q = 0; q < MB_ITEMS; ++q) {
+                const int k = c_k0[q] + t, r = c_row[q];
+                if (k >= l && k <= u - 1 && r <= k + 1 && k < (1 << 27)) {
+                    const int b = (l - c_k0[q]) / MB_D;
+                    const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
+                    cplx* p0 = H + hcol_off(k) + r;
+                    cplx* p1 = H + hcol_off(k + 1) + r;
+                    const cplx c0 = *p0, c1 = *p1;
+                    const cplx n0 = cfmac(c0, ga, cmulc(c1, gb));           // c0 conj(a) + c1 conj(b)
+                    const cplx n1 = csub(cmul(c1, ga), cmul(c0, gb));       // -c0 b + c1 a
+                    *p0 = n0;
+                    *p1 = n1;
+                    if (r == k + 1 && k + 2 <= u) {
+                        const cplx h = p1[1];                               // H(k+2, k+1)
+                        const cplx y = cmulc(h, gb);                        // new bulge H(k+2, k)
+                        p1[1] = cmul(h, ga);
+                        cplx a2, b2; double r2;
+                        make_rot(n0, y, a2, b2, r2);
+                        s_ra[nxt][b] = a2; s_rb[nxt][b] = b2; s_rr[nxt][b] = r2;
+                    }
+                }
+            }
+            if (tid == MB_THREADS - 1 && (t + 1) % MB_D == 0) {
+                const int b = (t + 1) / MB_D;
+                if (b < nb) {                                           // bulge b starts at step t+1
+                    cplx a2, b2; double r2;
+                    make_rot(csub(HC(H, l, l), s_shift[b]), HC(H, l + 1, l), a2, b2, r2);
+                    s_ra[nxt][b] = a2; s_rb[nxt][b] = b2; s_rr[nxt][b] = r2;
+                }
+            }
+            __syncthreads();
+            c_C += clock64() - c_a;
+        }
+    }
+    if (tid == 0) info[f] = failed;
+    if (tid == 0 && f == 0) { g_dbg[0] = clock64() - c_t0; g_dbg[1] = c_pro; g_dbg[2] = c_R; g_dbg[3] = c_C; g_dbg[4] = n_b; g_dbg[5] = n_st; }
+    (void)s_bulge;
+}
+
+static size_t hqr_mb_smem(int n) { return (size_t)hcol_size(n) * sizeof(cplx); }
+
+// -----------------------------------------------------------------------------------------
+// k_hqr_ws: explicit single-shift QR, warp-shuffle systolic wavefront without per-rotation
+// block barriers.
+//   threads [0, W)   own one COLUMN each (left rotations).  The warp that contains the
+//                    diagonal column k is the "front": lane k generates G_k, broadcasts it to its
+//                    warp with shuffles and publishes it in shared memory (rot[k], then
+//                    `ready = k+1` after a block-scope fence).  Warps that own later columns poll
+//                    `ready` and apply the rotations at their own pace until the front reaches them.
+//   threads [W, 2W)  own one ROW each (right rotations R G_k^H) and trail the front: step k of
+//                    row i runs as soon as ready >= k+2 (column k+1 is final by then).
+// One __syncthreads per sweep; the per-rotation critical path is apply -> rotg -> shuffle.
+__device__ __forceinline__ cplx shfl_c(cplx v, int src) {
+    v.x = __shfl_sync(0xffffffffu, v.x, src);
+    v.y = __shfl_sync(0xffffffffu, v.y, src);
+    return v;
+}
+
+__global__ void __launch_bounds__(384, 1)
+k_hqr_ws(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* __restrict__ info)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int W = blockDim.x >> 1;
+    const int hsz = hcol_size(n);
+    cplx* H = (cplx*)smem_raw;
+    cplx* ra = H + hsz;
+    cplx* rb = ra + n;
+    __shared__ int s_l;
+    __shared__ cplx s_shift;
+    __shared__ volatile int s_ready;
+
+    const cplx* Hg = Hc_all + (long long)f * hsz;
+    for (int i = tid; i < hsz; i += blockDim.x) H[i] = Hg[i];
+    cplx* eig = eig_all + (long long)f * n;
+    __syncthreads();
+
+    long long c_pro = 0, c_front = 0, c_tail = 0, n_sw = 0, n_rot = 0, c_t0 = clock64(), c_a;
+    int u = n - 1, its = 0, failed = 0;
+    while (u >= 0) {
+        c_a = clock64();
+        if (tid == 0) s_l = 0;
+        __syncthreads();
+        if (tid >= 1 && tid <= u) {
+            const int k = tid;
+            const double sub = cabs1(HC(H, k, k - 1));
+            bool neg = false;
+            if (sub <= SMALL_D) neg = true;
+            else {
+                const cplx hkk = HC(H, k, k), hk1k1 = HC(H, k - 1, k - 1);
+                double tst = cabs1(hk1k1) + cabs1(hkk);
+                if (tst == 0.0) {
+                    if (k - 2 >= 0) tst += cabs1(HC(H, k - 1, k - 2));
+                    if (k + 1 <= n - 1) tst += cabs1(HC(H, k + 1, k));
+                }
+                if (sub <= EPS_D * tst) {
+                    const double up = cabs1(HC(H, k - 1, k));
+                    const double ab = fmax(sub, up), ba = fmin(sub, up);
+                    const double dd = cabs1(csub(hk1k1, hkk));
+                    const double aa = fmax(cabs1(hkk), dd), bb = fmin(cabs1(hkk), dd);
+                    const double sm = aa + ab;
+                    if (ba * (ab / sm) <= fmax(SMALL_D, EPS_D * (bb * (aa / sm)))) neg = true;
+                }
+            }
+            if (neg) atomicMax(&s_l, k);
+        }
+        __syncthreads();
+        const int l = s_l;
+        if (l > 0 && tid == 0) HC(H, l, l - 1) = mk(0, 0);
+        if (l == u) {
+            if (tid == 0) eig[u] = HC(H, u, u);
+            --u; its = 0;
+            __syncthreads();
+            continue;
+        }
+        ++its;
+        if (its > 60) {
+            if (tid == 0) eig[u] = HC(H, u, u);
+            ++failed; --u; its = 0;
+            __syncthreads();
+            continue;
+        }
+        if (tid == 0) {
+            cplx sg;
+            if (its % 20 == 10) sg = cadd(HC(H, l, l), mk(0.75 * fabs(HC(H, l + 1, l).x), 0));
+            else if (its % 20 == 0) sg = cadd(HC(H, u, u), mk(0.75 * fabs(HC(H, u, u - 1).x), 0));
+            else sg = wilkinson_shift(H, u);
+            s_shift = sg;
+            s_ready = l;
+        }
+        __syncthreads();
+        const cplx sg = s_shift;
+        c_pro += clock64() - c_a; c_a = clock64(); n_sw++; n_rot += u - l;
+
+        if (tid < W) {
+            // ================= left rotations: one column per thread =========================
+            // Shared-memory stores of one thread become visible in program order (in-order LSU),
+            // so "rotation record, then ready counter" needs no fence; volatile keeps the compiler
+            // from reordering them.
+            volatile cplx* vra = ra;
+            volatile cplx* vrb = rb;
+            const int j = tid, wbase = tid & ~31;
+            if (wbase <= u && wbase + 31 >= l) {
+                const bool act = (j >= l && j <= u);
+                cplx carry = mk(0, 0);
+                if (act) { carry = HC(H, l, j); if (j == l) carry = csub(carry, sg); }
+                const int front0 = wbase > l ? wbase : l;
+                // phase 1: rotations generated by earlier warps, consumed in batches
+                int k = l;
+                while (k < front0) {
+                    int avail = s_ready;
+                    while (avail <= k) { __nanosleep(64); avail = s_ready; }
+                    asm volatile("" ::: "memory");      // compiler-only barrier (acquire)
+                    if (avail > front0) avail = front0;
+                    if (act) {
+                        cplx low = HC(H, k + 1, j);
+                        for (; k < avail; ++k) {
+                            const cplx a = mk(vra[k].x, vra[k].y), b = mk(vrb[k].x, vrb[k].y);
+                            cplx lw = low;
+                            if (k + 1 < avail || k + 2 <= u) low = HC(H, (k + 2 <= u) ? k + 2 : u, j);   // prefetch
+                            if (j == k + 1) lw = csub(lw, sg);
+                            HC(H, k, j) = cfma(a, carry, cmul(b, lw));
+                            carry = csub(cmulc(lw, a), cmulc(carry, b));
+                        }
+                    }
+                    k = avail;
+                }
+                // phase 2: this warp is the front
+                const int last = (wbase + 31 < u - 1) ? wbase + 31 : u - 1;
+                cplx low = mk(0, 0);
+                if (front0 <= last && j <= u && j > front0) low = HC(H, front0 + 1, j);
+                cplx g = mk(0, 0);
+                if (j >= front0 && j <= last) g = HC(H, j + 1, j);          // own subdiagonal entry
+                for (k = front0; k <= last; ++k) {
+                    cplx a = mk(1, 0), b = mk(0, 0);
+                    double r = 0.0;
+                    if (j == k) make_rot(carry, g, a, b, r);
+                    a = shfl_c(a, k - wbase);
+                    b = shfl_c(b, k - wbase);
+                    if (j > k && j <= u) {
+                        cplx lw = low;
+                        if (k + 2 <= u) low = HC(H, k + 2, j);              // prefetch next row
+                        if (j == k + 1) lw = csub(lw, sg);
+                        HC(H, k, j) = cfma(a, carry, cmul(b, lw));
+                        carry = csub(cmulc(lw, a), cmulc(carry, b));
+                    } else if (j == k) {                                    // publish off the critical path
+                        HC(H, k, k) = mk(r, 0.0);
+                        asm volatile("" ::: "memory");  // keep the stores in program order
+                        vra[k].x = a.x; vra[k].y = a.y; vrb[k].x = b.x; vrb[k].y = b.y;
+                        asm volatile("" ::: "memory");
+                        s_ready = k + 1;
+                    }
+                }
+                if (j == u) {
+                    HC(H, u, u) = carry;
+                    __threadfence_block();
+                    s_ready = u + 1;
+                    c_front += clock64() - c_a;
+                }
+            }
+        } else {
+            // ================= right rotations: one row per thread ===========================
+            volatile cplx* vra = ra;
+            volatile cplx* vrb = rb;
+            const int i = tid - W;
+            if (i >= l && i <= u) {
+                const int kk = (i - 1 >= l) ? i - 1 : l;
+                cplx left = mk(0, 0);
+                bool have_left = (i - 1 >= l);
+                int k = kk;
+                while (k < u) {                          // lanes advance independently of each other
+                    const int avail = s_ready;
+                    asm volatile("" ::: "memory");
+                    if (avail < k + 2) { __nanosleep(32); continue; }
+                    if (!have_left) { left = HC(H, i, l); have_left = true; }     // R[l,l]
+                    const cplx rt = HC(H, i, k + 1);
+                    const cplx a = mk(vra[k].x, vra[k].y), b = mk(vrb[k].x, vrb[k].y);
+                    cplx newl = cfmac(left, a, cmulc(rt, b));
+                    const cplx newr = csub(cmul(rt, a), cmul(left, b));
+                    if (k == i) newl = cadd(newl, sg);
+                    HC(H, i, k) = newl;
+                    left = newr;
+                    ++k;
+                }
+                if (i == u) left = cadd(left, sg);
+                HC(H, i, u) = left;
+            }
+        }
+        __syncthreads();
+        c_tail += clock64() - c_a;
+    }
+    if (tid == 0) info[f] = failed;
+    if (tid == 0 && f == 0) { g_dbg[0] = clock64() - c_t0; g_dbg[1] = c_pro; g_dbg[3] = c_tail; g_dbg[4] = n_sw; g_dbg[5] = n_rot; }
+    if (f == 0 && c_front) atomicAdd((unsigned long long*)&g_dbg[2], (unsigned long long)c_front);
+}
+
+static size_t hqr_ws_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(cplx); }
+
+
+
+
 
 // =========================================================================================
 // k_modes
@@ -477,6 +911,7 @@ k_modes(int N, int hb, const cplx* __restrict__ Cb, const cplx* __restrict__ K6d
         cplx carry = row[n - 1];
         if (k == n - 1) carry = csub(carry, lam);
         cplx acc = mk(1.0, 0.0);
+#pragma unroll 4
         for (int j = n - 2; j >= k; --j) {
             cplx a = row[j];
             if (j == k) a = csub(a, lam);
@@ -670,11 +1105,27 @@ extern "C" int axs_launch_reduce(int N, int hb, const cplx* K0s, const cplx* Cb,
 
 extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, cudaStream_t st)
 {
-    size_t smem = hqr_smem(n);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int threads = ((n + 31) / 32) * 32;
-    if (threads < 64) threads = 64;
-    k_hqr<<<nf, threads, smem, st>>>(n, wk.Hc, eig, info);
+    const char* mode = getenv("AXS_HQR_BULGES");
+    int bulges = mode ? atoi(mode) : MB_MAX; // default: 8 concurrent bulges (fastest measured on B200)
+    if (bulges < 0) {                        // -1: warp-shuffle systolic wavefront (kept for A/B)
+        size_t smem = hqr_ws_smem(n);
+        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int W = ((n + 31) / 32) * 32;
+        k_hqr_ws<<<nf, 2 * W, smem, st>>>(n, wk.Hc, eig, info);
+        return (int)cudaGetLastError();
+    }
+    if (bulges == 0) {                       // barrier-per-rotation variant (kept for A/B)
+        size_t smem = hqr_smem(n);
+        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int threads = ((n + 31) / 32) * 32;
+        if (threads < 64) threads = 64;
+        k_hqr<<<nf, threads, smem, st>>>(n, wk.Hc, eig, info);
+        return (int)cudaGetLastError();
+    }
+    if (bulges > MB_MAX) bulges = MB_MAX;
+    size_t smem = hqr_mb_smem(n);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_hqr_mb<<<nf, MB_THREADS, smem, st>>>(n, bulges, wk.Hc, eig, info);
     return (int)cudaGetLastError();
 }
 
