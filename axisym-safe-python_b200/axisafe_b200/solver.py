@@ -35,14 +35,10 @@ class _LazyModes(object):
     def materialise(self):
         if self.host is None:
             from . import _native
-            block = _native.download(self.tensor).reshape(self.shape)
-            if self.shape[0] == self.total:
-                self.host = block
-            else:
-                # sharded sweep: frequencies owned by other ranks stay zero on this rank
-                full = np.zeros((self.total,) + tuple(self.shape[1:]), complex)
-                full[self.first:self.first + self.shape[0]] = block
-                self.host = full
+            # single GPU: the full [nf, 2N, 2N] array of the reference.  Sharded sweep: only this
+            # rank's frequencies [first, first + shape[0]) exist here (see local_range); the full
+            # array (0.5 GB .. TBs) is never gathered.
+            self.host = _native.download(self.tensor).reshape(self.shape)
         return self.host
 
 

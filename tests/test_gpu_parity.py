@@ -271,3 +271,15 @@ def test_full_size_sweep_properties():
     for i in (0, 777, 1999):
         val, _ = so.eig_normalised(op, 2 * np.pi * c['f'][i])
         assert so.match_eigenvalues(val, sol.k[i])[1] < 1e-8
+
+
+def test_sharded_solve_matches_single_gpu():
+    """N > 1: frequency sharding + halo + NCCL gather must not change any result."""
+    import subprocess, sys, os, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                          '--master-addr', '127.0.0.1', '--master-port', '29617', 'tests/mgpu_check.py'],
+                         cwd=root, capture_output=True, text=True, timeout=600)
+    assert 'MGPU_CHECK PASS' in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
