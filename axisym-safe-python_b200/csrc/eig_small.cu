@@ -468,6 +468,7 @@ static size_t hqr_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(c
 #define MB_MAX 8
 #define MB_D 3
 #define MB_THREADS 512
+#define MB_WORKERS (MB_THREADS - 32)
 #define MB_ITEMS 3                      // ceil(MB_MAX * (AXS_MAX_SMALL_N2 + 1) / MB_THREADS)
 
 __device__ __forceinline__ void make_rot(cplx x, cplx y, cplx& a, cplx& b, double& r) {
@@ -576,7 +577,7 @@ k_hqr_mb(int n, int bmax, const cplx* __restrict__ Hc_all, cplx* __restrict__ ei
         int r_k0[MB_ITEMS], r_col[MB_ITEMS], r_off[MB_ITEMS], c_k0[MB_ITEMS], c_row[MB_ITEMS];
 #pragma unroll
         for (int q = 0; q < MB_ITEMS; ++q) {
-            const int item = tid + q * MB_THREADS;
+            const int item = (tid < MB_WORKERS) ? tid + q * MB_WORKERS : (1 << 30);   // last warp: leaders only
             r_k0[q] = c_k0[q] = 1 << 28;                 // "never active"
             r_col[q] = 0; r_off[q] = 0; c_row[q] = 0;
             if (item < nb * CW) {
@@ -612,20 +613,20 @@ k_hqr_mb(int n, int bmax, const cplx* __restrict__ Hc_all, cplx* __restrict__ ei
             __syncthreads();
             c_R += clock64() - c_a; c_a = clock64();
             // ---- phase C: column rotations, next rotation ---------------------------------------
-#pragma unroll
-            for (int q = 0; q < MB_ITEMS; ++q) {
-                const int k = c_k0[q] + t, r = c_row[q];
-                if (k >= l && k <= u - 1 && r <= k + 1 && k < (1 << 27)) {
-                    const int b = (l - c_k0[q]) / MB_D;
+            // The last warp owns the critical chain of every bulge (rows k+1, k+2 -> next rotation)
+            // so that it overlaps with the bulk updates done by the other warps.
+            if (tid >= MB_THREADS - 32) {
+                const int b = tid - (MB_THREADS - 32);
+                const int k = l + t - b * MB_D;
+                if (b < nb && k >= l && k <= u - 1) {
                     const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
-                    cplx* p0 = H + hcol_off(k) + r;
-                    cplx* p1 = H + hcol_off(k + 1) + r;
+                    cplx* p0 = H + hcol_off(k) + k + 1;
+                    cplx* p1 = H + hcol_off(k + 1) + k + 1;
                     const cplx c0 = *p0, c1 = *p1;
-                    const cplx n0 = cfmac(c0, ga, cmulc(c1, gb));           // c0 conj(a) + c1 conj(b)
-                    const cplx n1 = csub(cmul(c1, ga), cmul(c0, gb));       // -c0 b + c1 a
+                    const cplx n0 = cfmac(c0, ga, cmulc(c1, gb));
                     *p0 = n0;
-                    *p1 = n1;
-                    if (r == k + 1 && k + 2 <= u) {
+                    *p1 = csub(cmul(c1, ga), cmul(c0, gb));
+                    if (k + 2 <= u) {
                         const cplx h = p1[1];                               // H(k+2, k+1)
                         const cplx y = cmulc(h, gb);                        // new bulge H(k+2, k)
                         p1[1] = cmul(h, ga);
@@ -634,13 +635,24 @@ k_hqr_mb(int n, int bmax, const cplx* __restrict__ Hc_all, cplx* __restrict__ ei
                         s_ra[nxt][b] = a2; s_rb[nxt][b] = b2; s_rr[nxt][b] = r2;
                     }
                 }
-            }
-            if (tid == MB_THREADS - 1 && (t + 1) % MB_D == 0) {
-                const int b = (t + 1) / MB_D;
-                if (b < nb) {                                           // bulge b starts at step t+1
+                if (b == nb && (t + 1) % MB_D == 0 && (t + 1) / MB_D < nb) {   // bulge (t+1)/D starts next step
+                    const int bn = (t + 1) / MB_D;
                     cplx a2, b2; double r2;
-                    make_rot(csub(HC(H, l, l), s_shift[b]), HC(H, l + 1, l), a2, b2, r2);
-                    s_ra[nxt][b] = a2; s_rb[nxt][b] = b2; s_rr[nxt][b] = r2;
+                    make_rot(csub(HC(H, l, l), s_shift[bn]), HC(H, l + 1, l), a2, b2, r2);
+                    s_ra[nxt][bn] = a2; s_rb[nxt][bn] = b2; s_rr[nxt][bn] = r2;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < MB_ITEMS; ++q) {
+                const int k = c_k0[q] + t, r = c_row[q];
+                if (k >= l && k <= u - 1 && r <= k) {
+                    const int b = (l - c_k0[q]) / MB_D;
+                    const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
+                    cplx* p0 = H + hcol_off(k) + r;
+                    cplx* p1 = H + hcol_off(k + 1) + r;
+                    const cplx c0 = *p0, c1 = *p1;
+                    *p0 = cfmac(c0, ga, cmulc(c1, gb));                     // c0 conj(a) + c1 conj(b)
+                    *p1 = csub(cmul(c1, ga), cmul(c0, gb));                 // -c0 b + c1 a
                 }
             }
             __syncthreads();

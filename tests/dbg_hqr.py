@@ -18,5 +18,5 @@ os.environ['AXS_HQR_BULGES'] = sys.argv[1] if len(sys.argv) > 1 else '0'
 k, info = nat.hqr(N, nf, work); torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 16)()
 L.axs_debug_counters(buf)
-tot, pro, left, right, nsw, nrot = [buf[i] for i in range(6)]
+tot, pro, left, right, nsw, nrot = [buf[i] for i in range(6)]; print('defl', buf[6], 'load', buf[7])
 print('block0: total %d cyc; prologue %d (%.0f/sweep); left %d (%.0f/rot); right %d (%.0f/rot); sweeps %d rots %d' % (tot, pro, pro / nsw, left, left / nrot, right, right / nrot, nsw, nrot))
