@@ -38,6 +38,8 @@ _SIGNATURES = {
                         [ctypes.c_void_p] * 3 + [ctypes.c_longlong, ctypes.c_void_p]),
     'axs_track_scan': (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p]),
     'axs_apply_order': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 6),
+    'axs_energy_ratio': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 2 +
+                         [ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int] + [ctypes.c_void_p] * 5),
 }
 EXPORTED = tuple(_SIGNATURES)
 
@@ -334,3 +336,21 @@ def apply_order(n2, nf, order, k, psi):
     check(lib().axs_apply_order(n2, nf, _ptr(d_order), _ptr(k), _ptr(psi), _ptr(k_out), _ptr(psi_out),
                                 _stream(torch)), 'axs_apply_order')
     return k_out, psi_out
+
+
+def energy_ratio(N, nf, psi, tclass, total, pml):
+    """axs_energy_ratio: ``total`` / ``pml`` are (rows, cols, vals) COO triplets (host arrays)."""
+    torch = torch_cuda()
+
+    def up(triplet):
+        r, c, v = triplet
+        return (to_device(np.asarray(r, np.int32), torch), to_device(np.asarray(c, np.int32), torch),
+                to_device(np.asarray(v, np.complex128), torch), len(r))
+    rt, ct, vt, nt = up(total)
+    rp, cp, vp, npml = up(pml)
+    d_tc = to_device(np.asarray(tclass, np.int32), torch)
+    er = torch.empty(nf * 2 * N, dtype=torch.float64, device='cuda')
+    check(lib().axs_energy_ratio(N, nf, _ptr(psi), _ptr(d_tc), nt, _ptr(rt), _ptr(ct), _ptr(vt),
+                                 npml, _ptr(rp) if npml else None, _ptr(cp) if npml else None,
+                                 _ptr(vp) if npml else None, _ptr(er), _stream(torch)), 'axs_energy_ratio')
+    return er.cpu().numpy().reshape(nf, 2 * N)

@@ -166,6 +166,63 @@ class WaveElementAxisym(object):
         self.k_ready = 0
 
 
+    # ------------------------------------------------------------- mode-type filtering (row N1)
+    def energy_ratio(self, core_sets=None):
+        """Kinetic-energy ratio PML / whole waveguide per mode (ref solver.py:186-269).
+
+        The reference forms q = conj(T) psi_hat[:, N:, :] on the host and two dense batched
+        products with the (sub-)assembled mass matrices; here the tracked mode shapes stay on the
+        GPU (axs_energy_ratio) and only ``er`` [nf, 2N] comes back.
+        """
+        if not self.evaluated:
+            print('No solution is availble. Solve the system first.')
+            return
+        from . import _native
+        print('Calculating the energy ratio...')
+        mesh = self.Mesh
+        pml_elements = []
+        for key in mesh.dofs_per_elset:
+            if 'PML' in key:
+                pml_elements.extend(mesh.element_sets[key])
+        M_pml = mesh.assemble_subset(sorted(set(pml_elements)))['M'].tocoo() if pml_elements else None
+        M_tot = mesh.M.tocoo()
+        mult = np.ones(mesh.no_of_dofs)
+        if mesh.dof_domains['fluid'] != []:
+            mult[mesh.dof_domains['fluid']] = -1             # acts on columns (ref solver.py:234-239)
+
+        def triplets(coo):
+            if coo is None:
+                return (np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, complex))
+            coo.sum_duplicates()
+            keep = coo.data != 0
+            return coo.row[keep], coo.col[keep], (coo.data * mult[coo.col])[keep]
+        tclass = [0 if t == 1 else 1 for t in mesh.Tdiag]
+        lo, hi = self.local_range
+        if self.psi_hat_device is None:
+            raise RuntimeError('mode shapes are no longer on the device; call solve() again')
+        er_loc = _native.energy_ratio(mesh.no_of_dofs, hi - lo, self.psi_hat_device.reshape(-1), tclass,
+                                      triplets(M_tot), triplets(M_pml))
+        if hi - lo == len(self.w):
+            self.er = er_loc
+        else:
+            self.er = np.full([len(self.w), 2 * mesh.no_of_dofs], np.nan)   # other ranks' frequencies
+            self.er[lo:hi] = er_loc
+
+    def k_propagating(self, imag_threshold=10, ER_threshold=0.9):
+        """Positive-going propagating solutions (ref solver.py:271-299); host, O(nf * 2N)."""
+        if self.er is None:
+            print('Warning. Energy ratio must be evaluated first. ' + 'Use the trace_back method')
+            return
+        k = np.copy(self.k)
+        k[abs(k.imag) > imag_threshold] = 0
+        if ER_threshold != 0:
+            k[self.er > ER_threshold] = 0
+        k[k.real < 0] = 0
+        k[k.imag > .1] = 0
+        self.propagating_indices = np.where(~(k == 0).all(0))[0]
+        self.k_ready = k[:, self.propagating_indices]
+
+
 def _gather_blocks(torch, bounds, rank, n2, k_loc, arg_loc, amax_loc, info_loc):
     """All-gather the per-rank eigenvalue / tracking tables (NCCL); blocks are padded to equal size."""
     import torch.distributed as dist

@@ -17,6 +17,8 @@ int axs_launch_modes(int, int, const cplx*, const cplx*, int, const cplx*, cplx*
 int axs_launch_unpack(int, int, AxsWork, cplx*, cudaStream_t);
 int axs_launch_track(int, int, const cplx*, const cplx*, const cplx*, int, cplx*, int*, double*, cudaStream_t);
 int axs_launch_apply_order(int, int, const int*, const cplx*, const cplx*, cplx*, cplx*, cudaStream_t);
+int axs_launch_energy_ratio(int, int, const cplx*, const int*, int, const int*, const int*, const cplx*,
+                            int, const int*, const int*, const cplx*, double*, cudaStream_t);
 }
 
 #define AXS_ERR_TOO_LARGE 100001
@@ -237,4 +239,21 @@ extern "C" int axs_apply_order(int n2, int nf, const int* order, const axs_cplx*
     if (!k_out) return -6;
     return axs_launch_apply_order(n2, nf, order, (const cplx*)k, (const cplx*)psi, (cplx*)k_out,
                                   (cplx*)psi_out, (cudaStream_t)stream);
+}
+
+extern "C" int axs_energy_ratio(int N, int nf, const axs_cplx* psi, const int* tclass,
+                                int nnz_total, const int* rows_total, const int* cols_total, const axs_cplx* vals_total,
+                                int nnz_pml, const int* rows_pml, const int* cols_pml, const axs_cplx* vals_pml,
+                                double* er, void* stream)
+{
+    if (N <= 0) return -1;
+    if (nf <= 0) return -2;
+    if (!psi) return -3;
+    if (!tclass) return -4;
+    if (nnz_total <= 0 || !rows_total || !cols_total || !vals_total) return -5;
+    if (nnz_pml < 0 || (nnz_pml > 0 && (!rows_pml || !cols_pml || !vals_pml))) return -9;
+    if (!er) return -13;
+    return axs_launch_energy_ratio(N, nf, (const cplx*)psi, tclass, nnz_total, rows_total, cols_total,
+                                   (const cplx*)vals_total, nnz_pml, rows_pml, cols_pml, (const cplx*)vals_pml,
+                                   er, (cudaStream_t)stream);
 }

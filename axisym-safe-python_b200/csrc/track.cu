@@ -129,6 +129,38 @@ k_apply_order(int n, const int* __restrict__ order, const cplx* __restrict__ k_i
     }
 }
 
+// Kinetic-energy ratio PML / total per mode (solver.py:186-269):
+//   q = conj(T) psi[N:],  E = q^H M q  (M given as COO triplets, fluid columns already x -1),
+//   er = |E_pml| / |E_tot|.   grid = (ceil(n2/128), nf), thread = one mode.
+__global__ void __launch_bounds__(128)
+k_energy_ratio(int N, const cplx* __restrict__ psi_all, const int* __restrict__ tclass,
+               int nnz_t, const int* __restrict__ rt, const int* __restrict__ ct, const cplx* __restrict__ vt,
+               int nnz_p, const int* __restrict__ rp, const int* __restrict__ cp, const cplx* __restrict__ vp,
+               double* __restrict__ er)
+{
+    const int n = 2 * N, f = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const cplx* psi = psi_all + (long long)f * n * n + (long long)N * n + j;   // psi[N + r][j] = psi[r * n]
+    auto q_at = [&](int r) {
+        const cplx v = psi[(long long)r * n];
+        return tclass[r] ? mk(v.y, -v.x) : v;                                  // conj(T) = 1 or -i
+    };
+    cplx et = mk(0, 0), ep = mk(0, 0);
+    for (int e = 0; e < nnz_t; ++e) et = cfma(cmul(cconj(q_at(rt[e])), vt[e]), q_at(ct[e]), et);
+    for (int e = 0; e < nnz_p; ++e) ep = cfma(cmul(cconj(q_at(rp[e])), vp[e]), q_at(cp[e]), ep);
+    er[(long long)f * n + j] = cabsd(ep) / cabsd(et);
+}
+
+extern "C" int axs_launch_energy_ratio(int N, int nf, const cplx* psi, const int* tclass,
+                                       int nnz_t, const int* rt, const int* ct, const cplx* vt,
+                                       int nnz_p, const int* rp, const int* cp, const cplx* vp,
+                                       double* er, cudaStream_t st)
+{
+    const int n = 2 * N;
+    k_energy_ratio<<<dim3((n + 127) / 128, nf), 128, 0, st>>>(N, psi, tclass, nnz_t, rt, ct, vt, nnz_p, rp, cp, vp, er);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int axs_launch_track(int N, int hb, const cplx* Cb, const cplx* K6d, const cplx* psi,
                                 int npairs, cplx* Y, int* arg, double* amax, cudaStream_t st)
 {

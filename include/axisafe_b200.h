@@ -137,6 +137,17 @@ int axs_track_scan(const int* h_arg, const double* h_amax, int nf, int n2, int s
 int axs_apply_order(int n2, int nf, const int* order, const axs_cplx* k, const axs_cplx* psi,
                     axs_cplx* k_out, axs_cplx* psi_out, void* stream);
 
+/* ---- energy ratio ------------------------------------------
+ * Replaces the dense batched products of WaveElementAxisym.energy_ratio, solver.py:248-266:
+ *     q = conj(T) psi[N:],  E_tot = q^H M_total q,  E_pml = q^H M_pml q,  er = |E_pml| / |E_tot|
+ * (the common factor w^2/4 cancels).  Both mass matrices are passed as COO triplets over the
+ * global DOFs with the reference's fluid "multiplier" (-1 on fluid columns, solver.py:234-239)
+ * already applied.  psi is [nf][2N][2N] in the tracked column order; er is [nf][2N]. */
+int axs_energy_ratio(int N, int nf, const axs_cplx* psi, const int* tclass,
+                     int nnz_total, const int* rows_total, const int* cols_total, const axs_cplx* vals_total,
+                     int nnz_pml, const int* rows_pml, const int* cols_pml, const axs_cplx* vals_pml,
+                     double* er, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

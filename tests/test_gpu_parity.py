@@ -283,3 +283,35 @@ def test_sharded_solve_matches_single_gpu():
                           '--master-addr', '127.0.0.1', '--master-port', '29617', 'tests/mgpu_check.py'],
                          cwd=root, capture_output=True, text=True, timeout=600)
     assert 'MGPU_CHECK PASS' in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize('name,n,kw', [c for c in GOLDEN_CASES if c[0] not in ('free_steel_pipe',)],
+                         ids=[i for c, i in zip(GOLDEN_CASES, CASE_IDS) if c[0] not in ('free_steel_pipe',)])
+def test_energy_ratio_and_propagating_filter(name, n, kw):
+    """Row N1: energy_ratio + k_propagating against the reference's outputs."""
+    import axisafe_b200 as ax
+    g = load_golden(name, n)
+    c = make_case(name, n, kw)
+    m = _mesh(c)
+    sol = ax.solver.WaveElementAxisym(m)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sol.solve(c['f'])
+        sol.energy_ratio()
+        sol.k_propagating(*g['kprop_args'])
+    assert sol.er.shape == g['er'].shape
+    worst = 0.0
+    for i in range(1, len(c['f'])):
+        for col in range(sol.k.shape[1]):
+            mine = np.argmin(np.abs(sol.k[i] - g['k'][i][col]))
+            if abs(sol.k[i][mine] - g['k'][i][col]) > 1e-7 * abs(g['k'][i][col]):
+                continue
+            # +-k pairs and degenerate modes share er, so the nearest eigenvalue is enough
+            worst = max(worst, abs(sol.er[i][mine] - g['er'][i][col]) / max(g['er'][i][col], 1e-3))
+    assert worst < 1e-5, worst
+    # the filtered sets of propagating wavenumbers agree frequency by frequency
+    for i in range(1, len(c['f'])):
+        ref = np.sort_complex(g['k_ready'][i][g['k_ready'][i] != 0])
+        got = np.sort_complex(sol.k_ready[i][sol.k_ready[i] != 0])
+        assert len(ref) == len(got), (i, len(ref), len(got))
+        if len(ref):
+            assert np.abs(ref - got).max() <= 1e-6 * np.abs(ref).max()
