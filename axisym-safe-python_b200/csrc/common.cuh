@@ -72,6 +72,8 @@ struct AxsWork {
     cplx*   Hr;     // [nf][hrow_size] packed row-major Hessenberg (input of inverse iteration)
     cplx*   tau;    // [nf][n2]
     double* scale;  // [nf][n2]  balancing factors D
+    int*    ucur;   // [nf]      active-window top between QR stages
+    cplx*   Hp;     // [nf][hcol_size] leading block parked between QR stages (Hc stays intact)
 };
 
 static inline long long axs_align(long long x) { return (x + 255) & ~255LL; }
@@ -96,5 +98,9 @@ static inline long long axs_work_layout(int n2, int nf, void* base, AxsWork* w) 
     off += szT;
     if (w) w->scale = (double*)(b + off);
     off += szS;
+    if (w) w->ucur = (int*)(b + off);
+    off += axs_align((long long)nf * sizeof(int));
+    if (w) w->Hp = (cplx*)(b + off);
+    off += szHc;
     return off;
 }

@@ -481,8 +481,14 @@ __device__ __forceinline__ void make_rot(cplx x, cplx y, cplx& a, cplx& b, doubl
     } else { a = mk(1, 0); b = mk(0, 0); r = 0.0; }
 }
 
-__global__ void __launch_bounds__(MB_THREADS, 1)
-k_hqr_mb(int n, int bmax, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* __restrict__ info)
+// Staging: the active window only shrinks, so the sweep is cut into stages with a smaller
+// shared-memory footprint each; a stage stops once the window is <= m_stop, parks the leading
+// block and its size in global memory, and the next stage resumes with more CTAs per SM
+// (the kernel is latency bound, so co-resident matrices translate into throughput).
+template <int NT, int MINB, int NITEMS>
+__global__ void __launch_bounds__(NT, MINB)
+k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ Hc_all, cplx* __restrict__ Hp_all,
+         cplx* __restrict__ eig_all, int* __restrict__ info, int* __restrict__ ucur)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.x, tid = threadIdx.x;
@@ -494,19 +500,20 @@ k_hqr_mb(int n, int bmax, const cplx* __restrict__ Hc_all, cplx* __restrict__ ei
     __shared__ double s_rr[2][MB_MAX];
     __shared__ cplx s_bulge[MB_MAX];
 
-    const cplx* Hg = Hc_all + (long long)f * hsz;
-    for (int i = tid; i < hsz; i += MB_THREADS) H[i] = Hg[i];
+    const cplx* Hg = (first_stage ? Hc_all : Hp_all) + (long long)f * hsz;
+    cplx* Hpark = Hp_all + (long long)f * hsz;
+    int u = first_stage ? n - 1 : ucur[f];
+    if (u < 0) return;                                    // finished in an earlier stage
+    for (int i = tid; i < hcol_size(u + 1); i += NT) H[i] = Hg[i];
     cplx* eig = eig_all + (long long)f * n;
     __syncthreads();
 
-    long long c_pro = 0, c_R = 0, c_C = 0, n_b = 0, n_st = 0, c_t0 = clock64(), c_a;
-    int u = n - 1, its = 0, failed = 0;
-    while (u >= 0) {
-        c_a = clock64();
+    int its = 0, failed = 0;
+    while (u >= m_stop) {
         // ---- deflation scan ----------------------------------------------------------------
         if (tid == 0) s_l = 0;
         __syncthreads();
-        for (int k = 1 + tid; k <= u; k += MB_THREADS) {
+        for (int k = 1 + tid; k <= u; k += NT) {
             const double sub = cabs1(HC(H, k, k - 1));
             bool neg = false;
             if (sub <= SMALL_D) neg = true;
@@ -574,10 +581,10 @@ k_hqr_mb(int n, int bmax, const cplx* __restrict__ Hc_all, cplx* __restrict__ ei
         const int CW = m + 1;                            // columns l-1 .. u
         // per-thread work items are fixed for the whole batch: (bulge, column) for the row
         // rotations, (bulge, row) for the column rotations; only k = k0 + t moves.
-        int r_k0[MB_ITEMS], r_col[MB_ITEMS], r_off[MB_ITEMS], c_k0[MB_ITEMS], c_row[MB_ITEMS];
+        int r_k0[NITEMS], r_col[NITEMS], r_off[NITEMS], c_k0[NITEMS], c_row[NITEMS];
 #pragma unroll
-        for (int q = 0; q < MB_ITEMS; ++q) {
-            const int item = (tid < MB_WORKERS) ? tid + q * MB_WORKERS : (1 << 30);   // last warp: leaders only
+        for (int q = 0; q < NITEMS; ++q) {
+            const int item = (tid < (NT - 32)) ? tid + q * (NT - 32) : (1 << 30);   // last warp: leaders only
             r_k0[q] = c_k0[q] = 1 << 28;                 // "never active"
             r_col[q] = 0; r_off[q] = 0; c_row[q] = 0;
             if (item < nb * CW) {
@@ -590,13 +597,11 @@ k_hqr_mb(int n, int bmax, const cplx* __restrict__ Hc_all, cplx* __restrict__ ei
                 c_k0[q] = l - b * MB_D; c_row[q] = l + (item - b * m);
             }
         }
-        c_pro += clock64() - c_a; n_b++; n_st += nsteps;
         for (int t = 0; t < nsteps; ++t) {
             const int cur = t & 1, nxt = cur ^ 1;
-            c_a = clock64();
-            // ---- phase R: row rotations ---------------------------------------------------------
+                // ---- phase R: row rotations ---------------------------------------------------------
 #pragma unroll
-            for (int q = 0; q < MB_ITEMS; ++q) {
+            for (int q = 0; q < NITEMS; ++q) {
                 const int k = r_k0[q] + t, col = r_col[q];
                 if (k >= l && k <= u - 1 && col >= k - 1 && k < (1 << 27)) {
                     const int b = (l - r_k0[q]) / MB_D;
@@ -611,12 +616,11 @@ k_hqr_mb(int n, int bmax, const cplx* __restrict__ Hc_all, cplx* __restrict__ ei
                 }
             }
             __syncthreads();
-            c_R += clock64() - c_a; c_a = clock64();
             // ---- phase C: column rotations, next rotation ---------------------------------------
             // The last warp owns the critical chain of every bulge (rows k+1, k+2 -> next rotation)
             // so that it overlaps with the bulk updates done by the other warps.
-            if (tid >= MB_THREADS - 32) {
-                const int b = tid - (MB_THREADS - 32);
+            if (tid >= (NT - 32)) {
+                const int b = tid - ((NT - 32));
                 const int k = l + t - b * MB_D;
                 if (b < nb && k >= l && k <= u - 1) {
                     const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
@@ -643,7 +647,7 @@ k_hqr_mb(int n, int bmax, const cplx* __restrict__ Hc_all, cplx* __restrict__ ei
                 }
             }
 #pragma unroll
-            for (int q = 0; q < MB_ITEMS; ++q) {
+            for (int q = 0; q < NITEMS; ++q) {
                 const int k = c_k0[q] + t, r = c_row[q];
                 if (k >= l && k <= u - 1 && r <= k) {
                     const int b = (l - c_k0[q]) / MB_D;
@@ -656,11 +660,11 @@ k_hqr_mb(int n, int bmax, const cplx* __restrict__ Hc_all, cplx* __restrict__ ei
                 }
             }
             __syncthreads();
-            c_C += clock64() - c_a;
         }
     }
-    if (tid == 0) info[f] = failed;
-    if (tid == 0 && f == 0) { g_dbg[0] = clock64() - c_t0; g_dbg[1] = c_pro; g_dbg[2] = c_R; g_dbg[3] = c_C; g_dbg[4] = n_b; g_dbg[5] = n_st; }
+    if (tid == 0) { info[f] = first_stage ? failed : info[f] + failed; ucur[f] = u; }
+    if (u >= 0)                                           // park the remaining leading block
+        for (int i = tid; i < hcol_size(u + 1); i += NT) Hpark[i] = H[i];
     (void)s_bulge;
 }
 
@@ -1148,9 +1152,32 @@ extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, c
         return (int)cudaGetLastError();
     }
     if (bulges > MB_MAX) bulges = MB_MAX;
+    // stage 1: whole matrix, 512 threads, one CTA per SM; stage 2: window fits twice into shared
+    // memory (512 threads, 64 registers, 2 CTAs per SM); stage 3: fits three times (384 threads,
+    // 56 registers, 3 CTAs per SM).  AXS_HQR_STAGES=1|2|3 limits the cascade (A/B testing).
+    const char* st_env = getenv("AXS_HQR_STAGES");
+    const int stages = st_env ? atoi(st_env) : 3;
+    auto fit = [&](int per_sm) {
+        int m = 0;
+        while (m + 1 <= n && hqr_mb_smem(m + 1) + 2048 <= (size_t)(227 * 1024 / per_sm)) ++m;
+        return m;
+    };
+    int m2 = (stages >= 2) ? fit(2) : 0, m3 = (stages >= 3) ? fit(3) : 0;
+    if (m2 >= n || m2 < 8) m2 = 0;
+    if (m3 >= m2 || m3 < 8) m3 = 0;
     size_t smem = hqr_mb_smem(n);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_hqr_mb<<<nf, MB_THREADS, smem, st>>>(n, bulges, wk.Hc, eig, info);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_hqr_mb<512, 1, 3><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || m2 == 0) return (int)e;
+    size_t smem2 = hqr_mb_smem(m2);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    k_hqr_mb<512, 2, 3><<<nf, 512, smem2, st>>>(n, bulges, 0, m3, wk.Hc, wk.Hp, eig, info, wk.ucur);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || m3 == 0) return (int)e;
+    size_t smem3 = hqr_mb_smem(m3);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<384, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    k_hqr_mb<384, 3, 3><<<nf, 384, smem3, st>>>(n, bulges, 0, 0, wk.Hc, wk.Hp, eig, info, wk.ucur);
     return (int)cudaGetLastError();
 }
 

@@ -166,7 +166,7 @@ def gpu_arm(args):
     per_kernel = {name: 0.0 for name in ev}
 
     def device_step(timed):
-        """Whole hot path with inputs resident in HBM: 6 kernel launches."""
+        """Whole hot path with inputs resident in HBM: 9 kernel launches."""
         P = nat._ptr
         ev['reduce'][0].record()
         nat.check(L.axs_reduce(N, ops.hb, P(ops.K0s), P(ops.Cb), P(ops.Mb), P(ops.K1c), P(ops.K6d), P(omega),
@@ -262,7 +262,7 @@ def gpu_arm(args):
                 'h2d_bytes_per_step': int(8 * nloc),
                 'd2h_bytes_per_step': int(nloc * n2 * 16 + (nloc - 1) * n2 * 12 + nloc * 4 + POINTS_PER_GPU * n2 * n2 * 16),
                 'k_only': {'value': nf_total / e2e_k_s, 'note': 'solve() without reading psi_hat back'}},
-        'gpu_launches': 6 * args.steps,
+        'gpu_launches': 9 * args.steps,   # reduce, hqr x3 stages, modes, backnorm, bpsi, track_gemm, apply_order
         'clocks': clocks.summary(),
         'hbm_peak_gbs': peaks.get('hbm_gbs'),
     }

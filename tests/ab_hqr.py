@@ -19,6 +19,8 @@ nat.check(L.axs_reduce(N, ops.hb, P(ops.K0s), P(ops.Cb), P(ops.Mb), P(ops.K1c), 
 G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), 0); op = so.operators(G, 0)
 ref = {i: so.eig_normalised(op, 2 * np.pi * c['f'][i])[0] for i in (0, nf // 2, nf - 1)}
 for bul in sys.argv[2:] or ['0', '2', '4', '6', '8']:
+    if ':' in bul:
+        bul, stg = bul.split(':'); os.environ['AXS_HQR_STAGES'] = stg
     os.environ['AXS_HQR_BULGES'] = bul
     best = 1e9
     for _ in range(3):
