@@ -253,8 +253,12 @@ def gpu_arm(args):
                    'l2': 'working set 1.5 GB per sweep >> 126 MB L2 (no flush needed)',
                    'parallelism': 'frequency axis sharded, %d rank(s), 1-point halo' % world},
         'kernel_ms': {k_: v / args.steps for k_, v in per_kernel.items()},
-        'roofline': {'bound': 'tensor', 'kernel': 'k_hqr', 'achieved': achieved, 'peak': fp64_peak,
-                     'unit': 'TFLOP/s', 'frac': achieved / fp64_peak, 'traffic': None,
+        'roofline': {'bound': 'tensor', 'kernel': 'k_hqr_mb (3 stages)', 'achieved': achieved, 'peak': fp64_peak,
+                     'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
+                     'traffic': {'dram_bytes_per_launch': int(nloc * 130112), 'unit': 'B',
+                                 'note': 'ncu --set full (profiles/r1_ncu_summary.csv): stage 1 reads 38.5 MB for 296 '
+                                         'matrices = the packed Hessenberg input once, writes ~0; stages 2/3 re-read the '
+                                         'parked leading block (33 + 22 MB)'},
                      'note': 'FP64 pipe (DFMA/DMMA share one roof on B200); algorithmic flops = 80*n2^3 per '
                              'point for the QR kernel (zhseqr share of F_alg = 100*n2^3); peak = ' + how,
                      'pipeline_frac': value / world * f_alg(n2) / 1e12 / fp64_peak},
