@@ -8,6 +8,7 @@
 //   k_apply_order column gather of k and psi once the permutation scan has run.
 //   axs_track_scan (host) the sequential integer scan o_i[r] = a_i[o_{i-1}[r]].
 #include "common.cuh"
+#include <stdlib.h>
 
 // Y[f][r][j]:  r <  N : K6[r] * psi[N + r][j]
 //              r >= N : K6[r-N] * psi[r-N][j] + sum_c C[r-N][c] psi[N + c][j]
@@ -111,6 +112,111 @@ k_track_gemm(int n, const cplx* __restrict__ psi_all, const cplx* __restrict__ Y
     }
 }
 
+// -----------------------------------------------------------------------------------------
+// k_track_mma: the same contraction P = psi_prev^T Y on the FP64 tensor path
+// (mma.sync.aligned.m8n8k4.f64, "DMMA"; tcgen05 has no FP64 kind).  A complex product is four
+// real MMAs per 8x8x4 tile: Pre += Are Bre + (-Aim) Bim,  Pim += Are Bim + Aim Bre.
+// CTA = 32 rows (a) x all columns (b <= 192), 8 warps; warp w owns the n8 column tiles
+// w, w+8, w+16 for all four m8 row tiles.  Shared tiles are padded so that the fragment loads
+// (4 k-rows x 8 columns per quarter-warp) are bank-conflict free.
+#define TM_KC 16
+#define TM_SA 34                       // row stride of sA in cplx (32 + 2 -> 544 B = 32 mod 128)
+#define TM_SB 194                      // row stride of sB in cplx (192 + 2)
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256)
+k_track_mma(int n, const cplx* __restrict__ psi_all, const cplx* __restrict__ Y_all,
+            int* __restrict__ arg_all, double* __restrict__ amax_all)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* sA = (cplx*)smem_raw;                       // [TM_KC][TM_SA]
+    cplx* sB = sA + TM_KC * TM_SA;                    // [TM_KC][TM_SB]
+    double* s_best = (double*)(sB + TM_KC * TM_SB);   // [8 warps][32 rows]
+    int* s_bidx = (int*)(s_best + 8 * 32);
+    const int p = blockIdx.y, a0 = blockIdx.x * 32;
+    const cplx* psiP = psi_all + (long long)p * n * n;
+    const cplx* Y = Y_all + (long long)(p + 1) * n * n;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int gq = lane >> 2, tq = lane & 3;          // groupID, thread-in-group
+    const int ntiles = (n + 7) >> 3;
+    double cre[4][3][2], cim[4][3][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) { cre[mt][t][0] = cre[mt][t][1] = 0.0; cim[mt][t][0] = cim[mt][t][1] = 0.0; }
+
+    for (int r0 = 0; r0 < n; r0 += TM_KC) {
+        for (int idx = tid; idx < TM_KC * 32; idx += 256) {
+            const int rr = idx >> 5, aa = idx & 31, r = r0 + rr, a = a0 + aa;
+            sA[rr * TM_SA + aa] = (r < n && a < n) ? psiP[(long long)r * n + a] : mk(0, 0);
+        }
+        for (int idx = tid; idx < TM_KC * 192; idx += 256) {
+            const int rr = idx / 192, bb = idx - rr * 192, r = r0 + rr;
+            sB[rr * TM_SB + bb] = (r < n && bb < n) ? Y[(long long)r * n + bb] : mk(0, 0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < TM_KC; ks += 4) {
+            cplx af[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) af[mt] = sA[(ks + tq) * TM_SA + mt * 8 + gq];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int nt = w + 8 * t;
+                if (nt < ntiles) {
+                    const cplx bf = sB[(ks + tq) * TM_SB + nt * 8 + gq];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) {
+                        dmma(cre[mt][t][0], cre[mt][t][1], af[mt].x, bf.x);
+                        dmma(cre[mt][t][0], cre[mt][t][1], -af[mt].y, bf.y);
+                        dmma(cim[mt][t][0], cim[mt][t][1], af[mt].x, bf.y);
+                        dmma(cim[mt][t][0], cim[mt][t][1], af[mt].y, bf.x);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // epilogue: row arg-max of |P|^2 (lowest column index wins ties, like np.argmax)
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        double best = -1.0;
+        int bi = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int nt = w + 8 * t;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int b = nt * 8 + 2 * tq + e;
+                const double m2 = (nt < ntiles && b < n) ? cre[mt][t][e] * cre[mt][t][e] + cim[mt][t][e] * cim[mt][t][e] : -1.0;
+                if (m2 > best || (m2 == best && b < bi)) { best = m2; bi = b; }
+            }
+        }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {              // across the 4 lanes of a group
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (tq == 0) { s_best[w * 32 + mt * 8 + gq] = best; s_bidx[w * 32 + mt * 8 + gq] = bi; }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        double best = s_best[tid];
+        int bi = s_bidx[tid];
+        for (int ww = 1; ww < 8; ++ww) {
+            const double ob = s_best[ww * 32 + tid];
+            const int oi = s_bidx[ww * 32 + tid];
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        const int a = a0 + tid;
+        if (a < n) { arg_all[(long long)p * n + a] = bi; amax_all[(long long)p * n + a] = sqrt(best); }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_apply_order(int n, const int* __restrict__ order, const cplx* __restrict__ k_in,
               const cplx* __restrict__ psi_in, cplx* __restrict__ k_out, cplx* __restrict__ psi_out)
@@ -169,7 +275,15 @@ extern "C" int axs_launch_track(int N, int hb, const cplx* Cb, const cplx* K6d, 
     k_bpsi<<<dim3(bx, npairs + 1), 256, 0, st>>>(N, hb, Cb, K6d, psi, Y);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    k_track_gemm<<<dim3((n + TR_TA - 1) / TR_TA, npairs), 256, 0, st>>>(n, psi, Y, arg, amax);
+    const char* env = getenv("AXS_TRACK_FMA");
+    if (env && atoi(env)) {                                // scalar-FMA tiles (kept for A/B)
+        k_track_gemm<<<dim3((n + TR_TA - 1) / TR_TA, npairs), 256, 0, st>>>(n, psi, Y, arg, amax);
+        return (int)cudaGetLastError();
+    }
+    size_t smem = (size_t)(TM_KC * TM_SA + TM_KC * TM_SB) * sizeof(cplx) + 8 * 32 * (sizeof(double) + sizeof(int));
+    e = cudaFuncSetAttribute(k_track_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    k_track_mma<<<dim3((n + 31) / 32, npairs), 256, smem, st>>>(n, psi, Y, arg, amax);
     return (int)cudaGetLastError();
 }
 
