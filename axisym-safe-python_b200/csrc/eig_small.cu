@@ -310,11 +310,9 @@ __device__ cplx wilkinson_shift(cplx* H, int i) {
     return t;
 }
 
-__device__ long long g_dbg[16];
 __global__ void __launch_bounds__(192, 1)
 k_hqr(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* __restrict__ info)
 {
-    long long c_pro = 0, c_left = 0, c_right = 0, n_sw = 0, n_rot = 0, c_t0 = clock64(), c_a;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.x, tid = threadIdx.x;
     const int hsz = hcol_size(n);
@@ -332,7 +330,6 @@ k_hqr(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* _
     int u = n - 1, its = 0, failed = 0;
     const int itmax = 60;
     while (u >= 0) {
-        c_a = clock64();
         // ---- deflation scan (parallel over subdiagonal entries) -------------------------
         if (tid == 0) s_l = 0;
         __syncthreads();
@@ -386,7 +383,6 @@ k_hqr(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* _
         }
         __syncthreads();
         const cplx sg = s_shift;
-        c_pro += clock64() - c_a; c_a = clock64(); n_sw++; n_rot += u - l;
 
         // ---- left rotations: systolic wavefront, thread j owns column j --------------------
         const bool mine = (tid >= l && tid <= u);
@@ -424,7 +420,6 @@ k_hqr(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* _
         }
         if (tid == u) HC(H, u, u) = carry;
         __syncthreads();
-        c_left += clock64() - c_a; c_a = clock64();
 
         // ---- right rotations: thread i owns row i -----------------------------------------
         if (mine) {
@@ -445,13 +440,10 @@ k_hqr(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* _
             HC(H, i, u) = left;
         }
         __syncthreads();
-        c_right += clock64() - c_a;
     }
     if (tid == 0) info[f] = failed;
-    if (tid == 0 && f == 0) { g_dbg[0] = clock64() - c_t0; g_dbg[1] = c_pro; g_dbg[2] = c_left; g_dbg[3] = c_right; g_dbg[4] = n_sw; g_dbg[5] = n_rot; }
 }
 
-extern "C" void axs_debug_counters(long long* out) { cudaMemcpyFromSymbol(out, g_dbg, sizeof(long long) * 16); }
 
 static size_t hqr_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(cplx); }
 
@@ -498,7 +490,6 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
     __shared__ cplx s_shift[MB_MAX];
     __shared__ cplx s_ra[2][MB_MAX], s_rb[2][MB_MAX];
     __shared__ double s_rr[2][MB_MAX];
-    __shared__ cplx s_bulge[MB_MAX];
 
     const cplx* Hg = (first_stage ? Hc_all : Hp_all) + (long long)f * hsz;
     cplx* Hpark = Hp_all + (long long)f * hsz;
@@ -665,7 +656,6 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
     if (tid == 0) { info[f] = first_stage ? failed : info[f] + failed; ucur[f] = u; }
     if (u >= 0)                                           // park the remaining leading block
         for (int i = tid; i < hcol_size(u + 1); i += NT) Hpark[i] = H[i];
-    (void)s_bulge;
 }
 
 static size_t hqr_mb_smem(int n) { return (size_t)hcol_size(n) * sizeof(cplx); }
@@ -706,10 +696,8 @@ k_hqr_ws(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int
     cplx* eig = eig_all + (long long)f * n;
     __syncthreads();
 
-    long long c_pro = 0, c_front = 0, c_tail = 0, n_sw = 0, n_rot = 0, c_t0 = clock64(), c_a;
     int u = n - 1, its = 0, failed = 0;
     while (u >= 0) {
-        c_a = clock64();
         if (tid == 0) s_l = 0;
         __syncthreads();
         if (tid >= 1 && tid <= u) {
@@ -761,7 +749,6 @@ k_hqr_ws(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int
         }
         __syncthreads();
         const cplx sg = s_shift;
-        c_pro += clock64() - c_a; c_a = clock64(); n_sw++; n_rot += u - l;
 
         if (tid < W) {
             // ================= left rotations: one column per thread =========================
@@ -826,7 +813,6 @@ k_hqr_ws(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int
                     HC(H, u, u) = carry;
                     __threadfence_block();
                     s_ready = u + 1;
-                    c_front += clock64() - c_a;
                 }
             }
         } else {
@@ -858,11 +844,8 @@ k_hqr_ws(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int
             }
         }
         __syncthreads();
-        c_tail += clock64() - c_a;
     }
     if (tid == 0) info[f] = failed;
-    if (tid == 0 && f == 0) { g_dbg[0] = clock64() - c_t0; g_dbg[1] = c_pro; g_dbg[3] = c_tail; g_dbg[4] = n_sw; g_dbg[5] = n_rot; }
-    if (f == 0 && c_front) atomicAdd((unsigned long long*)&g_dbg[2], (unsigned long long)c_front);
 }
 
 static size_t hqr_ws_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(cplx); }
@@ -902,7 +885,6 @@ k_modes(int N, int hb, const cplx* __restrict__ Cb, const cplx* __restrict__ K6d
     cplx* z = mul + (size_t)n * M;                        // [n][M]
     cplx* rbuf = z + (size_t)n * M;                       // [nw][MD_G][2][n]
     unsigned char* swp = (unsigned char*)(rbuf + (size_t)nw * MD_G * 2 * n);   // [n][M]
-    volatile int* prog = (volatile int*)(swp + (size_t)n * M);                 // [nw]
     cplx* myrow = rbuf + ((size_t)(w * MD_G + g) * 2) * n;
 
     const cplx* Hr = wk.Hr + (long long)f * hrow_size(n);
@@ -924,7 +906,6 @@ k_modes(int N, int hb, const cplx* __restrict__ Cb, const cplx* __restrict__ K6d
     // >= k+4, which are final (previous row iteration): they run as one tight loop for all four
     // groups at once.  The last three steps + the new column operation of row k need row k+1, i.e.
     // the previous group's result of this very iteration: the four tails run in group order.
-    (void)prog;
     auto step = [&](const cplx* row, int k, int j, cplx& carry, cplx& acc) {
         cplx a = row[j];
         if (j == k) a = csub(a, lam);
