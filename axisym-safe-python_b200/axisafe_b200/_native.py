@@ -19,6 +19,7 @@ _SIGNATURES = {
     'axs_version': (ctypes.c_int, []),
     'axs_strerror': (ctypes.c_char_p, [ctypes.c_int]),
     'axs_max_small_n2': (ctypes.c_int, []),
+    'axs_max_n2': (ctypes.c_int, []),
     'axs_element_matrices': (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p] * 6),
     'axs_assemble_operators': (ctypes.c_int, [ctypes.c_int] + [ctypes.c_void_p] * 5 +
                                [ctypes.c_int] * 3 + [ctypes.c_void_p] * 5),
@@ -250,6 +251,8 @@ def eig_sweep(ops, omega, want_modes=True, work=None, chunks=2):
     info = torch.zeros(nf, dtype=torch.int32, device='cuda')
     chunks = max(1, min(int(chunks), nf // 64 if nf >= 128 else 1))
     L = lib()
+    if n2 > L.axs_max_small_n2():
+        chunks = 1                       # large path: one CTA per frequency already fills the GPU
 
     def launch(lo, hi, buf, nbytes):
         check(L.axs_eig_sweep(ops.N, ops.hb, _ptr(ops.K0s), _ptr(ops.Cb), _ptr(ops.Mb), _ptr(ops.K1c),
@@ -278,6 +281,14 @@ def eig_sweep(ops, omega, want_modes=True, work=None, chunks=2):
     for c in range(chunks):
         main.wait_stream(_SIDE_STREAMS[c])
     return k, psi, info, work
+
+
+def eig_sweep_into(ops, omega, k, psi, info, work):
+    """axs_eig_sweep into caller-provided device buffers (large path, chunked sweeps)."""
+    torch = torch_cuda()
+    check(lib().axs_eig_sweep(ops.N, ops.hb, _ptr(ops.K0s), _ptr(ops.Cb), _ptr(ops.Mb), _ptr(ops.K1c),
+                              _ptr(ops.K6d), _ptr(omega), len(omega), _ptr(k), _ptr(psi), _ptr(info),
+                              _ptr(work.buf), work.bytes, _stream(torch)), 'axs_eig_sweep')
 
 
 def reduce_dense(S, N, nf, work=None):

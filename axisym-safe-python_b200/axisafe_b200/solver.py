@@ -115,9 +115,9 @@ class WaveElementAxisym(object):
         N, n2, nf = mesh.no_of_dofs, 2 * mesh.no_of_dofs, len(f)
         self.B = sps.bmat([[None, mesh.K6.tocsr()],
                            [mesh.K6.tocsr(), n * mesh.K4.tocsr() + self.K3_hat.tocsr()]])
-        if n2 > _native.lib().axs_max_small_n2():
-            raise NotImplementedError('2N = %d exceeds the shared-memory eigen kernels (2N <= %d)'
-                                      % (n2, _native.lib().axs_max_small_n2()))
+        if n2 > _native.lib().axs_max_n2():
+            raise NotImplementedError('2N = %d exceeds the largest supported problem (2N <= %d)'
+                                      % (n2, _native.lib().axs_max_n2()))
 
         rank, world = 0, 1
         if distributed in ('auto', True):
@@ -132,12 +132,16 @@ class WaveElementAxisym(object):
         # host -> device: this rank's angular frequencies (with the halo point in front)
         omega = torch.from_numpy(self.w[lo - halo:hi].copy()).cuda()
         nloc = hi - lo + halo
-        k_nat, psi_nat, info, work = _native.eig_sweep(ops, omega, want_modes=True)
-        if nloc > 1:
-            arg, amax = _native.track_pairs(ops, psi_nat, nloc - 1, scratch=work.buf)
+        if n2 > _native.lib().axs_max_small_n2():
+            # large path: matrices stream from HBM, the sweep is cut into memory-sized chunks
+            k_nat, psi_nat, info, arg, amax = _sweep_large(torch, _native, ops, omega, halo)
         else:
-            arg = torch.empty(0, dtype=torch.int32, device='cuda')
-            amax = torch.empty(0, dtype=torch.float64, device='cuda')
+            k_nat, psi_nat, info, work = _native.eig_sweep(ops, omega, want_modes=True)
+            if nloc > 1:
+                arg, amax = _native.track_pairs(ops, psi_nat, nloc - 1, scratch=work.buf)
+            else:
+                arg = torch.empty(0, dtype=torch.int32, device='cuda')
+                amax = torch.empty(0, dtype=torch.float64, device='cuda')
         k_loc = k_nat.view(nloc, n2)[halo:]
         info_loc = info[halo:]
         if world > 1:
@@ -158,10 +162,18 @@ class WaveElementAxisym(object):
         self.k = np.take_along_axis(k_host, self.order.astype(np.int64), axis=1)
         # reorder this rank's mode shapes on the device; they are copied out lazily
         order_loc = np.ascontiguousarray(self.order[lo:hi])
-        psi_loc = psi_nat.view(nloc, n2 * n2)[halo:].reshape(-1)
-        _, psi_sorted = _native.apply_order(n2, hi - lo, order_loc, k_nat.view(nloc, n2)[halo:].reshape(-1),
-                                            psi_loc)
-        self._psi = _LazyModes(psi_sorted, (hi - lo, n2, n2), lo, nf)
+        if psi_nat is None:
+            # the mode shapes of the whole block do not fit in HBM (the reference's psi_hat would be
+            # nf x 2N x 2N x 16 B of host memory): eigenvalues and tracking are complete, shapes are not kept
+            self._psi = None
+        elif n2 > _native.lib().axs_max_small_n2():
+            self._psi = _LazyModes(_reorder_in_place(torch, _native, n2, order_loc, psi_nat, halo),
+                                   (hi - lo, n2, n2), lo, nf)
+        else:
+            psi_loc = psi_nat.view(nloc, n2 * n2)[halo:].reshape(-1)
+            _, psi_sorted = _native.apply_order(n2, hi - lo, order_loc,
+                                                k_nat.view(nloc, n2)[halo:].reshape(-1), psi_loc)
+            self._psi = _LazyModes(psi_sorted, (hi - lo, n2, n2), lo, nf)
         self.evaluated = True
         self.k_ready = 0
 
@@ -221,6 +233,71 @@ class WaveElementAxisym(object):
         k[k.imag > .1] = 0
         self.propagating_indices = np.where(~(k == 0).all(0))[0]
         self.k_ready = k[:, self.propagating_indices]
+
+
+def _sweep_large(torch, _native, ops, omega, halo):
+    """Chunked sweep for 2N above the shared-memory kernels (eig_big.cu).
+
+    The per-frequency workspace is ~32 (2N)^2 bytes, so the frequency block is processed in
+    chunks sized from the free HBM; consecutive chunks overlap by one frequency whose mode
+    shapes are carried over (not recomputed) for the tracking pair at the seam.  Returns the
+    same tables as the one-shot path; ``psi`` is None when the whole block of mode shapes does
+    not fit next to the workspace.
+    """
+    n2, nloc = 2 * ops.N, len(omega)
+    L = _native.lib()
+    free, _ = torch.cuda.mem_get_info()
+    per_mat = n2 * n2 * 16
+    keep = nloc * per_mat <= 0.45 * free
+    budget = 0.8 * (free - (nloc * per_mat if keep else 0))
+    fixed = int(L.axs_eig_worksize(ops.N, 1))
+    slope = int(L.axs_eig_worksize(ops.N, 2)) - fixed
+    fixed -= slope
+    # per chunk of C frequencies: workspace + (C + 1) mode-shape slots + (C + 1) slots of Y = B psi
+    C = int((budget - fixed - 2 * per_mat) // (slope + 2 * per_mat))
+    if C < 1:
+        raise MemoryError('2N = %d: one frequency needs %.1f GB of HBM workspace' % (n2, (fixed + slope) / 1e9))
+    C = min(C, nloc)
+    k = torch.empty(nloc * n2, dtype=torch.complex128, device='cuda')
+    info = torch.zeros(nloc, dtype=torch.int32, device='cuda')
+    arg = torch.empty(max(nloc - 1, 0) * n2, dtype=torch.int32, device='cuda')
+    amax = torch.empty(max(nloc - 1, 0) * n2, dtype=torch.float64, device='cuda')
+    psi_all = torch.empty(nloc * n2 * n2, dtype=torch.complex128, device='cuda') if keep else None
+    work = _native.EigWorkspace(ops.N, C)
+    slots = torch.empty((C + 1) * n2 * n2, dtype=torch.complex128, device='cuda')
+    nn = n2 * n2
+    for c0 in range(0, nloc, C):
+        c1 = min(c0 + C, nloc)
+        cur = slots[nn:(c1 - c0 + 1) * nn]
+        _native.eig_sweep_into(ops, omega[c0:c1], k[c0 * n2:c1 * n2], cur, info[c0:c1], work)
+        first = 0 if c0 > 0 else 1                    # slot 0 holds the last frequency of the previous chunk
+        npairs = (c1 - c0) - first
+        if npairs > 0:
+            a, m = _native.track_pairs(ops, slots[first * nn:(c1 - c0 + 1) * nn], npairs)
+            p0 = c0 - 1 + first
+            arg[p0 * n2:(p0 + npairs) * n2] = a
+            amax[p0 * n2:(p0 + npairs) * n2] = m
+        if keep:
+            psi_all[c0 * nn:c1 * nn] = cur
+        if c1 < nloc:
+            slots[:nn] = slots[(c1 - c0) * nn:(c1 - c0 + 1) * nn].clone()
+    return k, psi_all, info, arg, amax
+
+
+def _reorder_in_place(torch, _native, n2, order_loc, psi_nat, halo):
+    """Tracked column order applied frequency block by block (no second full-size copy)."""
+    nn = n2 * n2
+    psi = psi_nat[halo * nn:]
+    nf = order_loc.shape[0]
+    step = max(1, min(nf, (1 << 30) // (nn * 16)))
+    dummy = torch.empty(step * n2, dtype=torch.complex128, device='cuda')
+    for c0 in range(0, nf, step):
+        c1 = min(c0 + step, nf)
+        blk = psi[c0 * nn:c1 * nn]
+        _, out = _native.apply_order(n2, c1 - c0, np.ascontiguousarray(order_loc[c0:c1]),
+                                     dummy[:(c1 - c0) * n2], blk)
+        blk.copy_(out)
+    return psi
 
 
 def _gather_blocks(torch, bounds, rank, n2, k_loc, arg_loc, amax_loc, info_loc):

@@ -17,6 +17,11 @@ int axs_launch_modes(int, int, const cplx*, const cplx*, int, const cplx*, cplx*
 int axs_launch_unpack(int, int, AxsWork, cplx*, cudaStream_t);
 int axs_launch_track(int, int, const cplx*, const cplx*, const cplx*, int, cplx*, int*, double*, cudaStream_t);
 int axs_launch_apply_order(int, int, const int*, const cplx*, const cplx*, cplx*, cplx*, cudaStream_t);
+int axs_launch_reduce_big(int, int, const cplx*, const cplx*, const cplx*, const cplx*, const cplx*,
+                          const double*, int, const cplx*, AxsWorkBig, cudaStream_t);
+int axs_launch_hqr_big(int, int, cplx*, int*, AxsWorkBig, cudaStream_t);
+int axs_launch_modes_big(int, int, const cplx*, const cplx*, int, const cplx*, cplx*, AxsWorkBig, cudaStream_t);
+int axs_launch_unpack_big(int, int, AxsWorkBig, cplx*, cudaStream_t);
 int axs_launch_energy_ratio(int, int, const cplx*, const int*, int, const int*, const int*, const cplx*,
                             int, const int*, const int*, const cplx*, double*, cudaStream_t);
 }
@@ -29,12 +34,14 @@ extern "C" const char* axs_strerror(int code)
 {
     static __thread char buf[96];
     if (code == 0) return "success";
-    if (code == AXS_ERR_TOO_LARGE) return "problem size 2N exceeds the shared-memory eigen path (axs_max_small_n2)";
+    if (code == AXS_ERR_TOO_LARGE) return "problem size 2N exceeds the largest supported size (axs_max_n2)";
     if (code < 0) { snprintf(buf, sizeof buf, "invalid argument %d", -code); return buf; }
     return cudaGetErrorString((cudaError_t)code);
 }
 
 extern "C" int axs_max_small_n2(void) { return AXS_MAX_SMALL_N2; }
+extern "C" int axs_max_n2(void) { return AXS_MAX_BIG_N2; }
+static inline bool is_big(int N) { return 2 * N > AXS_MAX_SMALL_N2; }
 
 extern "C" int axs_element_matrices(int n_elem, const int* edesc_i, const double* edesc_d,
                                     const double* tables, const double* nodes, axs_cplx* out, void* stream)
@@ -96,6 +103,7 @@ extern "C" int axs_build_S(int N, int hb, const axs_cplx* K0s, const axs_cplx* C
 extern "C" long long axs_eig_worksize(int N, int nf)
 {
     if (N <= 0 || nf <= 0) return 0;
+    if (is_big(N)) return axs_work_layout_big(2 * N, nf, nullptr, nullptr);
     return axs_work_layout(2 * N, nf, nullptr, nullptr);
 }
 
@@ -104,7 +112,7 @@ extern "C" int axs_reduce(int N, int hb, const axs_cplx* K0s, const axs_cplx* Cb
                           const axs_cplx* S_in, void* work, long long work_bytes, void* stream)
 {
     if (N <= 0) return -1;
-    if (2 * N > AXS_MAX_SMALL_N2) return AXS_ERR_TOO_LARGE;
+    if (2 * N > AXS_MAX_BIG_N2) return AXS_ERR_TOO_LARGE;
     if (!S_in) {
         int rc = check_ops(N, hb, K0s, Cb, Mb, K6d);
         if (rc) return rc;
@@ -113,6 +121,12 @@ extern "C" int axs_reduce(int N, int hb, const axs_cplx* K0s, const axs_cplx* Cb
     if (nf <= 0) return -9;
     if (!work) return -11;
     if (work_bytes < axs_eig_worksize(N, nf)) return -12;
+    if (is_big(N)) {
+        AxsWorkBig wb;
+        axs_work_layout_big(2 * N, nf, work, &wb);
+        return axs_launch_reduce_big(N, hb, (const cplx*)K0s, (const cplx*)Cb, (const cplx*)Mb, (const cplx*)K1c,
+                                     (const cplx*)K6d, omega, nf, (const cplx*)S_in, wb, (cudaStream_t)stream);
+    }
     AxsWork wk;
     axs_work_layout(2 * N, nf, work, &wk);
     return axs_launch_reduce(N, hb, (const cplx*)K0s, (const cplx*)Cb, (const cplx*)Mb, (const cplx*)K1c,
@@ -122,12 +136,17 @@ extern "C" int axs_reduce(int N, int hb, const axs_cplx* K0s, const axs_cplx* Cb
 extern "C" int axs_hqr(int N, int nf, axs_cplx* k, int* info, void* work, long long work_bytes, void* stream)
 {
     if (N <= 0) return -1;
-    if (2 * N > AXS_MAX_SMALL_N2) return AXS_ERR_TOO_LARGE;
+    if (2 * N > AXS_MAX_BIG_N2) return AXS_ERR_TOO_LARGE;
     if (nf <= 0) return -2;
     if (!k) return -3;
     if (!info) return -4;
     if (!work) return -5;
     if (work_bytes < axs_eig_worksize(N, nf)) return -6;
+    if (is_big(N)) {
+        AxsWorkBig wb;
+        axs_work_layout_big(2 * N, nf, work, &wb);
+        return axs_launch_hqr_big(2 * N, nf, (cplx*)k, info, wb, (cudaStream_t)stream);
+    }
     AxsWork wk;
     axs_work_layout(2 * N, nf, work, &wk);
     return axs_launch_hqr(2 * N, nf, (cplx*)k, info, wk, (cudaStream_t)stream);
@@ -137,7 +156,7 @@ extern "C" int axs_modes(int N, int hb, const axs_cplx* Cb, const axs_cplx* K6d,
                          const axs_cplx* k, axs_cplx* psi, void* work, long long work_bytes, void* stream)
 {
     if (N <= 0) return -1;
-    if (2 * N > AXS_MAX_SMALL_N2) return AXS_ERR_TOO_LARGE;
+    if (2 * N > AXS_MAX_BIG_N2) return AXS_ERR_TOO_LARGE;
     if (hb < 0) return -2;
     if (!Cb) return -3;
     if (!K6d) return -4;
@@ -146,6 +165,12 @@ extern "C" int axs_modes(int N, int hb, const axs_cplx* Cb, const axs_cplx* K6d,
     if (!psi) return -7;
     if (!work) return -8;
     if (work_bytes < axs_eig_worksize(N, nf)) return -9;
+    if (is_big(N)) {
+        AxsWorkBig wb;
+        axs_work_layout_big(2 * N, nf, work, &wb);
+        return axs_launch_modes_big(N, hb, (const cplx*)Cb, (const cplx*)K6d, nf, (const cplx*)k, (cplx*)psi, wb,
+                                    (cudaStream_t)stream);
+    }
     AxsWork wk;
     axs_work_layout(2 * N, nf, work, &wk);
     return axs_launch_modes(N, hb, (const cplx*)Cb, (const cplx*)K6d, nf, (const cplx*)k, (cplx*)psi, wk,
@@ -172,6 +197,15 @@ extern "C" int axs_get_reduction(int N, int nf, const void* work, double* scale,
     if (N <= 0) return -1;
     if (nf <= 0) return -2;
     if (!work) return -3;
+    if (is_big(N)) {
+        AxsWorkBig wb;
+        axs_work_layout_big(2 * N, nf, (void*)work, &wb);
+        if (scale)
+            AXS_CUDA_OK(cudaMemcpyAsync(scale, wb.scale, (size_t)nf * 2 * N * sizeof(double),
+                                        cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        if (H) return axs_launch_unpack_big(2 * N, nf, wb, (cplx*)H, (cudaStream_t)stream);
+        return 0;
+    }
     AxsWork wk;
     axs_work_layout(2 * N, nf, (void*)work, &wk);
     if (scale)
@@ -192,7 +226,7 @@ extern "C" int axs_track_pairs(int N, int hb, const axs_cplx* Cb, const axs_cplx
                                void* stream)
 {
     if (N <= 0) return -1;
-    if (2 * N > 192) return AXS_ERR_TOO_LARGE;
+    if (2 * N > AXS_MAX_BIG_N2) return AXS_ERR_TOO_LARGE;
     if (hb < 0) return -2;
     if (!Cb) return -3;
     if (!K6d) return -4;

@@ -60,6 +60,62 @@ AXS_HD int hrow_off(int i, int n) { return i == 0 ? 0 : n + (i - 1) * (n + 1) - 
 AXS_HD int hrow_first(int i) { return i == 0 ? 0 : i - 1; }
 AXS_HD int hrow_size(int n) { return hrow_off(n - 1, n) + 2; }
 
+// ---- device helpers shared by eig_small.cu / eig_big.cu ----------------------------------
+#ifdef __CUDACC__
+#define EPS_D 2.220446049250313e-16
+#define SMALL_D (2.2250738585072014e-308 / EPS_D)
+
+__device__ __forceinline__ cplx band_get(const cplx* __restrict__ B, int W, int hb, int r, int c) {
+    int d = c - r;
+    return (d < -hb || d > hb) ? mk(0, 0) : B[(long long)r * W + d + hb];
+}
+
+__device__ __forceinline__ cplx companion_entry(int N, int hb, const cplx* K0s, const cplx* Cb,
+                                                const cplx* Mb, const cplx* K1c, const cplx* K6d,
+                                                double w, int r, int c)
+{
+    const int W = 2 * hb + 1;
+    if (r >= N) return mk((r - N == c) ? 1.0 : 0.0, 0.0);
+    cplx num;
+    if (c < N) {
+        if (c - r < -hb || c - r > hb) return mk(0, 0);
+        num = band_get(Cb, W, hb, r, c);
+    } else {
+        int cc = c - N;
+        if (cc - r < -hb || cc - r > hb) return mk(0, 0);
+        num = band_get(K0s, W, hb, r, cc);
+        num = cfma(mk(-w * w, 0), band_get(Mb, W, hb, r, cc), num);
+        if (K1c) num = cfma(mk(0, w), band_get(K1c, W, hb, r, cc), num);
+    }
+    return cneg(cdiv(num, K6d[r]));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sumf(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ cplx warp_csum(cplx v) {
+    v.x = warp_sum(v.x); v.y = warp_sum(v.y);
+    return v;
+}
+
+__device__ __forceinline__ cplx& HC(cplx* H, int i, int j) { return H[hcol_off(j) + i]; }
+
+__device__ __forceinline__ void make_rot(cplx x, cplx y, cplx& a, cplx& b, double& r) {
+    const double r2 = cabs2(x) + cabs2(y);
+    if (r2 > 0.0) {
+        const double ir = rsqrt(r2);
+        a = mk(x.x * ir, -x.y * ir);
+        b = mk(y.x * ir, -y.y * ir);
+        r = r2 * ir;
+    } else { a = mk(1, 0); b = mk(0, 0); r = 0.0; }
+}
+#endif
+
 #define AXS_CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
 // limits of the shared-memory ("small") eigen path
@@ -102,5 +158,53 @@ static inline long long axs_work_layout(int n2, int nf, void* base, AxsWork* w) 
     off += axs_align((long long)nf * sizeof(int));
     if (w) w->Hp = (cplx*)(b + off);
     off += szHc;
+    return off;
+}
+
+// ---- global-memory ("large", 2N > AXS_MAX_SMALL_N2) eigen path -------------------------------
+// Largest 2N the large path accepts (per-thread register slots of k_modes_col / k_backx_big).
+#define AXS_MAX_BIG_N2 8192
+#define AXS_BIG_MODE_GRID 592           // persistent CTAs of k_modes_col (4 per SM)
+
+struct AxsWorkBig {
+    cplx*   A;      // [nf][n2*n2]  dense column-major work matrix (S -> reflectors below subdiag)
+    cplx*   Hc;     // [nf][hcol_size] packed column-major Hessenberg, QR works in place here
+                    //                 (holds the fp32 |a_ij|^2 tables while balancing)
+    cplx*   Hm;     // [nf][hcol_size] second packed copy: input of the inverse iteration
+    cplx*   tau;    // [nf][n2]        tau[n2-1].x = max |H_ij|
+    double* scale;  // [nf][n2]
+    int*    ucur;   // [nf]
+    cplx*   yw;     // [nf][2*n2]      y = A^H v and w = A v of the Householder update
+    unsigned char* msc;   // per-CTA scratch of k_modes_col (multipliers, pivots, z, x)
+    long long msc_stride; // bytes per CTA
+};
+
+// modes per CTA of k_modes_col for a given problem size
+static inline int axs_big_modes_per_cta(int n2) { return n2 <= 512 ? 4 : n2 <= 1024 ? 2 : 1; }
+
+static inline long long axs_work_layout_big(int n2, int nf, void* base, AxsWorkBig* w) {
+    long long off = 0;
+    char* b = (char*)base;
+    const long long szA = axs_align((long long)nf * n2 * n2 * sizeof(cplx));
+    const long long szH = axs_align((long long)nf * hcol_size(n2) * sizeof(cplx));
+    const long long szT = axs_align((long long)nf * n2 * sizeof(cplx));
+    const long long szS = axs_align((long long)nf * n2 * sizeof(double));
+    const long long stride = axs_align((long long)axs_big_modes_per_cta(n2) * n2 * (3 * sizeof(cplx) + 1));
+    if (w) w->A = (cplx*)(b + off);
+    off += szA;
+    if (w) w->Hc = (cplx*)(b + off);
+    off += szH;
+    if (w) w->Hm = (cplx*)(b + off);
+    off += szH;
+    if (w) w->tau = (cplx*)(b + off);
+    off += szT;
+    if (w) w->scale = (double*)(b + off);
+    off += szS;
+    if (w) w->ucur = (int*)(b + off);
+    off += axs_align((long long)nf * sizeof(int));
+    if (w) w->yw = (cplx*)(b + off);
+    off += 2 * szT;
+    if (w) { w->msc = (unsigned char*)(b + off); w->msc_stride = stride; }
+    off += stride * AXS_BIG_MODE_GRID;
     return off;
 }

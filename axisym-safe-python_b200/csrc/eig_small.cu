@@ -21,47 +21,6 @@
 #include "common.cuh"
 #include <stdlib.h>
 
-#define EPS_D 2.220446049250313e-16
-#define SMALL_D (2.2250738585072014e-308 / EPS_D)
-
-__device__ __forceinline__ cplx band_get(const cplx* __restrict__ B, int W, int hb, int r, int c) {
-    int d = c - r;
-    return (d < -hb || d > hb) ? mk(0, 0) : B[(long long)r * W + d + hb];
-}
-
-__device__ __forceinline__ cplx companion_entry(int N, int hb, const cplx* K0s, const cplx* Cb,
-                                                const cplx* Mb, const cplx* K1c, const cplx* K6d,
-                                                double w, int r, int c)
-{
-    const int W = 2 * hb + 1;
-    if (r >= N) return mk((r - N == c) ? 1.0 : 0.0, 0.0);
-    cplx num;
-    if (c < N) {
-        if (c - r < -hb || c - r > hb) return mk(0, 0);
-        num = band_get(Cb, W, hb, r, c);
-    } else {
-        int cc = c - N;
-        if (cc - r < -hb || cc - r > hb) return mk(0, 0);
-        num = band_get(K0s, W, hb, r, cc);
-        num = cfma(mk(-w * w, 0), band_get(Mb, W, hb, r, cc), num);
-        if (K1c) num = cfma(mk(0, w), band_get(K1c, W, hb, r, cc), num);
-    }
-    return cneg(cdiv(num, K6d[r]));
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ float warp_sumf(float v) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ cplx warp_csum(cplx v) {
-    v.x = warp_sum(v.x); v.y = warp_sum(v.y);
-    return v;
-}
-
 // =========================================================================================
 // k_reduce
 // =========================================================================================
@@ -288,7 +247,6 @@ static size_t reduce_smem(int n) {
 // =========================================================================================
 // k_hqr
 // =========================================================================================
-__device__ __forceinline__ cplx& HC(cplx* H, int i, int j) { return H[hcol_off(j) + i]; }
 
 __device__ cplx wilkinson_shift(cplx* H, int i) {
     // eigenvalue of the trailing 2x2 closer to H(i,i)  (zlahqr)
@@ -462,16 +420,6 @@ static size_t hqr_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(c
 #define MB_THREADS 512
 #define MB_WORKERS (MB_THREADS - 32)
 #define MB_ITEMS 3                      // ceil(MB_MAX * (AXS_MAX_SMALL_N2 + 1) / MB_THREADS)
-
-__device__ __forceinline__ void make_rot(cplx x, cplx y, cplx& a, cplx& b, double& r) {
-    const double r2 = cabs2(x) + cabs2(y);
-    if (r2 > 0.0) {
-        const double ir = rsqrt(r2);
-        a = mk(x.x * ir, -x.y * ir);
-        b = mk(y.x * ir, -y.y * ir);
-        r = r2 * ir;
-    } else { a = mk(1, 0); b = mk(0, 0); r = 0.0; }
-}
 
 // Staging: the active window only shrinks, so the sweep is cut into stages with a smaller
 // shared-memory footprint each; a stage stops once the window is <= m_stop, parks the leading
@@ -1113,6 +1061,37 @@ extern "C" int axs_launch_reduce(int N, int hb, const cplx* K0s, const cplx* Cb,
     return (int)cudaGetLastError();
 }
 
+// Largest active window whose packed storage fits `per_sm` times into the shared memory of an SM.
+extern "C" int axs_hqr_stage_capacity(int per_sm)
+{
+    int m = 0;
+    while (hqr_mb_smem(m + 1) + 2048 <= (size_t)(227 * 1024 / per_sm)) ++m;
+    return m;
+}
+
+// Stages 2 and 3 of the QR cascade: resume from the leading blocks parked in Hp (active window
+// <= m_first, top index in ucur) with 2, then 3 CTAs per SM.  Also the tail of the large path.
+extern "C" int axs_launch_hqr_stages(int n, int nf, int m_first, cplx* Hp, cplx* eig, int* info, int* ucur,
+                                     cudaStream_t st)
+{
+    const char* st_env = getenv("AXS_HQR_STAGES");
+    const int stages = st_env ? atoi(st_env) : 3;
+    const char* mode = getenv("AXS_HQR_BULGES");
+    int bulges = mode ? atoi(mode) : MB_MAX;
+    if (bulges < 1 || bulges > MB_MAX) bulges = MB_MAX;
+    int m3 = (stages >= 3) ? axs_hqr_stage_capacity(3) : 0;
+    if (m3 >= m_first || m3 < 8) m3 = 0;
+    size_t smem2 = hqr_mb_smem(m_first);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    k_hqr_mb<512, 2, 3><<<nf, 512, smem2, st>>>(n, bulges, 0, m3, Hp, Hp, eig, info, ucur);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || m3 == 0) return (int)e;
+    size_t smem3 = hqr_mb_smem(m3);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<384, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    k_hqr_mb<384, 3, 3><<<nf, 384, smem3, st>>>(n, bulges, 0, 0, Hp, Hp, eig, info, ucur);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, cudaStream_t st)
 {
     const char* mode = getenv("AXS_HQR_BULGES");
@@ -1138,28 +1117,14 @@ extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, c
     // 56 registers, 3 CTAs per SM).  AXS_HQR_STAGES=1|2|3 limits the cascade (A/B testing).
     const char* st_env = getenv("AXS_HQR_STAGES");
     const int stages = st_env ? atoi(st_env) : 3;
-    auto fit = [&](int per_sm) {
-        int m = 0;
-        while (m + 1 <= n && hqr_mb_smem(m + 1) + 2048 <= (size_t)(227 * 1024 / per_sm)) ++m;
-        return m;
-    };
-    int m2 = (stages >= 2) ? fit(2) : 0, m3 = (stages >= 3) ? fit(3) : 0;
+    int m2 = (stages >= 2) ? axs_hqr_stage_capacity(2) : 0;
     if (m2 >= n || m2 < 8) m2 = 0;
-    if (m3 >= m2 || m3 < 8) m3 = 0;
     size_t smem = hqr_mb_smem(n);
     AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_hqr_mb<512, 1, 3><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || m2 == 0) return (int)e;
-    size_t smem2 = hqr_mb_smem(m2);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    k_hqr_mb<512, 2, 3><<<nf, 512, smem2, st>>>(n, bulges, 0, m3, wk.Hc, wk.Hp, eig, info, wk.ucur);
-    e = cudaGetLastError();
-    if (e != cudaSuccess || m3 == 0) return (int)e;
-    size_t smem3 = hqr_mb_smem(m3);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<384, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    k_hqr_mb<384, 3, 3><<<nf, 384, smem3, st>>>(n, bulges, 0, 0, wk.Hc, wk.Hp, eig, info, wk.ucur);
-    return (int)cudaGetLastError();
+    return axs_launch_hqr_stages(n, nf, m2, wk.Hp, eig, info, wk.ucur, st);
 }
 
 extern "C" int axs_launch_modes(int N, int hb, const cplx* Cb, const cplx* K6d, int nf,

@@ -141,79 +141,91 @@ k_track_mma(int n, const cplx* __restrict__ psi_all, const cplx* __restrict__ Y_
     const cplx* Y = Y_all + (long long)(p + 1) * n * n;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int gq = lane >> 2, tq = lane & 3;          // groupID, thread-in-group
-    const int ntiles = (n + 7) >> 3;
-    double cre[4][3][2], cim[4][3][2];
+    double best[4];
+    int bidx[4];
 #pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-        for (int t = 0; t < 3; ++t) { cre[mt][t][0] = cre[mt][t][1] = 0.0; cim[mt][t][0] = cim[mt][t][1] = 0.0; }
+    for (int mt = 0; mt < 4; ++mt) { best[mt] = -1.0; bidx[mt] = 0; }
 
-    for (int r0 = 0; r0 < n; r0 += TM_KC) {
-        for (int idx = tid; idx < TM_KC * 32; idx += 256) {
-            const int rr = idx >> 5, aa = idx & 31, r = r0 + rr, a = a0 + aa;
-            sA[rr * TM_SA + aa] = (r < n && a < n) ? psiP[(long long)r * n + a] : mk(0, 0);
-        }
-        for (int idx = tid; idx < TM_KC * 192; idx += 256) {
-            const int rr = idx / 192, bb = idx - rr * 192, r = r0 + rr;
-            sB[rr * TM_SB + bb] = (r < n && bb < n) ? Y[(long long)r * n + bb] : mk(0, 0);
-        }
-        __syncthreads();
+    // columns b in chunks of 192 (one chunk for the shared-memory eigen path, 2N <= 166)
+    for (int b0 = 0; b0 < n; b0 += 192) {
+        const int nbc = (n - b0 < 192) ? n - b0 : 192;
+        const int ntiles = (nbc + 7) >> 3;
+        double cre[4][3][2], cim[4][3][2];
 #pragma unroll
-        for (int ks = 0; ks < TM_KC; ks += 4) {
-            cplx af[4];
+        for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) af[mt] = sA[(ks + tq) * TM_SA + mt * 8 + gq];
+            for (int t = 0; t < 3; ++t) { cre[mt][t][0] = cre[mt][t][1] = 0.0; cim[mt][t][0] = cim[mt][t][1] = 0.0; }
+
+        for (int r0 = 0; r0 < n; r0 += TM_KC) {
+            for (int idx = tid; idx < TM_KC * 32; idx += 256) {
+                const int rr = idx >> 5, aa = idx & 31, r = r0 + rr, a = a0 + aa;
+                sA[rr * TM_SA + aa] = (r < n && a < n) ? psiP[(long long)r * n + a] : mk(0, 0);
+            }
+            for (int idx = tid; idx < TM_KC * 192; idx += 256) {
+                const int rr = idx / 192, bb = idx - rr * 192, r = r0 + rr;
+                sB[rr * TM_SB + bb] = (r < n && bb < nbc) ? Y[(long long)r * n + b0 + bb] : mk(0, 0);
+            }
+            __syncthreads();
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const int nt = w + 8 * t;
-                if (nt < ntiles) {
-                    const cplx bf = sB[(ks + tq) * TM_SB + nt * 8 + gq];
+            for (int ks = 0; ks < TM_KC; ks += 4) {
+                cplx af[4];
 #pragma unroll
-                    for (int mt = 0; mt < 4; ++mt) {
-                        dmma(cre[mt][t][0], cre[mt][t][1], af[mt].x, bf.x);
-                        dmma(cre[mt][t][0], cre[mt][t][1], -af[mt].y, bf.y);
-                        dmma(cim[mt][t][0], cim[mt][t][1], af[mt].x, bf.y);
-                        dmma(cim[mt][t][0], cim[mt][t][1], af[mt].y, bf.x);
+                for (int mt = 0; mt < 4; ++mt) af[mt] = sA[(ks + tq) * TM_SA + mt * 8 + gq];
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int nt = w + 8 * t;
+                    if (nt < ntiles) {
+                        const cplx bf = sB[(ks + tq) * TM_SB + nt * 8 + gq];
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) {
+                            dmma(cre[mt][t][0], cre[mt][t][1], af[mt].x, bf.x);
+                            dmma(cre[mt][t][0], cre[mt][t][1], -af[mt].y, bf.y);
+                            dmma(cim[mt][t][0], cim[mt][t][1], af[mt].x, bf.y);
+                            dmma(cim[mt][t][0], cim[mt][t][1], af[mt].y, bf.x);
+                        }
                     }
                 }
             }
+            __syncthreads();
         }
-        __syncthreads();
+        // running row arg-max of |P|^2 (lowest column index wins ties, like np.argmax)
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int nt = w + 8 * t;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int bl = nt * 8 + 2 * tq + e;
+                    const double m2 = (nt < ntiles && bl < nbc) ? cre[mt][t][e] * cre[mt][t][e] + cim[mt][t][e] * cim[mt][t][e] : -1.0;
+                    const int b = b0 + bl;
+                    if (m2 > best[mt] || (m2 == best[mt] && b < bidx[mt])) { best[mt] = m2; bidx[mt] = b; }
+                }
+            }
     }
-    // epilogue: row arg-max of |P|^2 (lowest column index wins ties, like np.argmax)
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
-        double best = -1.0;
-        int bi = 0;
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const int nt = w + 8 * t;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int b = nt * 8 + 2 * tq + e;
-                const double m2 = (nt < ntiles && b < n) ? cre[mt][t][e] * cre[mt][t][e] + cim[mt][t][e] * cim[mt][t][e] : -1.0;
-                if (m2 > best || (m2 == best && b < bi)) { best = m2; bi = b; }
-            }
-        }
+        double bb = best[mt];
+        int bi = bidx[mt];
 #pragma unroll
         for (int o = 1; o <= 2; o <<= 1) {              // across the 4 lanes of a group
-            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const double ob = __shfl_xor_sync(0xffffffffu, bb, o);
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            if (ob > bb || (ob == bb && oi < bi)) { bb = ob; bi = oi; }
         }
-        if (tq == 0) { s_best[w * 32 + mt * 8 + gq] = best; s_bidx[w * 32 + mt * 8 + gq] = bi; }
+        if (tq == 0) { s_best[w * 32 + mt * 8 + gq] = bb; s_bidx[w * 32 + mt * 8 + gq] = bi; }
     }
     __syncthreads();
     if (tid < 32) {
-        double best = s_best[tid];
+        double bb = s_best[tid];
         int bi = s_bidx[tid];
         for (int ww = 1; ww < 8; ++ww) {
             const double ob = s_best[ww * 32 + tid];
             const int oi = s_bidx[ww * 32 + tid];
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            if (ob > bb || (ob == bb && oi < bi)) { bb = ob; bi = oi; }
         }
         const int a = a0 + tid;
-        if (a < n) { arg_all[(long long)p * n + a] = bi; amax_all[(long long)p * n + a] = sqrt(best); }
+        if (a < n) { arg_all[(long long)p * n + a] = bi; amax_all[(long long)p * n + a] = sqrt(bb); }
     }
 }
 
@@ -276,7 +288,7 @@ extern "C" int axs_launch_track(int N, int hb, const cplx* Cb, const cplx* K6d, 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     const char* env = getenv("AXS_TRACK_FMA");
-    if (env && atoi(env)) {                                // scalar-FMA tiles (kept for A/B)
+    if (env && atoi(env) && n <= TR_BMAX) {                // scalar-FMA tiles (kept for A/B)
         k_track_gemm<<<dim3((n + TR_TA - 1) / TR_TA, npairs), 256, 0, st>>>(n, psi, Y, arg, amax);
         return (int)cudaGetLastError();
     }
