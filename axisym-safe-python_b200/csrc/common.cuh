@@ -165,6 +165,9 @@ static inline long long axs_work_layout(int n2, int nf, void* base, AxsWork* w) 
 // Largest 2N the large path accepts (per-thread register slots of k_modes_col / k_backx_big).
 #define AXS_MAX_BIG_N2 8192
 #define AXS_BIG_MODE_GRID 592           // persistent CTAs of k_modes_col (4 per SM)
+#define AXS_BIG_RB 64                   // row blocks of 128 rows (2N <= 8192)
+#define AXS_BIG_CG 32                   // column groups
+#define AXS_BIG_YW (4 + AXS_BIG_RB + AXS_BIG_CG)   // y, w (double buffered) + partial sums
 
 struct AxsWorkBig {
     cplx*   A;      // [nf][n2*n2]  dense column-major work matrix (S -> reflectors below subdiag)
@@ -174,7 +177,7 @@ struct AxsWorkBig {
     cplx*   tau;    // [nf][n2]        tau[n2-1].x = max |H_ij|
     double* scale;  // [nf][n2]
     int*    ucur;   // [nf]
-    cplx*   yw;     // [nf][2*n2]      y = A^H v and w = A v of the Householder update
+    cplx*   yw;     // [nf][AXS_BIG_YW*n2] y = A^H v, w = A v of the Householder update + partial sums
     unsigned char* msc;   // per-CTA scratch of k_modes_col (multipliers, pivots, z, x)
     long long msc_stride; // bytes per CTA
 };
@@ -203,7 +206,7 @@ static inline long long axs_work_layout_big(int n2, int nf, void* base, AxsWorkB
     if (w) w->ucur = (int*)(b + off);
     off += axs_align((long long)nf * sizeof(int));
     if (w) w->yw = (cplx*)(b + off);
-    off += 2 * szT;
+    off += AXS_BIG_YW * szT;
     if (w) { w->msc = (unsigned char*)(b + off); w->msc_stride = stride; }
     off += stride * AXS_BIG_MODE_GRID;
     return off;

@@ -11,7 +11,7 @@
 //                 DIAGONAL WINDOW held in shared memory for 24 steps ("phase D", the latency
 //                 bound part, identical to k_hqr_mb), the 24 x 8 rotations are recorded, and
 //                 the off-diagonal strips (columns right of the window, rows above it) are
-//                 then updated from 256-wide shared-memory tiles, one thread per column/row,
+//                 then updated from 128-wide shared-memory tiles, one thread per column/row,
 //                 bulge-major so that the running element stays in a register ("phase O":
 //                 ~8 rotation updates per element moved, FP64-pipe bound instead of L2 bound).
 //                 Once the active block fits the shared-memory kernels the sweep is handed
@@ -26,17 +26,12 @@
 #include "common.cuh"
 #include <stdlib.h>
 
-__device__ __forceinline__ void red_add(cplx* p, cplx v) {
-    atomicAdd(&p->x, v.x);
-    atomicAdd(&p->y, v.y);
-}
-
 // =========================================================================================
 // k_reduce_big
 // =========================================================================================
 #define RB_NT 512
 #define RB_NW (RB_NT / 32)
-#define RB_SLOTS 8                      // rows per lane in one row block (256 rows)
+#define RB_SLOTS 4                      // rows per lane in one row block (128 rows)
 
 __device__ __forceinline__ double block_sum_d(double v, double* red, int warp, int lane) {
     v = warp_sum(v);
@@ -132,56 +127,162 @@ k_reduce_big(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict
     __syncthreads();
 
     // ---- phase C: Householder reduction to Hessenberg form -------------------------------
-    cplx* v = (cplx*)smem_raw;                             // [n] (reuses the balancing tables)
-    cplx* yv = wk.yw + (long long)f * 2 * n;               // y_j = v^H A[k+1:, j]
-    cplx* wv = yv + n;                                     // w_i = (A[:, k+1:] v)_i
-    const int nrb = (n + 32 * RB_SLOTS - 1) / (32 * RB_SLOTS);
-    const int CG = (RB_NW >= nrb) ? RB_NW / nrb : 1;       // column groups per row block
+    // One read + one write of the trailing matrix per reflector: the rank-2 update of reflector k
+    //     A[i,j] -= tau w_i conj(v_j)  (all i)   and   -= conj(tau) v_i z_j  (i > k),
+    //     z_j = y_j - tau (v^H w) conj(v_j),    w = A v,   y_j = v^H A[:, j]
+    // is fused with the products w', y' of reflector k+1: column k+1 is updated first, reflector
+    // k+1 is generated from it, and the pass over the columns j >= k+2 updates every entry and
+    // immediately accumulates w' += a_ij v'_j and y'_j += conj(v'_i) a_ij.  The pass is a 2-D
+    // (row block x column group) decomposition over the warps; the partial sums are combined in
+    // a fixed order, so results are bit-reproducible.
+    cplx* v = (cplx*)smem_raw;                             // [n] current reflector (reuses the balancing tables)
+    cplx* ywb = wk.yw + (long long)f * AXS_BIG_YW * n;
+    const int RBH = 32 * RB_SLOTS;                         // rows per row block
+    const int nrb = (n + RBH - 1) / RBH;
+    int CG = (48 + nrb - 1) / nrb;                         // column groups: >= 48 tasks for 16 warps
+    if (CG > AXS_BIG_CG) CG = AXS_BIG_CG;
     const int ntask = nrb * CG;
-    for (int k = 0; k < n - 2; ++k) {
-        cplx* colk = A + (long long)k * n;
+    cplx* ypart = ywb + 4 * (long long)n;                  // [nrb][n]  per row block
+    cplx* wpart = ypart + (long long)AXS_BIG_RB * n;       // [CG][n]   per column group
+
+    // prologue: reflector 0 and its products y, w (plain pass over the whole matrix)
+    cplx tau = mk(0, 0);
+    {
+        cplx* col0 = A;
         double part = 0.0;
-        for (int i = k + 2 + tid; i < n; i += RB_NT) part += cabs2(colk[i]);
+        for (int i = 2 + tid; i < n; i += RB_NT) part += cabs2(col0[i]);
         const double xnorm2 = block_sum_d(part, red, warp, lane);
-        const cplx alpha = colk[k + 1];
-        cplx tau = mk(0, 0);
-        if (xnorm2 == 0.0 && alpha.y == 0.0) {             // uniform: nothing to do
-            if (tid == 0) wk.tau[(long long)f * n + k] = tau;
-            __syncthreads();
-            continue;
-        }
-        const double beta = -copysign(sqrt(cabs2(alpha) + xnorm2), alpha.x);
-        tau = mk((beta - alpha.x) / beta, -alpha.y / beta);
-        {
+        const cplx alpha = col0[1];
+        __syncthreads();
+        if (!(xnorm2 == 0.0 && alpha.y == 0.0)) {
+            const double beta = -copysign(sqrt(cabs2(alpha) + xnorm2), alpha.x);
+            tau = mk((beta - alpha.x) / beta, -alpha.y / beta);
             const cplx sc = cdiv(mk(1.0, 0.0), mk(alpha.x - beta, alpha.y));
-            for (int i = k + 1 + tid; i < n; i += RB_NT) {
-                const cplx vi = (i == k + 1) ? mk(1.0, 0.0) : cmul(colk[i], sc);
-                v[i] = vi;
-                if (i > k + 1) colk[i] = vi;               // keep the reflector for the back-transformation
+            for (int i = 2 + tid; i < n; i += RB_NT) col0[i] = cmul(col0[i], sc);
+            if (tid == 0) col0[1] = mk(beta, 0.0);
+        } else {
+            for (int i = 2 + tid; i < n; i += RB_NT) col0[i] = mk(0, 0);   // v = e_1, tau = 0
+        }
+        if (tid == 0) wk.tau[(long long)f * n] = tau;
+        __syncthreads();
+    }
+    for (int k = 0; k < n - 2; ++k) {
+        cplx* ycur = ywb + ((k & 1) ? 2 * (long long)n : 0);
+        cplx* wcur = ycur + n;
+        cplx* ynext = ywb + ((k & 1) ? 0 : 2 * (long long)n);
+        cplx* wnext = ynext + n;
+        cplx* colk = A + (long long)k * n;
+        // current reflector into shared memory: v[k+1] = 1, v[i] = A[i,k] below
+        for (int i = tid; i < n; i += RB_NT) v[i] = (i <= k) ? mk(0, 0) : (i == k + 1) ? mk(1.0, 0.0) : colk[i];
+        __syncthreads();
+        if (k == 0) {
+            // products of reflector 0: w = A[:, 1:] v, y_j = v^H A[1:, j]
+            for (int task = warp; task < ntask; task += RB_NW) {
+                const int rb = task / CG, g = task - rb * CG;
+                const int i0 = rb * RBH + lane;
+                cplx vi[RB_SLOTS], wacc[RB_SLOTS];
+#pragma unroll
+                for (int q = 0; q < RB_SLOTS; ++q) {
+                    const int i = i0 + 32 * q;
+                    vi[q] = (i < n) ? v[i] : mk(0, 0);
+                    wacc[q] = mk(0, 0);
+                }
+                for (int j = 1 + g; j < n; j += CG) {
+                    const cplx* col = A + (long long)j * n;
+                    const cplx vj = v[j];
+                    cplx yp = mk(0, 0);
+#pragma unroll
+                    for (int q = 0; q < RB_SLOTS; ++q) {
+                        const int i = i0 + 32 * q;
+                        const cplx e = (i < n) ? col[i] : mk(0, 0);
+                        wacc[q] = cfma(e, vj, wacc[q]);
+                        yp = cfmac(e, vi[q], yp);
+                    }
+                    yp = warp_csum(yp);
+                    if (lane == 0) ypart[(long long)rb * n + j] = yp;
+                }
+#pragma unroll
+                for (int q = 0; q < RB_SLOTS; ++q) {
+                    const int i = i0 + 32 * q;
+                    if (i < n) wpart[(long long)g * n + i] = wacc[q];
+                }
             }
-            for (int i = tid; i < 2 * n; i += RB_NT) yv[i] = mk(0, 0);
+            __syncthreads();
+            for (int j = 1 + tid; j < n; j += RB_NT) {
+                cplx sy = mk(0, 0);
+                for (int rb = 0; rb < nrb; ++rb) sy = cadd(sy, __ldcg(&ypart[(long long)rb * n + j]));
+                ycur[j] = sy;
+            }
+            for (int i = tid; i < n; i += RB_NT) {
+                cplx sw = mk(0, 0);
+                for (int g = 0; g < CG; ++g) sw = cadd(sw, __ldcg(&wpart[(long long)g * n + i]));
+                wcur[i] = sw;
+            }
+            __syncthreads();
         }
-        __threadfence();
-        __syncthreads();                                   // every thread has read alpha
-        if (tid == 0) {
-            colk[k + 1] = mk(beta, 0.0);
-            wk.tau[(long long)f * n + k] = tau;
+        // alpha2 = v^H w
+        cplx ap = mk(0, 0);
+        for (int i = k + 1 + tid; i < n; i += RB_NT) ap = cfmac(__ldcg(&wcur[i]), v[i], ap);
+        ap = warp_csum(ap);
+        if (lane == 0) { red[2 * warp] = ap.x; red[2 * warp + 1] = ap.y; }
+        __syncthreads();
+        cplx al = mk(0, 0);
+#pragma unroll
+        for (int q = 0; q < RB_NW; ++q) { al.x += red[2 * q]; al.y += red[2 * q + 1]; }
+        __syncthreads();
+        const cplx tal = cmul(tau, al);
+        const cplx ctau = cconj(tau);
+        // ---- column k+1 first: update it, then generate reflector k+1 from it -----------------
+        const bool has_next = (k + 1 < n - 2);
+        cplx* coln = A + (long long)(k + 1) * n;
+        cplx tau2 = mk(0, 0);
+        {
+            const cplx cvj = cconj(v[k + 1]);
+            const cplx t = cmul(tau, cvj);
+            const cplx z = cmul(ctau, csub(__ldcg(&ycur[k + 1]), cmul(tal, cvj)));
+            double part = 0.0;
+            for (int i = tid; i < n; i += RB_NT) {
+                const cplx a = cfms(v[i], z, cfms(__ldcg(&wcur[i]), t, coln[i]));
+                coln[i] = a;
+                if (i >= k + 3) part += cabs2(a);
+            }
+            if (has_next) {
+                const double xnorm2 = block_sum_d(part, red, warp, lane);   // (barriers: column is visible)
+                const cplx alpha = coln[k + 2];
+                __syncthreads();
+                if (!(xnorm2 == 0.0 && alpha.y == 0.0)) {
+                    const double beta = -copysign(sqrt(cabs2(alpha) + xnorm2), alpha.x);
+                    tau2 = mk((beta - alpha.x) / beta, -alpha.y / beta);
+                    const cplx sc = cdiv(mk(1.0, 0.0), mk(alpha.x - beta, alpha.y));
+                    for (int i = k + 3 + tid; i < n; i += RB_NT) coln[i] = cmul(coln[i], sc);
+                    if (tid == 0) coln[k + 2] = mk(beta, 0.0);
+                } else {
+                    for (int i = k + 3 + tid; i < n; i += RB_NT) coln[i] = mk(0, 0);
+                }
+                if (tid == 0) wk.tau[(long long)f * n + k + 1] = tau2;
+            }
+            __syncthreads();
         }
-        // pass 1: w = A[:, k+1:] v  and  y_j = v^H A[k+1:, j]
+        // ---- fused pass over the columns j >= k+2 ------------------------------------------------
         for (int task = warp; task < ntask; task += RB_NW) {
             const int rb = task / CG, g = task - rb * CG;
-            const int i0 = rb * 32 * RB_SLOTS + lane;
-            const bool any_y = rb * 32 * RB_SLOTS + 32 * RB_SLOTS - 1 > k;
-            cplx vi[RB_SLOTS], wacc[RB_SLOTS];
+            const int i0 = rb * RBH + lane;
+            const bool any_y = has_next && (rb * RBH + RBH - 1 > k + 1);
+            cplx vi[RB_SLOTS], wi[RB_SLOTS], vi2[RB_SLOTS], wacc[RB_SLOTS];
 #pragma unroll
             for (int q = 0; q < RB_SLOTS; ++q) {
                 const int i = i0 + 32 * q;
-                vi[q] = (i < n && i > k) ? v[i] : mk(0, 0);
+                vi[q] = (i < n) ? v[i] : mk(0, 0);
+                wi[q] = (i < n) ? __ldcg(&wcur[i]) : mk(0, 0);
+                vi2[q] = (!has_next || i >= n || i < k + 2) ? mk(0, 0) : (i == k + 2) ? mk(1.0, 0.0) : coln[i];
                 wacc[q] = mk(0, 0);
             }
-            for (int j = k + 1 + g; j < n; j += CG) {
-                const cplx* col = A + (long long)j * n;
-                const cplx vj = v[j];
+            for (int j = k + 2 + g; j < n; j += CG) {
+                cplx* col = A + (long long)j * n;
+                const cplx cvj = cconj(v[j]);
+                const cplx t = cmul(tau, cvj);
+                const cplx z = cmul(ctau, csub(__ldcg(&ycur[j]), cmul(tal, cvj)));
+                const cplx v2j = (j == k + 2) ? mk(1.0, 0.0) : coln[j];
                 cplx e[RB_SLOTS];
 #pragma unroll
                 for (int q = 0; q < RB_SLOTS; ++q) {
@@ -191,65 +292,43 @@ k_reduce_big(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict
                 cplx yp = mk(0, 0);
 #pragma unroll
                 for (int q = 0; q < RB_SLOTS; ++q) {
-                    wacc[q] = cfma(e[q], vj, wacc[q]);
-                    yp = cfmac(e[q], vi[q], yp);
+                    const int i = i0 + 32 * q;
+                    const cplx a = cfms(vi[q], z, cfms(wi[q], t, e[q]));
+                    if (i < n) col[i] = a;
+                    wacc[q] = cfma(a, v2j, wacc[q]);
+                    yp = cfmac(a, vi2[q], yp);
                 }
                 if (any_y) {
                     yp = warp_csum(yp);
-                    if (lane == 0) red_add(&yv[j], yp);
+                    if (lane == 0) ypart[(long long)rb * n + j] = yp;
                 }
             }
-#pragma unroll
-            for (int q = 0; q < RB_SLOTS; ++q) {
-                const int i = i0 + 32 * q;
-                if (i < n) red_add(&wv[i], wacc[q]);
-            }
-        }
-        __threadfence();
-        __syncthreads();
-        // alpha2 = v^H w[k+1:]
-        cplx ap = mk(0, 0);
-        for (int i = k + 1 + tid; i < n; i += RB_NT) ap = cfmac(__ldcg(&wv[i]), v[i], ap);
-        ap = warp_csum(ap);
-        if (lane == 0) { red[2 * warp] = ap.x; red[2 * warp + 1] = ap.y; }
-        __syncthreads();
-        cplx al = mk(0, 0);
-#pragma unroll
-        for (int q = 0; q < RB_NW; ++q) { al.x += red[2 * q]; al.y += red[2 * q + 1]; }
-        const cplx tal = cmul(tau, al);
-        const cplx ctau = cconj(tau);
-        // pass 2: A[i,j] -= tau w_i conj(v_j) (all i)  and  -= conj(tau) v_i z_j (i > k),
-        //         z_j = y_j - tau alpha2 conj(v_j)
-        for (int task = warp; task < ntask; task += RB_NW) {
-            const int rb = task / CG, g = task - rb * CG;
-            const int i0 = rb * 32 * RB_SLOTS + lane;
-            cplx vi[RB_SLOTS], wi[RB_SLOTS];
-#pragma unroll
-            for (int q = 0; q < RB_SLOTS; ++q) {
-                const int i = i0 + 32 * q;
-                vi[q] = (i < n && i > k) ? v[i] : mk(0, 0);
-                wi[q] = (i < n) ? __ldcg(&wv[i]) : mk(0, 0);
-            }
-            for (int j = k + 1 + g; j < n; j += CG) {
-                cplx* col = A + (long long)j * n;
-                const cplx cvj = cconj(v[j]);
-                const cplx t = cmul(tau, cvj);
-                const cplx z = cmul(ctau, csub(__ldcg(&yv[j]), cmul(tal, cvj)));
-                cplx e[RB_SLOTS];
+            if (has_next) {
 #pragma unroll
                 for (int q = 0; q < RB_SLOTS; ++q) {
                     const int i = i0 + 32 * q;
-                    e[q] = (i < n) ? col[i] : mk(0, 0);
-                }
-#pragma unroll
-                for (int q = 0; q < RB_SLOTS; ++q) {
-                    const int i = i0 + 32 * q;
-                    if (i < n) col[i] = cfms(vi[q], z, cfms(wi[q], t, e[q]));
+                    if (i < n) wpart[(long long)g * n + i] = wacc[q];
                 }
             }
         }
+        __syncthreads();
+        if (has_next) {
+            const int rb0 = (k + 2) / RBH;                 // first row block with rows > k+1
+            for (int j = k + 2 + tid; j < n; j += RB_NT) {
+                cplx sy = mk(0, 0);
+                for (int rb = rb0; rb < nrb; ++rb) sy = cadd(sy, __ldcg(&ypart[(long long)rb * n + j]));
+                ynext[j] = sy;
+            }
+            for (int i = tid; i < n; i += RB_NT) {
+                cplx sw = mk(0, 0);
+                for (int g = 0; g < CG; ++g) sw = cadd(sw, __ldcg(&wpart[(long long)g * n + i]));
+                wnext[i] = sw;
+            }
+        }
+        tau = tau2;
         __syncthreads();
     }
+    cplx* yv = ywb;                                        // (scratch is free now)
 
     // ---- phase D: two packed copies of H (QR input, inverse-iteration input), max |H| -------
     cplx* Hc = wk.Hc + (long long)f * hcol_size(n);
@@ -261,6 +340,7 @@ k_reduce_big(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict
             const cplx a = A[idx];
             Hc[hcol_off(c) + r] = a;
             Hm[hcol_off(c) + r] = a;
+            if (r == c + 1) yv[c] = a;                     // contiguous subdiagonal for k_modes_col
             hm = fmax(hm, cabs1(a));
         }
     }
@@ -282,12 +362,13 @@ k_reduce_big(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict
 #define HB_S 24                         // macro steps per window
 #define HB_WS (HB_S + HB_D * HB_NB)     // 48: largest window
 #define HB_WLD (HB_WS + 1)              // window leading dimension (column-major)
-#define HB_TILE 256                     // columns (rows) per off-diagonal tile
+#define HB_TILE 128                     // columns (rows) per off-diagonal tile: 2 CTAs per SM, so the
+                                        // latency-bound phase D of one matrix overlaps phase O of another
 #define HB_TLD (HB_TILE + 1)
 #define HB_WORKERS (HB_NT - 32)
 #define HB_ITEMS 2                      // ceil(HB_NB * HB_WS / HB_WORKERS)
 
-__global__ void __launch_bounds__(HB_NT, 1)
+__global__ void __launch_bounds__(HB_NT, 2)
 k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_all,
           int* __restrict__ info, int* __restrict__ ucur)
 {
@@ -538,14 +619,18 @@ static size_t hqr_big_smem() { return (size_t)HB_WS * HB_TLD * sizeof(cplx); }
 // k_modes_col
 // =========================================================================================
 template <int NT, int R, int M>
-__global__ void __launch_bounds__(NT, (NT == 256 && R * M <= 8) ? 2 : 1)
+__global__ void __launch_bounds__(NT, (NT == 256 && R < 8) ? 2 : 1)
 k_modes_col(int n, int nf, const cplx* __restrict__ eig_all, cplx* __restrict__ psi_all, AxsWorkBig wk)
 {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* s_sub = (cplx*)smem_raw;                 // [n] s_sub[j] = H(j+1, j)
     __shared__ cplx s_mul[2][M], s_z[2][M];
     __shared__ int s_sw[2][M];
+    __shared__ cplx s_pc[M], s_pa[M];              // carry / acc of the row that has just become final
     __shared__ double s_red[NT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int groups = (n + M - 1) / M;
+    int f_loaded = -1;
     unsigned char* base = wk.msc + (long long)blockIdx.x * wk.msc_stride;
     cplx* mul_s = (cplx*)base;                      // [M][n]
     cplx* z_s = mul_s + (size_t)M * n;              // [M][n]
@@ -556,17 +641,24 @@ k_modes_col(int n, int nf, const cplx* __restrict__ eig_all, cplx* __restrict__ 
         const int f = item / groups, mode0 = (item - f * groups) * M;
         const cplx* Hm = wk.Hm + (long long)f * hcol_size(n);
         const double tiny = fmax(EPS_D * wk.tau[(long long)f * n + n - 1].x, SMALL_D);
+        if (f != f_loaded) {                           // uniform
+            const cplx* sub = wk.yw + (long long)f * AXS_BIG_YW * n;
+            for (int i = tid; i < n - 1; i += NT) s_sub[i] = sub[i];
+            f_loaded = f;
+            __syncthreads();
+        }
         cplx lam[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) lam[m] = eig_all[(long long)f * n + ((mode0 + m < n) ? mode0 + m : n - 1)];
 
         // pivot of column jn = (row jn+1 is final): swap flag, multiplier, solution entry
         auto pivot = [&](int jrow, int m, cplx carry, cplx acc, int slot) {
-            // jrow = the finished row; decides column jrow-1
+            // jrow = the finished row; decides column jrow-1.  The subdiagonal H(jrow, jrow-1) comes
+            // from shared memory so that no global load sits on the critical chain.
             cplx rkk = carry, a2 = mk(0, 0);
             bool sw = false;
             if (jrow > 0) {
-                const cplx a = Hm[hcol_off(jrow - 1) + jrow];      // subdiagonal H(jrow, jrow-1)
+                const cplx a = s_sub[jrow - 1];
                 sw = cabs1(a) > cabs1(carry);
                 a2 = sw ? carry : a;
                 rkk = sw ? a : carry;
@@ -585,6 +677,15 @@ k_modes_col(int n, int nf, const cplx* __restrict__ eig_all, cplx* __restrict__ 
         };
 
         cplx carry[R][M], acc[R][M];
+        cplx hn[R];                                    // column j-1, loaded one step ahead (L2 latency)
+        if (n >= 2) {
+            const cplx* col = Hm + hcol_off(n - 2);
+#pragma unroll
+            for (int q = 0; q < R; ++q) {
+                const int k = tid + NT * q;
+                hn[q] = (k <= n - 2) ? col[k] : mk(0, 0);
+            }
+        }
         {
             const cplx* col = Hm + hcol_off(n - 1);
 #pragma unroll
@@ -595,41 +696,69 @@ k_modes_col(int n, int nf, const cplx* __restrict__ eig_all, cplx* __restrict__ 
                 for (int m = 0; m < M; ++m) {
                     carry[q][m] = (k == n - 1) ? csub(h, lam[m]) : h;
                     acc[q][m] = mk(1.0, 0.0);
-                    if (k == n - 1) pivot(n - 1, m, carry[q][m], acc[q][m], 0);
+                    if (k == n - 1) { s_pc[m] = carry[q][m]; s_pa[m] = acc[q][m]; }
                 }
+            }
+            if (tid == (n - 1) % NT) {
+#pragma unroll
+                for (int m = 0; m < M; ++m) pivot(n - 1, m, s_pc[m], s_pa[m], 0);
             }
         }
         __syncthreads();
-        int slot = 0;
-        for (int j = n - 2; j >= 0; --j, slot ^= 1) {
-            const cplx* col = Hm + hcol_off(j);
-            cplx h[R];
+        // one column step: all rows k <= j absorb column j (already in hc), the next column is
+        // fetched into hx meanwhile, the owner of row j decides the pivot of column j-1
+        auto step = [&](int j, int slot, cplx (&hc)[R], cplx (&hx)[R]) {
+            if (j > 0) {
+                const cplx* col = Hm + hcol_off(j - 1) + tid;
 #pragma unroll
-            for (int q = 0; q < R; ++q) {
-                const int k = tid + NT * q;
-                h[q] = (k <= j) ? col[k] : mk(0, 0);
+                for (int q = 0; q < R; ++q)
+                    if (tid + NT * q <= j - 1) hx[q] = col[NT * q];
             }
 #pragma unroll
             for (int m = 0; m < M; ++m) {
                 const cplx mu = s_mul[slot][m], z = s_z[slot][m];
-                const bool sw = s_sw[slot][m] != 0;
+                if (s_sw[slot][m]) {                   // uniform branch: column swap
 #pragma unroll
-                for (int q = 0; q < R; ++q) {
-                    const int k = tid + NT * q;
-                    if (k <= j) {
-                        cplx a = h[q];
-                        if (k == j) a = csub(a, lam[m]);
-                        cplx a2 = sw ? carry[q][m] : a;
-                        const cplx c2 = sw ? a : carry[q][m];
-                        a2 = cfms(mu, c2, a2);
-                        acc[q][m] = cfms(c2, z, acc[q][m]);
-                        carry[q][m] = a2;
-                        if (k == j) pivot(j, m, a2, acc[q][m], slot ^ 1);
+                    for (int q = 0; q < R; ++q) {
+                        const int k = tid + NT * q;
+                        if (k <= j) {
+                            cplx a = hc[q];
+                            if (k == j) a = csub(a, lam[m]);
+                            acc[q][m] = cfms(a, z, acc[q][m]);
+                            carry[q][m] = cfms(mu, a, carry[q][m]);
+                            if (k == j) { s_pc[m] = carry[q][m]; s_pa[m] = acc[q][m]; }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < R; ++q) {
+                        const int k = tid + NT * q;
+                        if (k <= j) {
+                            cplx a = hc[q];
+                            if (k == j) a = csub(a, lam[m]);
+                            const cplx c2 = carry[q][m];
+                            acc[q][m] = cfms(c2, z, acc[q][m]);
+                            carry[q][m] = cfms(mu, c2, a);
+                            if (k == j) { s_pc[m] = carry[q][m]; s_pa[m] = acc[q][m]; }
+                        }
                     }
                 }
             }
+            if (tid == j % NT) {                       // this thread holds row j
+#pragma unroll
+                for (int m = 0; m < M; ++m) pivot(j, m, s_pc[m], s_pa[m], slot ^ 1);
+            }
             __syncthreads();
+        };
+        cplx hb[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) hb[q] = mk(0, 0);
+        int j = n - 2;
+        for (; j >= 1; j -= 2) {                       // two steps per iteration: register ping-pong
+            step(j, 0, hn, hb);
+            step(j - 1, 1, hb, hn);
         }
+        if (j == 0) step(0, 0, hn, hb);
         // x = W z: undo the column operations (forward), one thread per mode
         if (tid < M) {
             const int m = tid;
@@ -705,8 +834,10 @@ k_backx_big(int n, int T, cplx* __restrict__ psi_all, AxsWorkBig wk)
         x[q] = (live && i < n) ? psi[(long long)i * n + mode] : mk(0, 0);
     }
     int par = 0;
+    cplx tnext = (n >= 3) ? tau[n - 3] : mk(0, 0);
     for (int kk = n - 3; kk >= 0; --kk) {
-        const cplx t = tau[kk];
+        const cplx t = tnext;
+        if (kk > 0) tnext = tau[kk - 1];
         if (t.x == 0.0 && t.y == 0.0) continue;         // uniform
         const cplx* vcol = A + (long long)kk * n;
         const int qmin = (kk + 1) / T;
@@ -743,6 +874,82 @@ k_backx_big(int n, int T, cplx* __restrict__ psi_all, AxsWorkBig wk)
             const int i = tt + T * q;
             if (i < n) psi[(long long)i * n + mode] = cscale(x[q], dsc[i]);
         }
+    }
+}
+
+// k_backx_slab: the same back-transformation for sizes whose slab of C mode vectors fits the
+// shared memory next to three reflector buffers: CTA = one frequency x C modes, 256 threads =
+// C columns x (256 / C) row groups, reflectors prefetched with cp.async two steps ahead so that
+// one block barrier per reflector suffices.
+#include <cuda_pipeline.h>
+__global__ void __launch_bounds__(256, 1)
+k_backx_slab(int n, int C, cplx* __restrict__ psi_all, AxsWorkBig wk)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* Xs = (cplx*)smem_raw;                        // [n][C]
+    cplx* vbuf = Xs + (size_t)n * C;                   // [3][n]
+    __shared__ cplx s_red[2][8][8];
+    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col = tid & (C - 1), grp = tid / C, G = 256 / C;
+    const int m0 = blockIdx.x * C;
+    const cplx* A = wk.A + (long long)f * n * n;
+    const cplx* tau = wk.tau + (long long)f * n;
+    const double* dsc = wk.scale + (long long)f * n;
+    cplx* psi = psi_all + (long long)f * n * n;
+
+    for (int idx = tid; idx < n * C; idx += 256) {
+        const int i = idx / C, c = idx - i * C;
+        Xs[idx] = (m0 + c < n) ? psi[(long long)i * n + m0 + c] : mk(0, 0);
+    }
+    auto stage = [&](int kk) {                         // reflector kk: rows kk+2 .. n-1 of column kk
+        cplx* dst = vbuf + (size_t)(kk % 3) * n;
+        const cplx* src = A + (long long)kk * n;
+        for (int i = kk + 2 + tid; i < n; i += 256) __pipeline_memcpy_async(dst + i, src + i, sizeof(cplx));
+        if (tid == 0) __pipeline_memcpy_async(dst + kk + 1, tau + kk, sizeof(cplx));   // slot of v[kk+1] = 1
+        __pipeline_commit();
+    };
+    if (n >= 3) stage(n - 3);
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    for (int kk = n - 3; kk >= 0; --kk) {
+        const cplx* vv = vbuf + (size_t)(kk % 3) * n;
+        if (kk > 0) stage(kk - 1);
+        const cplx t = vv[kk + 1];
+        const bool skip = (t.x == 0.0 && t.y == 0.0);
+        const int i0 = kk + 1 + ((grp - (kk + 1)) % G + G) % G;   // first row >= kk+1 owned by this group
+        cplx part = mk(0, 0);
+        if (!skip) {
+            int i = i0;
+            if (i == kk + 1) { part = Xs[i * C + col]; i += G; }
+            cplx p1 = mk(0, 0);
+            for (; i + G < n; i += 2 * G) {
+                part = cfmac(Xs[i * C + col], vv[i], part);
+                p1 = cfmac(Xs[(i + G) * C + col], vv[i + G], p1);
+            }
+            if (i < n) part = cfmac(Xs[i * C + col], vv[i], part);
+            part = cadd(part, p1);
+            for (int o = 16; o >= C; o >>= 1) {
+                part.x += __shfl_xor_sync(0xffffffffu, part.x, o);
+                part.y += __shfl_xor_sync(0xffffffffu, part.y, o);
+            }
+            if (lane < C) s_red[kk & 1][warp][lane] = part;
+        }
+        __pipeline_wait_prior(0);
+        __syncthreads();
+        if (!skip) {
+            cplx dot = s_red[kk & 1][0][col];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) dot = cadd(dot, s_red[kk & 1][w][col]);
+            const cplx td = cmul(t, dot);
+            int i = i0;
+            if (i == kk + 1) { Xs[i * C + col] = csub(Xs[i * C + col], td); i += G; }
+            for (; i < n; i += G) Xs[i * C + col] = cfms(td, vv[i], Xs[i * C + col]);
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < n * C; idx += 256) {
+        const int i = idx / C, c = idx - i * C;
+        if (m0 + c < n) psi[(long long)i * n + m0 + c] = cscale(Xs[idx], dsc[i]);
     }
 }
 
@@ -831,7 +1038,12 @@ static int launch_modes_col(int n, int nf, const cplx* eig, cplx* psi, AxsWorkBi
     const int groups = (n + M - 1) / M;
     long long items = (long long)nf * groups;
     int grid = items < AXS_BIG_MODE_GRID ? (int)items : AXS_BIG_MODE_GRID;
-    k_modes_col<NT, R, M><<<grid, NT, 0, st>>>(n, nf, eig, psi, wk);
+    const size_t smem = (size_t)n * sizeof(cplx);
+    if (smem > 48 * 1024) {
+        cudaError_t ea = cudaFuncSetAttribute(k_modes_col<NT, R, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (ea != cudaSuccess) return (int)ea;
+    }
+    k_modes_col<NT, R, M><<<grid, NT, smem, st>>>(n, nf, eig, psi, wk);
     return (int)cudaGetLastError();
 }
 
@@ -840,18 +1052,32 @@ extern "C" int axs_launch_modes_big(int N, int hb, const cplx* Cb, const cplx* K
 {
     const int n = 2 * N;
     int rc;
-    if (n <= 512) rc = launch_modes_col<256, 2, 4>(n, nf, eig, psi, wk, st);      // M = axs_big_modes_per_cta(n)
+    // <threads, rows per thread, modes per CTA>; M must equal axs_big_modes_per_cta(n)
+    if (n <= 512) rc = launch_modes_col<256, 2, 4>(n, nf, eig, psi, wk, st);
+    else if (n <= 768) rc = launch_modes_col<256, 3, 2>(n, nf, eig, psi, wk, st);
     else if (n <= 1024) rc = launch_modes_col<256, 4, 2>(n, nf, eig, psi, wk, st);
+    else if (n <= 1280) rc = launch_modes_col<256, 5, 1>(n, nf, eig, psi, wk, st);
+    else if (n <= 1536) rc = launch_modes_col<256, 6, 1>(n, nf, eig, psi, wk, st);
     else if (n <= 2048) rc = launch_modes_col<256, 8, 1>(n, nf, eig, psi, wk, st);
-    else if (n <= 4096) rc = launch_modes_col<256, 16, 1>(n, nf, eig, psi, wk, st);
-    else rc = launch_modes_col<512, 16, 1>(n, nf, eig, psi, wk, st);
+    else if (n <= 4096) rc = launch_modes_col<512, 8, 1>(n, nf, eig, psi, wk, st);
+    else rc = launch_modes_col<1024, 8, 1>(n, nf, eig, psi, wk, st);
     if (rc) return rc;
-    int T = 32, NTb = 256;
-    while (T * BX_RS < n) T *= 2;                        // 32 .. 512 threads per mode
-    if (T > 256) NTb = 512;
-    const int C = NTb / T;
-    k_backx_big<<<dim3((n + C - 1) / C, nf), NTb, 0, st>>>(n, T, psi, wk);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    int Cs = 8;                                          // slab width that fits next to 3 reflector buffers
+    while (Cs >= 1 && (size_t)(Cs + 3) * n * sizeof(cplx) > 220 * 1024) Cs >>= 1;
+    if (Cs >= 1) {
+        const size_t smem = (size_t)(Cs + 3) * n * sizeof(cplx);
+        AXS_CUDA_OK(cudaFuncSetAttribute(k_backx_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_backx_slab<<<dim3((n + Cs - 1) / Cs, nf), 256, smem, st>>>(n, Cs, psi, wk);
+        e = cudaGetLastError();
+    } else {
+        int T = 32, NTb = 256;
+        while (T * BX_RS < n) T *= 2;                    // 32 .. 512 threads per mode
+        if (T > 256) NTb = 512;
+        const int C = NTb / T;
+        k_backx_big<<<dim3((n + C - 1) / C, nf), NTb, 0, st>>>(n, T, psi, wk);
+        e = cudaGetLastError();
+    }
     if (e != cudaSuccess) return (int)e;
     k_norm_big<<<dim3((n + 31) / 32, nf), 256, 0, st>>>(N, hb, Cb, K6d, eig, psi);
     return (int)cudaGetLastError();

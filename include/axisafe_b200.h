@@ -32,8 +32,13 @@ typedef struct { double re, im; } axs_cplx;
 int         axs_version(void);
 const char* axs_strerror(int code);
 
-/* Largest dense problem size (2N) handled by the shared-memory eigen kernels. */
+/* Largest dense problem size (2N) handled by the shared-memory eigen kernels (one SM holds the
+ * whole Hessenberg matrix); above it and up to axs_max_n2() the same entry points run the
+ * global-memory instance of the kernels (csrc/eig_big.cu): one CTA per frequency, the matrix
+ * streams from L2/HBM, the QR sweep chases its bulge chain through a shared-memory diagonal
+ * window and updates the off-diagonal strips from tiles. */
 int axs_max_small_n2(void);
+int axs_max_n2(void);
 
 /* ---- kernel 1a: Gauss-Lobatto quadrature of the element matrices ------------------
  * Replaces the per-element Python loops Element.calculate_matrices()

@@ -124,7 +124,9 @@ def test_cabi_exports_every_declared_symbol(built_lib):
     # argument checking happens before any CUDA call
     assert L.axs_element_matrices(0, None, None, None, None, None, None) == -1
     assert L.axs_hqr(63, 4, None, None, None, 0, None) == -3
-    assert L.axs_reduce(200, 1, None, None, None, None, None, None, 1, None, None, 0, None) == 100001
+    assert L.axs_max_n2() >= 7806                    # cfg5 of BASELINE.json
+    assert L.axs_eig_worksize(200, 4) > 4 * 400 * 400 * 32
+    assert L.axs_reduce(5000, 1, None, None, None, None, None, None, 1, None, None, 0, None) == 100001
 
 
 def _python_scan(arg, amax, n2):
