@@ -878,16 +878,16 @@ k_backx_big(int n, int T, cplx* __restrict__ psi_all, AxsWorkBig wk)
 }
 
 // k_backx_slab: the same back-transformation for sizes whose slab of C mode vectors fits the
-// shared memory next to three reflector buffers: CTA = one frequency x C modes, 256 threads =
-// C columns x (256 / C) row groups, reflectors prefetched with cp.async two steps ahead so that
-// one block barrier per reflector suffices.
+// shared memory next to a ring of four reflector buffers: CTA = one frequency x C modes, 256 threads =
+// C columns x (256 / C) row groups, reflectors prefetched with cp.async two steps ahead (L2
+// latency), one block barrier per reflector.
 #include <cuda_pipeline.h>
 __global__ void __launch_bounds__(256, 1)
 k_backx_slab(int n, int C, cplx* __restrict__ psi_all, AxsWorkBig wk)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* Xs = (cplx*)smem_raw;                        // [n][C]
-    cplx* vbuf = Xs + (size_t)n * C;                   // [3][n]
+    cplx* vbuf = Xs + (size_t)n * C;                   // [4][n] ring: reflectors are fetched two steps ahead
     __shared__ cplx s_red[2][8][8];
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int col = tid & (C - 1), grp = tid / C, G = 256 / C;
@@ -902,18 +902,19 @@ k_backx_slab(int n, int C, cplx* __restrict__ psi_all, AxsWorkBig wk)
         Xs[idx] = (m0 + c < n) ? psi[(long long)i * n + m0 + c] : mk(0, 0);
     }
     auto stage = [&](int kk) {                         // reflector kk: rows kk+2 .. n-1 of column kk
-        cplx* dst = vbuf + (size_t)(kk % 3) * n;
+        cplx* dst = vbuf + (size_t)(kk & 3) * n;
         const cplx* src = A + (long long)kk * n;
         for (int i = kk + 2 + tid; i < n; i += 256) __pipeline_memcpy_async(dst + i, src + i, sizeof(cplx));
         if (tid == 0) __pipeline_memcpy_async(dst + kk + 1, tau + kk, sizeof(cplx));   // slot of v[kk+1] = 1
         __pipeline_commit();
     };
     if (n >= 3) stage(n - 3);
-    __pipeline_wait_prior(0);
+    if (n >= 4) stage(n - 4); else __pipeline_commit();
+    __pipeline_wait_prior(1);
     __syncthreads();
     for (int kk = n - 3; kk >= 0; --kk) {
-        const cplx* vv = vbuf + (size_t)(kk % 3) * n;
-        if (kk > 0) stage(kk - 1);
+        const cplx* vv = vbuf + (size_t)(kk & 3) * n;
+        if (kk > 1) stage(kk - 2); else __pipeline_commit();   // (empty group keeps the accounting uniform)
         const cplx t = vv[kk + 1];
         const bool skip = (t.x == 0.0 && t.y == 0.0);
         const int i0 = kk + 1 + ((grp - (kk + 1)) % G + G) % G;   // first row >= kk+1 owned by this group
@@ -934,7 +935,7 @@ k_backx_slab(int n, int C, cplx* __restrict__ psi_all, AxsWorkBig wk)
             }
             if (lane < C) s_red[kk & 1][warp][lane] = part;
         }
-        __pipeline_wait_prior(0);
+        __pipeline_wait_prior(1);                          // reflector kk-1 has landed, kk-2 may be in flight
         __syncthreads();
         if (!skip) {
             cplx dot = s_red[kk & 1][0][col];
@@ -1064,9 +1065,9 @@ extern "C" int axs_launch_modes_big(int N, int hb, const cplx* Cb, const cplx* K
     if (rc) return rc;
     cudaError_t e;
     int Cs = 8;                                          // slab width that fits next to 3 reflector buffers
-    while (Cs >= 1 && (size_t)(Cs + 3) * n * sizeof(cplx) > 220 * 1024) Cs >>= 1;
+    while (Cs >= 1 && (size_t)(Cs + 4) * n * sizeof(cplx) > 224 * 1024) Cs >>= 1;
     if (Cs >= 1) {
-        const size_t smem = (size_t)(Cs + 3) * n * sizeof(cplx);
+        const size_t smem = (size_t)(Cs + 4) * n * sizeof(cplx);
         AXS_CUDA_OK(cudaFuncSetAttribute(k_backx_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_backx_slab<<<dim3((n + Cs - 1) / Cs, nf), 256, smem, st>>>(n, Cs, psi, wk);
         e = cudaGetLastError();
