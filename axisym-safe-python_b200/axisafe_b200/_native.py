@@ -342,6 +342,38 @@ def track_pairs(ops, psi, npairs, scratch=None):
     return arg, amax
 
 
+def track_pairs_into(ops, psi, npairs, arg, amax, scratch):
+    """axs_track_pairs into caller-provided tables (pipelined sweep)."""
+    torch = torch_cuda()
+    need = int(lib().axs_track_worksize(ops.N, npairs))
+    if scratch.numel() * scratch.element_size() < need:
+        raise RuntimeError('tracking scratch too small')
+    check(lib().axs_track_pairs(ops.N, ops.hb, _ptr(ops.Cb), _ptr(ops.K6d), _ptr(psi), npairs, _ptr(arg),
+                                _ptr(amax), _ptr(scratch), need, _stream(torch)), 'axs_track_pairs')
+
+
+def track_scan_range(arg, amax, order, start, stop, n2):
+    """Rows [start, stop) of the reference column order (see track_scan); ``order`` [nf, n2] int32 is
+    updated in place and must already hold rows < start.  ``arg``/``amax`` are the full host tables."""
+    L = lib()
+    while True:
+        i = L.axs_track_scan(arg.ctypes.data, amax.ctypes.data, stop, n2, start, order.ctypes.data)
+        if i >= stop:
+            return
+        prev = order[i - 1]
+        new_order = arg[i - 1][prev].copy()
+        valid = np.round(amax[i - 1][prev], 2) > 0.9
+        valid_entries = np.delete(new_order, np.where(valid == False))   # noqa: E712 (as the reference)
+        unassigned = list(set(range(n2)) - set(valid_entries))
+        j = 0
+        for ii in range(n2):
+            if not valid[ii]:
+                new_order[ii] = unassigned[j]
+                j += 1
+        order[i] = new_order
+        start = i + 1
+
+
 def track_scan(arg, amax, nf, n2):
     """Reference column order per frequency (solver.py:159-182) from the arg-max tables.
 

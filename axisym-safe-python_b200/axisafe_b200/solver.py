@@ -91,13 +91,16 @@ class WaveElementAxisym(object):
         self.T = T
 
     # ------------------------------------------------------------------------- the sweep
-    def solve(self, f, no_of_waves='full', central_wavespeed=0, distributed='auto'):
+    def solve(self, f, no_of_waves='full', central_wavespeed=0, distributed='auto', pipeline=True):
         """All wavenumbers and mode shapes at every frequency of ``f`` (ref solver.py:76-184).
 
         ``no_of_waves`` other than 'full' (the reference's sparse shift-invert mode,
         solver.py:137-140) is outside the accelerated path and raises.
         ``distributed``: 'auto' shards the frequency axis over the ranks of an initialised
         ``torch.distributed`` process group; False forces a single-GPU sweep.
+        ``pipeline``: single-GPU sweeps of >= 128 points run as a 4-chunk pipeline that copies the
+        tracked ``psi_hat`` to (pinned) host memory while the next chunk computes; False keeps the
+        mode shapes on the device until ``psi_hat`` is read.
         """
         from . import _native
         print('Calculating dispersion curves...')
@@ -108,13 +111,18 @@ class WaveElementAxisym(object):
         ops = mesh._device_ops
         if ops is None:
             raise RuntimeError('Mesh.assemble_matrices(n) must be called before solve()')
-        self.t_transform()
         n = mesh.n
         f = np.asarray(f, dtype=float)
         self.w = 2 * np.pi * f
         N, n2, nf = mesh.no_of_dofs, 2 * mesh.no_of_dofs, len(f)
-        self.B = sps.bmat([[None, mesh.K6.tocsr()],
-                           [mesh.K6.tocsr(), n * mesh.K4.tocsr() + self.K3_hat.tocsr()]])
+
+        def host_attributes():
+            # the reference's sparse by-products (solver.py:102-117): T, K*_hat, B.  The GPU path does
+            # not need them (the device operators were assembled with the mesh), so the pipelined
+            # sweep builds them while the first chunks compute.
+            self.t_transform()
+            self.B = sps.bmat([[None, mesh.K6.tocsr()],
+                               [mesh.K6.tocsr(), n * mesh.K4.tocsr() + self.K3_hat.tocsr()]])
         if n2 > _native.lib().axs_max_n2():
             raise NotImplementedError('2N = %d exceeds the largest supported problem (2N <= %d)'
                                       % (n2, _native.lib().axs_max_n2()))
@@ -129,10 +137,19 @@ class WaveElementAxisym(object):
         halo = 1 if lo > 0 else 0
         self.local_range = (lo, hi)
 
+        small = n2 <= _native.lib().axs_max_small_n2()
+        if small and world == 1 and pipeline and nf >= 128:
+            # single GPU, shared-memory kernels: chunk pipeline (compute of chunk c+1 overlaps the
+            # host scan, the column gather and the psi_hat download of chunk c)
+            _solve_pipelined(self, torch, _native, ops, nf, n2, host_attributes)
+            self.evaluated = True
+            self.k_ready = 0
+            return
+        host_attributes()
         # host -> device: this rank's angular frequencies (with the halo point in front)
         omega = torch.from_numpy(self.w[lo - halo:hi].copy()).cuda()
         nloc = hi - lo + halo
-        if n2 > _native.lib().axs_max_small_n2():
+        if not small:
             # large path: matrices stream from HBM, the sweep is cut into memory-sized chunks
             k_nat, psi_nat, info, arg, amax = _sweep_large(torch, _native, ops, omega, halo)
         else:
@@ -166,7 +183,7 @@ class WaveElementAxisym(object):
             # the mode shapes of the whole block do not fit in HBM (the reference's psi_hat would be
             # nf x 2N x 2N x 16 B of host memory): eigenvalues and tracking are complete, shapes are not kept
             self._psi = None
-        elif n2 > _native.lib().axs_max_small_n2():
+        elif not small:
             self._psi = _LazyModes(_reorder_in_place(torch, _native, n2, order_loc, psi_nat, halo),
                                    (hi - lo, n2, n2), lo, nf)
         else:
@@ -233,6 +250,145 @@ class WaveElementAxisym(object):
         k[k.imag > .1] = 0
         self.propagating_indices = np.where(~(k == 0).all(0))[0]
         self.k_ready = k[:, self.propagating_indices]
+
+
+_PIPE = {}
+
+
+def _solve_pipelined(sol, torch, _native, ops, nf, n2, host_work=None):
+    """Single-GPU sweep as a software pipeline over K frequency chunks.
+
+    stream A/B (alternating)  reduce, QR, modes of chunk c; tracking pairs of chunk c (+ the seam
+                              pair, after chunk c-1's modes on the other stream)
+    stream X                  D2H of the small tables of chunk c -> [host: scan rows of chunk c]
+                              -> H2D order, column gather (apply_order), D2H of psi_hat chunk c
+    The host only ever waits for the small tables of chunk c AFTER the kernels of chunk c+1 are
+    queued, so the scan, the gather and the 0.5 GB psi_hat download hide behind compute.
+    Results are identical to the one-shot path (same kernels on the same inputs).
+    """
+    import os
+    import time
+    K = int(os.environ.get('AXS_PIPE_CHUNKS', 4 if nf >= 512 else 2))
+    trace = os.environ.get('AXS_PIPE_TRACE')
+    tl = [('start', time.perf_counter())]
+    if K == 4:
+        # chunks run pairwise on two streams; the last pair is smaller so that the un-overlapped
+        # tail (scan + gather + download of the final chunk) is short
+        bounds = [0, int(nf * 0.32), int(nf * 0.64), int(nf * 0.82), nf]
+    else:
+        bounds = [nf * c // K for c in range(K + 1)]
+    nn = n2 * n2
+    if not _PIPE:
+        _PIPE['cs'] = [torch.cuda.Stream(), torch.cuda.Stream()]
+        _PIPE['xs'] = torch.cuda.Stream()
+        _PIPE['ss'] = torch.cuda.Stream()
+    cs, xs, ss = _PIPE['cs'], _PIPE['xs'], _PIPE['ss']
+    main = torch.cuda.current_stream()
+    cmax = max(bounds[c + 1] - bounds[c] for c in range(K))
+    dev = 'cuda'
+    omega = torch.from_numpy(sol.w.copy()).cuda()
+    k_nat = torch.empty(nf * n2, dtype=torch.complex128, device=dev)
+    psi_nat = torch.empty(nf * nn, dtype=torch.complex128, device=dev)
+    psi_sorted = torch.empty(nf * nn, dtype=torch.complex128, device=dev)
+    info = torch.zeros(nf, dtype=torch.int32, device=dev)
+    arg = torch.empty((nf - 1) * n2, dtype=torch.int32, device=dev)
+    amax = torch.empty((nf - 1) * n2, dtype=torch.float64, device=dev)
+    order_d = torch.empty(nf * n2, dtype=torch.int32, device=dev)
+    k_dummy = torch.empty(cmax * n2, dtype=torch.complex128, device=dev)
+    works = [_native.EigWorkspace(ops.N, cmax) for _ in range(2)]
+    ybuf = [torch.empty(int(_native.lib().axs_track_worksize(ops.N, cmax)), dtype=torch.uint8, device=dev)
+            for _ in range(2)]
+    pin = lambda *shape, dtype: torch.empty(*shape, dtype=dtype, pin_memory=True)
+    k_h = pin(nf, n2, dtype=torch.complex128)
+    arg_h = pin(max(nf - 1, 1), n2, dtype=torch.int32)
+    amax_h = pin(max(nf - 1, 1), n2, dtype=torch.float64)
+    info_h = pin(nf, dtype=torch.int32)
+    order_h = pin(nf, n2, dtype=torch.int32)
+    psi_h = pin(nf, n2, n2, dtype=torch.complex128)
+    order = order_h.numpy()
+    ev_modes = [torch.cuda.Event(enable_timing=bool(trace)) for _ in range(K)]
+    ev_track = [torch.cuda.Event(enable_timing=bool(trace)) for _ in range(K)]
+    ev_small = [torch.cuda.Event(enable_timing=bool(trace)) for _ in range(K)]
+    ev_done = [torch.cuda.Event(enable_timing=bool(trace)) for _ in range(K)]
+    ev0 = torch.cuda.Event(enable_timing=bool(trace))
+    ev0.record(main)
+    tl.append(('alloc', time.perf_counter()))
+    for s_ in cs + [xs, ss]:
+        s_.wait_stream(main)
+
+    def compute(c):
+        lo, hi = bounds[c], bounds[c + 1]
+        st = cs[c % 2]
+        with torch.cuda.stream(st):
+            _native.eig_sweep_into(ops, omega[lo:hi], k_nat[lo * n2:hi * n2], psi_nat[lo * nn:hi * nn],
+                                   info[lo:hi], works[c % 2])
+            ev_modes[c].record(st)
+            if c > 0:
+                st.wait_event(ev_modes[c - 1])           # the seam pair needs the previous chunk's shapes
+            p0 = max(lo - 1, 0)
+            npairs = hi - 1 - p0
+            if npairs > 0:
+                _native.track_pairs_into(ops, psi_nat[p0 * nn:hi * nn], npairs, arg[p0 * n2:(hi - 1) * n2],
+                                         amax[p0 * n2:(hi - 1) * n2], ybuf[c % 2])
+            ev_track[c].record(st)
+        with torch.cuda.stream(ss):                      # small tables on their own stream: waiting for the
+            ss.wait_event(ev_track[c])                   # tracking of chunk c must not hold up psi downloads
+            k_h[lo:hi].copy_(k_nat[lo * n2:hi * n2].view(hi - lo, n2), non_blocking=True)
+            info_h[lo:hi].copy_(info[lo:hi], non_blocking=True)
+            if hi - 1 > p0:
+                arg_h[p0:hi - 1].copy_(arg[p0 * n2:(hi - 1) * n2].view(-1, n2), non_blocking=True)
+                amax_h[p0:hi - 1].copy_(amax[p0 * n2:(hi - 1) * n2].view(-1, n2), non_blocking=True)
+            ev_small[c].record(ss)
+
+    def finish(c):
+        lo, hi = bounds[c], bounds[c + 1]
+        ev_small[c].synchronize()
+        if info_h[lo:hi].numpy().any():
+            torch.cuda.synchronize()
+            bad = int(np.count_nonzero(info_h[lo:hi].numpy()))
+            raise np.linalg.LinAlgError('eig algorithm (QR) did not converge at %d frequencies' % bad)
+        _native.track_scan_range(arg_h.numpy(), amax_h.numpy(), order, lo, hi, n2)
+        with torch.cuda.stream(xs):
+            xs.wait_event(ev_track[c])
+            order_d[lo * n2:hi * n2].copy_(order_h[lo:hi].view(-1), non_blocking=True)
+            _native.check(_native.lib().axs_apply_order(
+                n2, hi - lo, _native._ptr(order_d[lo * n2:hi * n2]), _native._ptr(k_dummy),
+                _native._ptr(psi_nat[lo * nn:hi * nn]), _native._ptr(k_dummy[:(hi - lo) * n2]),
+                _native._ptr(psi_sorted[lo * nn:hi * nn]), _native._stream(torch)), 'axs_apply_order')
+            psi_h[lo:hi].copy_(psi_sorted[lo * nn:hi * nn].view(hi - lo, n2, n2), non_blocking=True)
+            ev_done[c].record(xs)
+
+    for c in range(K):
+        compute(c)
+        tl.append(('enq%d' % c, time.perf_counter()))
+        if c == min(1, K - 1) and host_work is not None:
+            host_work()                                  # sparse host by-products, hidden behind the kernels
+            tl.append(('host', time.perf_counter()))
+        if c >= 1:
+            finish(c - 1)
+            tl.append(('fin%d' % (c - 1), time.perf_counter()))
+    finish(K - 1)
+    tl.append(('fin%d' % (K - 1), time.perf_counter()))
+    xs.synchronize()
+    tl.append(('sync', time.perf_counter()))
+    if trace:
+        t0 = tl[0][1]
+        print('AXS_PIPE host ms:', ' '.join('%s=%.1f' % (n_, (t_ - t0) * 1e3) for n_, t_ in tl), file=__import__('sys').stderr)
+        print('AXS_PIPE device ms since start:', ' '.join(
+            'c%d modes=%.1f track=%.1f small=%.1f done=%.1f' % (c, ev0.elapsed_time(ev_modes[c]), ev0.elapsed_time(ev_track[c]),
+                                                             ev0.elapsed_time(ev_small[c]), ev0.elapsed_time(ev_done[c]))
+            for c in range(K)), file=__import__('sys').stderr)
+    main.wait_stream(xs)
+    for s_ in cs:
+        main.wait_stream(s_)
+    sol.info = info_h.numpy().copy()
+    sol.k_native = k_h.numpy()
+    sol.order = order.copy()
+    sol.k = np.take_along_axis(sol.k_native, sol.order.astype(np.int64), axis=1)
+    sol.local_range = (0, nf)
+    modes = _LazyModes(psi_sorted, (nf, n2, n2), 0, nf)
+    modes.host = psi_h.numpy()
+    sol._psi = modes
 
 
 def _sweep_large(torch, _native, ops, omega, halo):

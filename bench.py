@@ -266,7 +266,7 @@ def gpu_arm(args):
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'points_per_gpu': POINTS_PER_GPU, 'n2': n2,
                    'l2': 'working set 1.5 GB per sweep >> 126 MB L2 (no flush needed)',
-                   'parallelism': 'frequency axis sharded, %d rank(s), 1-point halo; 2 frequency chunks on 2 CUDA streams per rank' % world},
+                   'parallelism': 'frequency axis sharded, %d rank(s), 1-point halo; 2 frequency chunks on 2 CUDA streams per rank (value); e2e = solve(): 4-chunk pipeline, psi_hat download overlapped with compute at N=1' % world},
         'kernel_ms': {k_: v / args.steps for k_, v in per_kernel.items()},
         'roofline': {'bound': 'tensor', 'kernel': 'k_hqr_mb (3 stages)', 'achieved': achieved, 'peak': fp64_peak,
                      'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
