@@ -41,6 +41,8 @@ _SIGNATURES = {
     'axs_apply_order': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 6),
     'axs_energy_ratio': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 2 +
                          [ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int] + [ctypes.c_void_p] * 5),
+    'axs_quadratic_forms': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 2 + [ctypes.c_int, ctypes.c_void_p,
+                                           ctypes.c_int] + [ctypes.c_void_p] * 6),
 }
 EXPORTED = tuple(_SIGNATURES)
 
@@ -431,3 +433,22 @@ def energy_ratio(N, nf, psi, tclass, total, pml):
                                  npml, _ptr(rp) if npml else None, _ptr(cp) if npml else None,
                                  _ptr(vp) if npml else None, _ptr(er), _stream(torch)), 'axs_energy_ratio')
     return er.cpu().numpy().reshape(nf, 2 * N)
+
+
+def quadratic_forms(N, nf, psi, tclass, sel, matrices):
+    """axs_quadratic_forms: ``matrices`` is a list of (rows, cols, vals) COO triplets (host arrays);
+    returns the forms as a host array [nf, n_sel, n_mat] (complex)."""
+    torch = torch_cuda()
+    off = np.cumsum([0] + [len(m[0]) for m in matrices]).astype(np.int32)
+    rows = np.concatenate([np.asarray(m[0], np.int32) for m in matrices] + [np.zeros(1, np.int32)])
+    cols = np.concatenate([np.asarray(m[1], np.int32) for m in matrices] + [np.zeros(1, np.int32)])
+    vals = np.concatenate([np.asarray(m[2], np.complex128) for m in matrices] + [np.zeros(1, np.complex128)])
+    n_sel = 2 * N if sel is None else len(sel)
+    d_sel = None if sel is None else to_device(np.asarray(sel, np.int32), torch)
+    d_off, d_r, d_c, d_v = (to_device(a, torch) for a in (off, rows, cols, vals))
+    d_tc = to_device(np.asarray(tclass, np.int32), torch)
+    out = torch.empty(nf * n_sel * len(matrices), dtype=torch.complex128, device='cuda')
+    check(lib().axs_quadratic_forms(N, nf, _ptr(psi), _ptr(d_tc), n_sel, _ptr(d_sel), len(matrices), _ptr(d_off),
+                                    _ptr(d_r), _ptr(d_c), _ptr(d_v), _ptr(out), _stream(torch)),
+          'axs_quadratic_forms')
+    return out.cpu().numpy().reshape(nf, n_sel, len(matrices))

@@ -252,6 +252,79 @@ class WaveElementAxisym(object):
         self.k_ready = k[:, self.propagating_indices]
 
 
+    # ----------------------------------------------------------------- energy velocity (row N3)
+    def energy_velocity(self, core_sets=None, only_propagating=True):
+        """Kinetic / potential energy, power flow and energy velocity per mode (ref solver.py:301-409).
+
+        The reference takes q = conj(T) psi_hat[:, N:, :] to the host and evaluates dense batched
+        products with the core-subset matrices; here the nine quadratic forms q^H X q
+        (X = M, K1, K2, K5, KF, KF^T, KFt^T, KFt, K6 of the non-PML elements, fluid columns x -1 as in
+        solver.py:353-362) are evaluated on the GPU from the device-resident tracked mode shapes
+        (axs_quadratic_forms) and only [nf, modes, 9] numbers come back; the combination with k, n, w
+        (solver.py:395-409) is O(nf * modes) host work.  Sets ``e_k, e_p, p, en_vel``.
+
+        ``core_sets``: the reference's handling of a user list is broken (it ends with empty
+        subsets, solver.py:318-341); here the listed element sets are used, as its docstring says.
+        ``only_propagating``: needs ``k_propagating()`` first (the reference's own check
+        ``propagating_indices == []`` raises on current NumPy; the intent is kept).
+        """
+        if not self.evaluated:
+            print('No solution is availble. Solve the system first.')
+            return
+        from . import _native
+        mesh = self.Mesh
+        pml_elements, core_elements = [], []
+        for key in mesh.dofs_per_elset:
+            if core_sets is None:
+                (pml_elements if 'PML' in key else core_elements).extend(mesh.element_sets[key])
+            elif key in core_sets:
+                core_elements.extend(mesh.element_sets[key])
+        core_elements = sorted(set(core_elements) - set(pml_elements))
+        sub = mesh.assemble_subset(core_elements)
+        mult = np.ones(mesh.no_of_dofs)
+        if mesh.dof_domains['fluid'] != []:
+            mult[mesh.dof_domains['fluid']] = -1
+
+        def triplets(name, transpose=False):
+            coo = sub[name].tocoo()
+            coo.sum_duplicates()
+            vals = coo.data * mult[coo.col]
+            keep = vals != 0
+            r, c = (coo.col, coo.row) if transpose else (coo.row, coo.col)
+            return r[keep], c[keep], vals[keep]
+        mats = [triplets('M'), triplets('K1'), triplets('K2'), triplets('K5'), triplets('KF'),
+                triplets('KF', True), triplets('KFt', True), triplets('KFt'), triplets('K6')]
+        if only_propagating:
+            if self.propagating_indices is None or len(self.propagating_indices) == 0:
+                self.k_propagating()
+            sel = np.asarray(self.propagating_indices, dtype=np.int32)
+        else:
+            sel = None
+        if self.psi_hat_device is None:
+            raise RuntimeError('mode shapes are no longer on the device; call solve() again')
+        lo, hi = self.local_range
+        tclass = [0 if t == 1 else 1 for t in mesh.Tdiag]
+        forms = _native.quadratic_forms(mesh.no_of_dofs, hi - lo, self.psi_hat_device.reshape(-1), tclass, sel, mats)
+        fM, fK1, fK2, fK5, fKF, fKFT, fKFtT, fKFt, fK6 = (forms[:, :, i] for i in range(9))
+        k = self.k[lo:hi] if sel is None else self.k[lo:hi][:, sel]
+        w = self.w[lo:hi].reshape(-1, 1)
+        n = mesh.n
+        e_k = w ** 2 / 4 * fM
+        e_p = 0.25 * (fK1 + 1j * n * fK2 + n ** 2 * fK5 + 1j * k.conj() * fKF - 1j * k * fKFT +
+                      k * n * fKFtT + k.conj() * n * fKFt + k * k.conj() * fK6)
+        p = -w / 2 * np.imag(fKF - 1j * n * fKFt - 1j * k * fK6)
+
+        def full(a):
+            if hi - lo == len(self.w):
+                return a
+            out = np.full([len(self.w), a.shape[1]], np.nan, dtype=a.dtype)   # other ranks' frequencies
+            out[lo:hi] = a
+            return out
+        self.e_k, self.e_p, self.p = full(e_k), full(e_p), full(p)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            self.en_vel = self.p / (self.e_k + self.e_p)
+
+
 _PIPE = {}
 
 

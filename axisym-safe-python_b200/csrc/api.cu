@@ -22,6 +22,8 @@ int axs_launch_reduce_big(int, int, const cplx*, const cplx*, const cplx*, const
 int axs_launch_hqr_big(int, int, cplx*, int*, AxsWorkBig, cudaStream_t);
 int axs_launch_modes_big(int, int, const cplx*, const cplx*, int, const cplx*, cplx*, AxsWorkBig, cudaStream_t);
 int axs_launch_unpack_big(int, int, AxsWorkBig, cplx*, cudaStream_t);
+int axs_launch_quad_forms(int, int, const cplx*, const int*, int, const int*, int, const int*, const int*, const int*,
+                          const cplx*, cplx*, cudaStream_t);
 int axs_launch_energy_ratio(int, int, const cplx*, const int*, int, const int*, const int*, const cplx*,
                             int, const int*, const int*, const cplx*, double*, cudaStream_t);
 }
@@ -290,4 +292,23 @@ extern "C" int axs_energy_ratio(int N, int nf, const axs_cplx* psi, const int* t
     return axs_launch_energy_ratio(N, nf, (const cplx*)psi, tclass, nnz_total, rows_total, cols_total,
                                    (const cplx*)vals_total, nnz_pml, rows_pml, cols_pml, (const cplx*)vals_pml,
                                    er, (cudaStream_t)stream);
+}
+
+extern "C" int axs_quadratic_forms(int N, int nf, const axs_cplx* psi, const int* tclass, int n_sel, const int* sel,
+                                   int n_mat, const int* mat_off, const int* rows, const int* cols,
+                                   const axs_cplx* vals, axs_cplx* out, void* stream)
+{
+    if (N <= 0) return -1;
+    if (nf <= 0) return -2;
+    if (!psi) return -3;
+    if (!tclass) return -4;
+    if (n_sel <= 0 || n_sel > 2 * N) return -5;
+    if (n_mat <= 0) return -7;
+    if (!mat_off) return -8;
+    if (!rows) return -9;
+    if (!cols) return -10;
+    if (!vals) return -11;
+    if (!out) return -12;
+    return axs_launch_quad_forms(N, nf, (const cplx*)psi, tclass, n_sel, sel, n_mat, mat_off, rows, cols,
+                                 (const cplx*)vals, (cplx*)out, (cudaStream_t)stream);
 }

@@ -269,6 +269,40 @@ k_energy_ratio(int N, const cplx* __restrict__ psi_all, const int* __restrict__ 
     er[(long long)f * n + j] = cabsd(ep) / cabsd(et);
 }
 
+// Quadratic forms of the tracked mode shapes with a list of sparse matrices (energy_velocity,
+// solver.py:374-409):  out[f][s][m] = q^H X_m q,  q = conj(T) psi[N:, sel[s]],  X_m given as COO
+// triplets e in [mat_off[m], mat_off[m+1]).  grid = (ceil(n_sel/128), nf), thread = one mode.
+__global__ void __launch_bounds__(128)
+k_quad_forms(int N, const cplx* __restrict__ psi_all, const int* __restrict__ tclass, int n_sel,
+             const int* __restrict__ sel, int n_mat, const int* __restrict__ mat_off,
+             const int* __restrict__ rows, const int* __restrict__ cols, const cplx* __restrict__ vals,
+             cplx* __restrict__ out)
+{
+    const int n = 2 * N, f = blockIdx.y, s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sel) return;
+    const int j = sel ? sel[s] : s;
+    const cplx* psi = psi_all + (long long)f * n * n + (long long)N * n + j;
+    auto q_at = [&](int r) {
+        const cplx v = psi[(long long)r * n];
+        return tclass[r] ? mk(v.y, -v.x) : v;                                  // conj(T) = 1 or -i
+    };
+    for (int m = 0; m < n_mat; ++m) {
+        cplx acc = mk(0, 0);
+        for (int e = mat_off[m]; e < mat_off[m + 1]; ++e)
+            acc = cfma(cmul(cconj(q_at(rows[e])), vals[e]), q_at(cols[e]), acc);
+        out[((long long)f * n_sel + s) * n_mat + m] = acc;
+    }
+}
+
+extern "C" int axs_launch_quad_forms(int N, int nf, const cplx* psi, const int* tclass, int n_sel, const int* sel,
+                                     int n_mat, const int* mat_off, const int* rows, const int* cols,
+                                     const cplx* vals, cplx* out, cudaStream_t st)
+{
+    k_quad_forms<<<dim3((n_sel + 127) / 128, nf), 128, 0, st>>>(N, psi, tclass, n_sel, sel, n_mat, mat_off, rows,
+                                                               cols, vals, out);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int axs_launch_energy_ratio(int N, int nf, const cplx* psi, const int* tclass,
                                        int nnz_t, const int* rt, const int* ct, const cplx* vt,
                                        int nnz_p, const int* rp, const int* cp, const cplx* vp,

@@ -153,6 +153,17 @@ int axs_energy_ratio(int N, int nf, const axs_cplx* psi, const int* tclass,
                      int nnz_pml, const int* rows_pml, const int* cols_pml, const axs_cplx* vals_pml,
                      double* er, void* stream);
 
+/* ---- energy velocity -----------------------------------------
+ * Replaces the dense batched products of WaveElementAxisym.energy_velocity, solver.py:374-408:
+ * the quadratic forms  out[f][s][m] = q^H X_m q,  q = conj(T) psi[N:, sel[s]]  for n_mat sparse
+ * matrices X_m (the core-subset M, K1, K2, K5, KF, KF^T, KFt^T, KFt, K6 with the fluid
+ * multiplier applied) given as concatenated COO triplets, matrix m = entries
+ * [mat_off[m], mat_off[m+1]).  sel (may be NULL = all 2N modes) lists the mode columns
+ * (propagating_indices).  The host combines the forms with k, n and w into e_k, e_p, p. */
+int axs_quadratic_forms(int N, int nf, const axs_cplx* psi, const int* tclass, int n_sel, const int* sel,
+                        int n_mat, const int* mat_off, const int* rows, const int* cols,
+                        const axs_cplx* vals, axs_cplx* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,5 +113,40 @@ def main():
     print('suggest_PML_parameters: identical', a)
 
 
+ENVEL_CASES = [('aristegui', 0, {'nf': 40}), ('pipe_soil_pml', 0, {'nf': 30}), ('gravenkamp', 1, {'nf': 30})]
+
+
+def energy_velocity_fixtures():
+    """tests/golden/envel_*.npz: the reference's energy_velocity (solver.py:301-409) for all modes.
+
+    ``only_propagating=False`` because the reference's own ``propagating_indices == []`` test
+    (solver.py:386) raises on current NumPy; the propagating subset is a column selection of these
+    arrays.  Stored: tracked k, e_k, e_p, p, en_vel ([nf, 2N]) and the k_propagating arguments.
+    """
+    ref = refshim.load()
+    from axisafe_b200 import cases
+    outdir = os.path.join(ROOT, 'tests', 'golden')
+    for name, n, kw in ENVEL_CASES:
+        c = cases.ALL[name](n=n, **kw)
+        with refshim.quiet():
+            mesh = ref.mesh.Mesh()
+            mesh.create(c['sets'], c['fmax'], PML=c['PML'], PML_props=c['PML_props'])
+            mesh.assemble_matrices(n)
+            sol = ref.solver.WaveElementAxisym(mesh)
+            sol.solve(c['f'])
+            sol.energy_ratio()
+            sol.k_propagating(*KPROP[name])
+            sol.energy_velocity(only_propagating=False)
+        path = os.path.join(outdir, 'envel_%s_n%d.npz' % (name, n))
+        np.savez_compressed(path, f=c['f'], k=sol.k, e_k=sol.e_k, e_p=sol.e_p, p=sol.p, en_vel=sol.en_vel,
+                            prop_idx=np.array(sol.propagating_indices), kprop_args=np.array(KPROP[name]))
+        print('%-32s nf=%3d 2N=%3d %6.0f KB' % (os.path.basename(path), len(c['f']), sol.k.shape[1],
+                                               os.path.getsize(path) / 1024))
+
+
 if __name__ == '__main__':
-    main()
+    if 'envel' in sys.argv[1:]:
+        energy_velocity_fixtures()
+    else:
+        main()
+        energy_velocity_fixtures()

@@ -428,6 +428,42 @@ def solve(G, n, f):
     return k, psi
 
 
+# ------------------------------------------------------------- energy velocity (row N3)
+
+
+def energy_velocity(G, mesh, n, w, k, psi):
+    """e_k, e_p, p, en_vel for all modes (solver.py:301-409, ``only_propagating=False``).
+
+    ``mesh`` is the build_mesh dict (its ``pml_elems`` are excluded, solver.py:318-341),
+    ``k`` [nf, 2N] and ``psi`` [nf, 2N, 2N] a tracked sweep.  Dense NumPy, small cases only.
+    """
+    num, em = G['num'], G['elements']
+    N = num['N']
+    names = dict(K1='K_1', K2='K_2', K5='K_5', K6='K_6', M='M', KF='K_F', KFt='K_Ft')
+    core = [e for e in range(len(em)) if e not in mesh['pml_elems']]
+    sub = {key: np.zeros([N, N], complex) for key in names}
+    for e in core:                                            # Mesh.assemble_subset, mesh.py:621-755
+        lm = np.array(num['LM'][e], int)
+        for gk, ek in names.items():
+            sub[gk][np.ix_(lm, lm)] += em[e][ek]
+    mult = np.ones(N)
+    mult[num['fluid']] = -1                                   # physical pressure sign, solver.py:353-362
+    for key in sub:
+        sub[key] = sub[key] * mult[None, :]
+    core_dofs = sorted({d for e in core for d in num['LM'][e]})
+    q = (num['Tdiag'].conj()[None, :, None] * psi[:, N:, :])[:, core_dofs, :]     # [nf, dofs, modes]
+    R = {key: m[np.ix_(core_dofs, core_dofs)] for key, m in sub.items()}
+    form = lambda X: np.einsum('fam,ab,fbm->fm', q.conj(), X, q)
+    w = np.asarray(w, float).reshape(-1, 1)
+    e_k = w ** 2 / 4 * form(R['M'])
+    e_p = 0.25 * (form(R['K1']) + 1j * n * form(R['K2']) + n ** 2 * form(R['K5']) + 1j * k.conj() * form(R['KF'])
+                  - 1j * k * form(R['KF'].T) + k * n * form(R['KFt'].T) + k.conj() * n * form(R['KFt'])
+                  + k * k.conj() * form(R['K6']))
+    p = -w / 2 * np.imag(form(R['KF']) - 1j * n * form(R['KFt']) - 1j * k * form(R['K6']))
+    with np.errstate(divide='ignore', invalid='ignore'):
+        return e_k, e_p, p, p / (e_k + e_p)
+
+
 # ------------------------------------------------------------- comparison utilities
 
 

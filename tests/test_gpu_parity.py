@@ -316,3 +316,39 @@ def test_energy_ratio_and_propagating_filter(name, n, kw):
         assert len(ref) == len(got), (i, len(ref), len(got))
         if len(ref):
             assert np.abs(ref - got).max() <= 1e-6 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize('name,n,kw', [('aristegui', 0, {'nf': 40}), ('pipe_soil_pml', 0, {'nf': 30}),
+                                       ('gravenkamp', 1, {'nf': 30})],
+                         ids=['aristegui-n0', 'pipe_soil_pml-n0', 'gravenkamp-n1'])
+def test_energy_velocity_vs_reference(name, n, kw):
+    """Row N3: energy_velocity (GPU quadratic forms) against the reference's arrays and
+    against the NumPy restatement evaluated on our own tracked mode shapes."""
+    import os
+    import axisafe_b200 as ax
+    from conftest import GOLDEN
+    from test_oracle_golden import envel_by_eigenvalue
+    g = np.load(os.path.join(GOLDEN, 'envel_%s_n%d.npz' % (name, n)))
+    c = make_case(name, n, kw)
+    m = _mesh(c)
+    sol = ax.solver.WaveElementAxisym(m)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sol.solve(c['f'])
+        sol.energy_ratio()
+        sol.k_propagating(*g['kprop_args'])
+        sol.energy_velocity(only_propagating=False)
+    assert sol.e_k.shape == g['e_k'].shape == sol.k.shape
+    for mine, ref in ((sol.e_k, g['e_k']), (sol.e_p, g['e_p']), (sol.p, g['p'])):
+        assert envel_by_eigenvalue(g['k'], ref, sol.k, mine) < 1e-5
+    # column-wise against the oracle's dense formula on the very same psi_hat / k
+    mesh_o = so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props'])
+    G = so.assemble(mesh_o, n)
+    e_k, e_p, p, en_vel = so.energy_velocity(G, mesh_o, n, sol.w, sol.k, sol.psi_hat)
+    for mine, ref in ((sol.e_k, e_k), (sol.e_p, e_p), (sol.p, p)):
+        assert np.abs(mine - ref).max() <= 1e-9 * np.abs(ref).max()
+    # the propagating subset is a column selection
+    full_vel = sol.en_vel.copy()
+    with contextlib.redirect_stdout(io.StringIO()):
+        sol.energy_velocity()
+    assert sol.en_vel.shape == (len(c['f']), len(sol.propagating_indices))
+    assert np.allclose(sol.en_vel, full_vel[:, sol.propagating_indices], rtol=1e-12, atol=0, equal_nan=True)
