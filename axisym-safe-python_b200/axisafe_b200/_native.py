@@ -43,6 +43,7 @@ _SIGNATURES = {
                          [ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int] + [ctypes.c_void_p] * 5),
     'axs_quadratic_forms': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 2 + [ctypes.c_int, ctypes.c_void_p,
                                            ctypes.c_int] + [ctypes.c_void_p] * 6),
+    'axs_modal_projection': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 4),
 }
 EXPORTED = tuple(_SIGNATURES)
 
@@ -452,3 +453,13 @@ def quadratic_forms(N, nf, psi, tclass, sel, matrices):
                                     _ptr(d_r), _ptr(d_c), _ptr(d_v), _ptr(out), _stream(torch)),
           'axs_quadratic_forms')
     return out.cpu().numpy().reshape(nf, n_sel, len(matrices))
+
+
+def modal_projection(N, nf, psi, fvec):
+    """axs_modal_projection: psi^T fvec per frequency; returns a host array [nf, 2N]."""
+    torch = torch_cuda()
+    d_f = to_device(np.asarray(fvec, np.complex128), torch)
+    out = torch.empty(nf * 2 * N, dtype=torch.complex128, device='cuda')
+    check(lib().axs_modal_projection(N, nf, _ptr(psi), _ptr(d_f), _ptr(out), _stream(torch)),
+          'axs_modal_projection')
+    return out.cpu().numpy().reshape(nf, 2 * N)

@@ -325,6 +325,36 @@ class WaveElementAxisym(object):
             self.en_vel = self.p / (self.e_k + self.e_p)
 
 
+    # ------------------------------------------------------------------ forced response (row N4)
+    def point_excited_waves(self, theta_0, r_f, f_ext, propagating=False):
+        """Excited wave amplitudes for a point force (ref solver.py:411-435).
+
+        ``psi_hat^T [0; f_ext]`` is evaluated on the GPU from the device-resident mode shapes
+        (axs_modal_projection); returns [nf, 2N, 1] like the reference.  As in the reference, only
+        ``propagating=False`` returns a value.
+        """
+        from . import _native
+        if not propagating:
+            N = self.Mesh.no_of_dofs
+            force_vector = np.r_[np.zeros(N), np.asarray(f_ext).reshape(-1)]
+            if self.psi_hat_device is None:
+                raise RuntimeError('mode shapes are no longer on the device; call solve() again')
+            lo, hi = self.local_range
+            proj = _native.modal_projection(N, hi - lo, self.psi_hat_device.reshape(-1), force_vector)
+            if hi - lo != len(self.w):
+                full = np.full([len(self.w), 2 * N], np.nan + 0j)              # other ranks' frequencies
+                full[lo:hi] = proj
+                proj = full
+            return (1j * np.sinc(self.Mesh.n * theta_0 / np.pi) / (2 * np.pi * r_f) * proj)[:, :, np.newaxis]
+
+    def calculate_frf(self, theta_0, r_f, f_ext, distance=0):
+        """Modal contributions to the point-force FRF at ``distance`` (ref solver.py:437-474)."""
+        idx = self.propagating_indices
+        amps = self.point_excited_waves(theta_0, r_f, f_ext)[:, idx, 0] * np.exp(-1j * self.k[:, idx] * distance)
+        shapes = self.psi_hat[:, self.Mesh.no_of_dofs:, idx]
+        return shapes * amps[:, np.newaxis, :]
+
+
 _PIPE = {}
 
 

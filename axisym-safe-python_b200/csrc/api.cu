@@ -24,6 +24,7 @@ int axs_launch_modes_big(int, int, const cplx*, const cplx*, int, const cplx*, c
 int axs_launch_unpack_big(int, int, AxsWorkBig, cplx*, cudaStream_t);
 int axs_launch_quad_forms(int, int, const cplx*, const int*, int, const int*, int, const int*, const int*, const int*,
                           const cplx*, cplx*, cudaStream_t);
+int axs_launch_modal_projection(int, int, const cplx*, const cplx*, cplx*, cudaStream_t);
 int axs_launch_energy_ratio(int, int, const cplx*, const int*, int, const int*, const int*, const cplx*,
                             int, const int*, const int*, const cplx*, double*, cudaStream_t);
 }
@@ -311,4 +312,16 @@ extern "C" int axs_quadratic_forms(int N, int nf, const axs_cplx* psi, const int
     if (!out) return -12;
     return axs_launch_quad_forms(N, nf, (const cplx*)psi, tclass, n_sel, sel, n_mat, mat_off, rows, cols,
                                  (const cplx*)vals, (cplx*)out, (cudaStream_t)stream);
+}
+
+extern "C" int axs_modal_projection(int N, int nf, const axs_cplx* psi, const axs_cplx* fvec, axs_cplx* out,
+                                    void* stream)
+{
+    if (N <= 0) return -1;
+    if (nf <= 0) return -2;
+    if (!psi) return -3;
+    if (!fvec) return -4;
+    if (!out) return -5;
+    return axs_launch_modal_projection(2 * N, nf, (const cplx*)psi, (const cplx*)fvec, (cplx*)out,
+                                       (cudaStream_t)stream);
 }

@@ -303,6 +303,28 @@ extern "C" int axs_launch_quad_forms(int N, int nf, const cplx* psi, const int* 
     return (int)cudaGetLastError();
 }
 
+// Modal projection (point_excited_waves, solver.py:411-435): out[f][j] = sum_r psi[f][r][j] * fvec[r]
+// over all 2N rows (the reference multiplies psi_hat^T by the force vector [0; f_ext]).
+__global__ void __launch_bounds__(128)
+k_modal_projection(int n, const cplx* __restrict__ psi_all, const cplx* __restrict__ fvec, cplx* __restrict__ out)
+{
+    const int f = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const cplx* psi = psi_all + (long long)f * n * n + j;
+    cplx acc = mk(0, 0);
+    for (int r = 0; r < n; ++r) {
+        const cplx fr = fvec[r];
+        if (fr.x != 0.0 || fr.y != 0.0) acc = cfma(psi[(long long)r * n], fr, acc);
+    }
+    out[(long long)f * n + j] = acc;
+}
+
+extern "C" int axs_launch_modal_projection(int n, int nf, const cplx* psi, const cplx* fvec, cplx* out, cudaStream_t st)
+{
+    k_modal_projection<<<dim3((n + 127) / 128, nf), 128, 0, st>>>(n, psi, fvec, out);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int axs_launch_energy_ratio(int N, int nf, const cplx* psi, const int* tclass,
                                        int nnz_t, const int* rt, const int* ct, const cplx* vt,
                                        int nnz_p, const int* rp, const int* cp, const cplx* vp,

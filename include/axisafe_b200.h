@@ -164,6 +164,13 @@ int axs_quadratic_forms(int N, int nf, const axs_cplx* psi, const int* tclass, i
                         int n_mat, const int* mat_off, const int* rows, const int* cols,
                         const axs_cplx* vals, axs_cplx* out, void* stream);
 
+/* ---- forced response -------------------------------------------
+ * Replaces np.matmul(psi_hat^T, force_vector) of WaveElementAxisym.point_excited_waves,
+ * solver.py:428-435:  out[f][j] = sum_r psi[f][r][j] * fvec[r],  fvec = [0; f_ext] of length 2N.
+ * The scalar factor i sinc(n theta_0 / pi) / (2 pi r_f) is applied by the host. */
+int axs_modal_projection(int N, int nf, const axs_cplx* psi, const axs_cplx* fvec, axs_cplx* out,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

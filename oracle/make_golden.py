@@ -137,9 +137,15 @@ def energy_velocity_fixtures():
             sol.energy_ratio()
             sol.k_propagating(*KPROP[name])
             sol.energy_velocity(only_propagating=False)
+        # forced response (solver.py:411-474): unit force on the first solid DOF
+        f_ext = np.zeros(mesh.no_of_dofs)
+        f_ext[mesh.dof_domains['solid'][0]] = 1.0
+        with refshim.quiet():
+            frf = sol.calculate_frf(0.01, 0.05, f_ext, distance=0.3)
         path = os.path.join(outdir, 'envel_%s_n%d.npz' % (name, n))
         np.savez_compressed(path, f=c['f'], k=sol.k, e_k=sol.e_k, e_p=sol.e_p, p=sol.p, en_vel=sol.en_vel,
-                            prop_idx=np.array(sol.propagating_indices), kprop_args=np.array(KPROP[name]))
+                            prop_idx=np.array(sol.propagating_indices), kprop_args=np.array(KPROP[name]),
+                            frf=frf, frf_dof=int(mesh.dof_domains['solid'][0]))
         print('%-32s nf=%3d 2N=%3d %6.0f KB' % (os.path.basename(path), len(c['f']), sol.k.shape[1],
                                                os.path.getsize(path) / 1024))
 

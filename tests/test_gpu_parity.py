@@ -352,3 +352,48 @@ def test_energy_velocity_vs_reference(name, n, kw):
         sol.energy_velocity()
     assert sol.en_vel.shape == (len(c['f']), len(sol.propagating_indices))
     assert np.allclose(sol.en_vel, full_vel[:, sol.propagating_indices], rtol=1e-12, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize('name,n,kw', [('aristegui', 0, {'nf': 40}), ('pipe_soil_pml', 0, {'nf': 30}),
+                                       ('gravenkamp', 1, {'nf': 30})],
+                         ids=['aristegui-n0', 'pipe_soil_pml-n0', 'gravenkamp-n1'])
+def test_forced_response_vs_reference(name, n, kw):
+    """Row N4: point_excited_waves / calculate_frf against the reference's modal FRF contributions
+    (shape x amplitude is invariant under the +-1 ambiguity of the B-normalised mode shapes)."""
+    import os
+    import axisafe_b200 as ax
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'envel_%s_n%d.npz' % (name, n)))
+    c = make_case(name, n, kw)
+    m = _mesh(c)
+    sol = ax.solver.WaveElementAxisym(m)
+    with contextlib.redirect_stdout(io.StringIO()):
+        sol.solve(c['f'])
+        sol.energy_ratio()
+        sol.k_propagating(*g['kprop_args'])
+    N = m.no_of_dofs
+    f_ext = np.zeros(N)
+    f_ext[int(g['frf_dof'])] = 1.0
+    amps = sol.point_excited_waves(0.01, 0.05, f_ext)
+    assert amps.shape == (len(c['f']), 2 * N, 1)
+    psi = sol.psi_hat
+    want = 1j * np.sinc(n * 0.01 / np.pi) / (2 * np.pi * 0.05) * np.einsum('frj,r->fj', psi[:, N:, :], f_ext)
+    assert np.abs(amps[:, :, 0] - want).max() <= 1e-12 * np.abs(want).max()
+    frf = sol.calculate_frf(0.01, 0.05, f_ext, distance=0.3)
+    assert frf.shape == (len(c['f']), N, len(sol.propagating_indices))
+    ref, kref = g['frf'], g['k'][:, g['prop_idx']]
+    kmine = sol.k[:, sol.propagating_indices]
+    checked = 0
+    for i in range(1, len(c['f'])):
+        for a in range(kref.shape[1]):
+            if abs(kref[i, a].imag) > 50 or np.abs(ref[i, :, a]).max() <= 1e-6 * np.abs(ref[i]).max():
+                continue                                   # decayed over the distance / not excited by this force
+            d = np.abs(kmine[i] - kref[i, a])
+            b = int(d.argmin())
+            gap = np.sort(np.abs(g['k'][i] - kref[i, a]))[1] / abs(kref[i, a])
+            if d[b] > 1e-7 * abs(kref[i, a]) or gap < 1e-4:
+                continue
+            err = np.abs(frf[i, :, b] - ref[i, :, a]).max() / np.abs(ref[i, :, a]).max()
+            assert err < 1e-5, (i, a, err)
+            checked += 1
+    assert checked > 5
