@@ -105,9 +105,16 @@ k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ C
     __syncthreads();
 
     // ---- phase C: Householder reduction to Hessenberg form ------------------------------
-    for (int k = 0; k < n - 2; ++k) {
-        // reflector from column k, rows k+1..n-1  (zlarfg)
-        const cplx* colk = A + (long long)k * n;
+    // One pass over the L2-resident trailing matrix per reflector: the rank-2 update of reflector
+    // k is fused with the products w' = A v', y' = A^H v' of reflector k+1 (column k+1 is updated
+    // first and the next reflector generated from it; same scheme as k_reduce_big).
+    cplx* v2 = (cplx*)(Wn + (size_t)n * n);          // next reflector and its products
+    cplx* w2 = v2 + n;
+    cplx* y2 = w2 + n;
+
+    // reflector from column k (rows k+1..n-1) into vd; returns tau (uniform).  zlarfg.
+    auto gen_reflector = [&](int k, cplx* vd) -> cplx {
+        cplx* colk = A + (long long)k * n;
         double part = 0.0;
         for (int i = k + 2 + tid; i < n; i += RED_THREADS) part += cabs2(colk[i]);
         part = warp_sum(part);
@@ -117,33 +124,38 @@ k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ C
         for (int q = 0; q < RED_WARPS; ++q) xnorm2 += red[q];
         const cplx alpha = colk[k + 1];
         cplx tau = mk(0, 0);
-        double beta = 0.0;
-        if (!(xnorm2 == 0.0 && alpha.y == 0.0)) {
+        double beta = alpha.x;
+        cplx sc = mk(0, 0);
+        const bool trivial = (xnorm2 == 0.0 && alpha.y == 0.0);
+        if (!trivial) {
             beta = -copysign(sqrt(cabs2(alpha) + xnorm2), alpha.x);
             tau = mk((beta - alpha.x) / beta, -alpha.y / beta);
-            cplx sc = cdiv(mk(1.0, 0.0), mk(alpha.x - beta, alpha.y));
-            for (int i = k + 1 + tid; i < n; i += RED_THREADS) {
-                cplx vi = (i == k + 1) ? mk(1.0, 0.0) : cmul(colk[i], sc);
-                v[i] = vi;
-                if (i > k + 1) A[(long long)k * n + i] = vi;      // keep the reflector for the back-transformation
-            }
-        } else {
-            if (tid == 0) wk.tau[(long long)f * n + k] = tau;
-            __syncthreads();
-            continue;                                             // uniform: nothing to do
+            sc = cdiv(mk(1.0, 0.0), mk(alpha.x - beta, alpha.y));
         }
-        __syncthreads();                                          // every thread has read alpha
+        for (int i = tid; i < n; i += RED_THREADS) {
+            cplx vi = mk(0, 0);
+            if (i == k + 1) vi = mk(1.0, 0.0);
+            else if (i > k + 1) {
+                vi = cmul(colk[i], sc);
+                colk[i] = vi;                                 // keep the reflector for the back-transformation
+            }
+            vd[i] = vi;
+        }
+        __syncthreads();                                      // every thread has read alpha
         if (tid == 0) {
-            A[(long long)k * n + k + 1] = mk(beta, 0.0);
+            if (!trivial) colk[k + 1] = mk(beta, 0.0);
             wk.tau[(long long)f * n + k] = tau;
         }
+        return tau;
+    };
 
-        // pass 1: w = A[:, k+1:] v   and   y_j = v^H A[k+1:, j].  Two columns per warp iteration
-        // with all loads issued first (the matrix lives in L2: latency, not bandwidth, is the cost).
+    cplx tau = gen_reflector(0, v);
+    {
+        // products of reflector 0: w = A[:, 1:] v and y_j = v^H A[:, j]
         cplx wacc[RED_ROWS];
 #pragma unroll
         for (int q = 0; q < RED_ROWS; ++q) wacc[q] = mk(0, 0);
-        for (int j = k + 1 + 2 * warp; j < n; j += 2 * RED_WARPS) {
+        for (int j = 1 + 2 * warp; j < n; j += 2 * RED_WARPS) {
             const bool two = (j + 1 < n);
             const cplx* col0 = A + (long long)j * n;
             const cplx* col1 = col0 + n;
@@ -161,11 +173,9 @@ k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ C
                 const int i = lane + 32 * q;
                 if (i < n) {
                     wacc[q] = cfma(e0[q], v0, cfma(e1[q], v1, wacc[q]));
-                    if (i > k) {
-                        const cplx vi = v[i];
-                        y0 = cfmac(e0[q], vi, y0);
-                        y1 = cfmac(e1[q], vi, y1);
-                    }
+                    const cplx vi = v[i];
+                    y0 = cfmac(e0[q], vi, y0);
+                    y1 = cfmac(e1[q], vi, y1);
                 }
             }
             y0 = warp_csum(y0); y1 = warp_csum(y1);
@@ -173,17 +183,19 @@ k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ C
         }
 #pragma unroll
         for (int q = 0; q < RED_ROWS; ++q) {
-            int i = lane + 32 * q;
+            const int i = lane + 32 * q;
             if (i < n) wpart[warp * n + i] = wacc[q];
         }
         __syncthreads();
         for (int i = tid; i < n; i += RED_THREADS) {
-            cplx s = mk(0, 0);
-            for (int q = 0; q < RED_WARPS; ++q) s = cadd(s, wpart[q * n + i]);
-            wv[i] = s;
+            cplx sacc = mk(0, 0);
+            for (int q = 0; q < RED_WARPS; ++q) sacc = cadd(sacc, wpart[q * n + i]);
+            wv[i] = sacc;
         }
         __syncthreads();
-        // alpha2 = v^H w[k+1:]
+    }
+    for (int k = 0; k < n - 2; ++k) {
+        // alpha2 = v^H w
         cplx ap = mk(0, 0);
         for (int i = k + 1 + tid; i < n; i += RED_THREADS) ap = cfmac(wv[i], v[i], ap);
         ap = warp_csum(ap);
@@ -193,9 +205,24 @@ k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ C
         for (int q = 0; q < RED_WARPS; ++q) { al.x += red[2 * q]; al.y += red[2 * q + 1]; }
         const cplx tal = cmul(tau, al);
         const cplx ctau = cconj(tau);
-        // pass 2: A[i,j] -= tau w_i conj(v_j)  (all i)  and  -= conj(tau) v_i z_j (i > k),
-        //         z_j = y_j - tau alpha conj(v_j)
-        for (int j = k + 1 + 2 * warp; j < n; j += 2 * RED_WARPS) {
+        // column k+1 first: A[i,j] -= tau w_i conj(v_j) + conj(tau) v_i z_j,  z_j = y_j - tau alpha2 conj(v_j)
+        {
+            const int j = k + 1;
+            cplx* col = A + (long long)j * n;
+            const cplx cvj = cconj(v[j]);
+            const cplx t = cmul(tau, cvj);
+            const cplx z = cmul(ctau, csub(y[j], cmul(tal, cvj)));
+            for (int i = tid; i < n; i += RED_THREADS) col[i] = cfms(v[i], z, cfms(wv[i], t, col[i]));
+        }
+        __syncthreads();
+        const bool has_next = (k + 1 < n - 2);
+        cplx tau2 = mk(0, 0);
+        if (has_next) tau2 = gen_reflector(k + 1, v2);        // (barriers inside; uniform branch)
+        // fused pass over the columns j >= k+2
+        cplx wacc[RED_ROWS];
+#pragma unroll
+        for (int q = 0; q < RED_ROWS; ++q) wacc[q] = mk(0, 0);
+        for (int j = k + 2 + 2 * warp; j < n; j += 2 * RED_WARPS) {
             const bool two = (j + 1 < n);
             cplx* col0 = A + (long long)j * n;
             cplx* col1 = col0 + n;
@@ -210,19 +237,46 @@ k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ C
             const cplx t0 = cmul(tau, cv0), t1 = cmul(tau, cv1);
             const cplx z0 = cmul(ctau, csub(y[j], cmul(tal, cv0)));
             const cplx z1 = two ? cmul(ctau, csub(y[j + 1], cmul(tal, cv1))) : mk(0, 0);
+            const cplx n0 = has_next ? v2[j] : mk(0, 0), n1 = (has_next && two) ? v2[j + 1] : mk(0, 0);
+            cplx y0 = mk(0, 0), y1 = mk(0, 0);
 #pragma unroll
             for (int q = 0; q < RED_ROWS; ++q) {
                 const int i = lane + 32 * q;
                 if (i < n) {
-                    const cplx wi = wv[i];
-                    cplx a0 = cfms(wi, t0, e0[q]), a1 = cfms(wi, t1, e1[q]);
-                    if (i > k) { const cplx vi = v[i]; a0 = cfms(vi, z0, a0); a1 = cfms(vi, z1, a1); }
+                    const cplx wi = wv[i], vi = v[i];
+                    const cplx a0 = cfms(vi, z0, cfms(wi, t0, e0[q]));
+                    const cplx a1 = cfms(vi, z1, cfms(wi, t1, e1[q]));
                     col0[i] = a0;
                     if (two) col1[i] = a1;
+                    if (has_next) {
+                        const cplx vn = v2[i];
+                        wacc[q] = cfma(a0, n0, cfma(a1, n1, wacc[q]));
+                        y0 = cfmac(a0, vn, y0);
+                        y1 = cfmac(a1, vn, y1);
+                    }
                 }
+            }
+            if (has_next) {
+                y0 = warp_csum(y0); y1 = warp_csum(y1);
+                if (lane == 0) { y2[j] = y0; if (two) y2[j + 1] = y1; }
+            }
+        }
+        if (has_next) {
+#pragma unroll
+            for (int q = 0; q < RED_ROWS; ++q) {
+                const int i = lane + 32 * q;
+                if (i < n) wpart[warp * n + i] = wacc[q];
+            }
+            __syncthreads();
+            for (int i = tid; i < n; i += RED_THREADS) {
+                cplx sacc = mk(0, 0);
+                for (int q = 0; q < RED_WARPS; ++q) sacc = cadd(sacc, wpart[q * n + i]);
+                w2[i] = sacc;
             }
         }
         __syncthreads();
+        { cplx* tp = v; v = v2; v2 = tp; tp = wv; wv = w2; w2 = tp; tp = y; y = y2; y2 = tp; }
+        tau = tau2;
     }
 
     // ---- phase D: packed copies of H -----------------------------------------------------
@@ -241,7 +295,7 @@ k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ C
 static size_t reduce_smem(int n) {
     return (size_t)(3 + RED_WARPS) * n * sizeof(cplx) + (size_t)n * sizeof(double)
            + (RED_WARPS * 2 + 8) * sizeof(double) + (size_t)2 * n * sizeof(float)
-           + (size_t)n * n * sizeof(float);
+           + (size_t)n * n * sizeof(float) + (size_t)3 * n * sizeof(cplx) + 16;
 }
 
 // =========================================================================================
@@ -1075,7 +1129,7 @@ extern "C" int axs_launch_hqr_stages(int n, int nf, int m_first, cplx* Hp, cplx*
                                      cudaStream_t st)
 {
     const char* st_env = getenv("AXS_HQR_STAGES");
-    const int stages = st_env ? atoi(st_env) : 3;
+    const int stages = st_env ? atoi(st_env) : 4;      // 4 stages measured fastest on B200 (36.3 vs 37.7 ms)
     const char* mode = getenv("AXS_HQR_BULGES");
     int bulges = mode ? atoi(mode) : MB_MAX;
     if (bulges < 1 || bulges > MB_MAX) bulges = MB_MAX;
@@ -1086,9 +1140,24 @@ extern "C" int axs_launch_hqr_stages(int n, int nf, int m_first, cplx* Hp, cplx*
     k_hqr_mb<512, 2, 3><<<nf, 512, smem2, st>>>(n, bulges, 0, m3, Hp, Hp, eig, info, ucur);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || m3 == 0) return (int)e;
+    // stages 4 and 5 (AXS_HQR_STAGES >= 4 / 5): 256 threads, 4 and 5 CTAs per SM
+    int m4 = (stages >= 4) ? axs_hqr_stage_capacity(4) : 0;
+    if (m4 >= m3 || m4 < 8) m4 = 0;
+    int m5 = (stages >= 5 && m4) ? axs_hqr_stage_capacity(5) : 0;
+    if (m5 >= m4 || m5 < 8) m5 = 0;
     size_t smem3 = hqr_mb_smem(m3);
     AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<384, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    k_hqr_mb<384, 3, 3><<<nf, 384, smem3, st>>>(n, bulges, 0, 0, Hp, Hp, eig, info, ucur);
+    k_hqr_mb<384, 3, 3><<<nf, 384, smem3, st>>>(n, bulges, 0, m4, Hp, Hp, eig, info, ucur);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || m4 == 0) return (int)e;
+    size_t smem4 = hqr_mb_smem(m4);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<256, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+    k_hqr_mb<256, 4, 3><<<nf, 256, smem4, st>>>(n, bulges, 0, m5, Hp, Hp, eig, info, ucur);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || m5 == 0) return (int)e;
+    size_t smem5 = hqr_mb_smem(m5);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<256, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+    k_hqr_mb<256, 5, 3><<<nf, 256, smem5, st>>>(n, bulges, 0, 0, Hp, Hp, eig, info, ucur);
     return (int)cudaGetLastError();
 }
 
@@ -1116,7 +1185,7 @@ extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, c
     // memory (512 threads, 64 registers, 2 CTAs per SM); stage 3: fits three times (384 threads,
     // 56 registers, 3 CTAs per SM).  AXS_HQR_STAGES=1|2|3 limits the cascade (A/B testing).
     const char* st_env = getenv("AXS_HQR_STAGES");
-    const int stages = st_env ? atoi(st_env) : 3;
+    const int stages = st_env ? atoi(st_env) : 4;
     int m2 = (stages >= 2) ? axs_hqr_stage_capacity(2) : 0;
     if (m2 >= n || m2 < 8) m2 = 0;
     size_t smem = hqr_mb_smem(n);
