@@ -1022,6 +1022,17 @@ extern "C" int axs_launch_reduce_big(int N, int hb, const cplx* K0s, const cplx*
     return (int)cudaGetLastError();
 }
 
+// windowed QR down to an active block of m_stop rows, in place on packed matrices H (also usable as
+// stage 0 of the shared-memory cascade: AXS_HQR_WINDOW_FIRST)
+extern "C" int axs_launch_hqr_window(int n, int nf, int m_stop, cplx* H, cplx* eig, int* info, int* ucur,
+                                     cudaStream_t st)
+{
+    const size_t smem = hqr_big_smem();
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_hqr_big<<<nf, HB_NT, smem, st>>>(n, m_stop, H, eig, info, ucur);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int axs_launch_hqr_big(int n, int nf, cplx* eig, int* info, AxsWorkBig wk, cudaStream_t st)
 {
     const int m2 = axs_hqr_stage_capacity(2);            // what the 2-CTA/SM shared-memory stage can hold

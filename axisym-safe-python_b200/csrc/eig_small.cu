@@ -1089,6 +1089,137 @@ static size_t backnorm_smem(int n) {
 }
 
 
+// -----------------------------------------------------------------------------------------
+// k_backnorm_reg: same operation as k_backnorm with the mode vectors in REGISTERS.
+// CTA = one frequency x 16 modes, 256 threads = 16 modes x 16 row groups (rows i = grp mod 16,
+// at most 11 per thread); a reflector costs one shared-memory read of v per row, a 2-step
+// reduction (shuffle across the two row groups of a warp, 8 partials through shared memory) and
+// one block barrier.  k_backnorm keeps the 64-mode slab in shared memory and is bound by its
+// bandwidth (three passes over the slab per reflector); this one is bound by instruction issue.
+#define BR_COLS 16
+#define BR_ROWS 11                      // ceil(AXS_MAX_SMALL_N2 / 16); the slot switches below list 0..10
+static_assert(AXS_MAX_SMALL_N2 <= 16 * 11, "k_backnorm_reg: register slots");
+#define BR_AHEAD 4
+#define BR_RING (BR_AHEAD + 2)
+__global__ void __launch_bounds__(256, 3)
+k_backnorm_reg(int N, int hb, const cplx* __restrict__ Cb, const cplx* __restrict__ K6d,
+               const cplx* __restrict__ eig_all, cplx* __restrict__ psi_all, AxsWork wk)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = 2 * N;
+    cplx* vbuf = (cplx*)smem_raw;                     // [BR_RING][n]   (slot kk+1 of a buffer holds tau[kk])
+    cplx* red = vbuf + BR_RING * n;                         // [2][8][16], reused [16][16] by the epilogue
+    cplx* Xs = red + 256;                             // [n][16]  (epilogue only)
+    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int col = tid & 15, grp = tid >> 4;
+    const int mode = blockIdx.x * BR_COLS + col;
+    const bool live = mode < n;
+    const cplx* A = wk.A + (long long)f * n * n;
+    const cplx* tau = wk.tau + (long long)f * n;
+    const double* dsc = wk.scale + (long long)f * n;
+    cplx* psi = psi_all + (long long)f * n * n;
+
+    cplx x[BR_ROWS];
+#pragma unroll
+    for (int q = 0; q < BR_ROWS; ++q) {
+        const int i = grp + 16 * q;
+        x[q] = (live && i < n) ? psi[(long long)i * n + mode] : mk(0, 0);
+    }
+    // reflectors travel through a ring of BR_RING shared-memory buffers, fetched BR_AHEAD steps
+    // ahead with cp.async (L2 latency ~ 4 steps of this kernel)
+    auto stage = [&](int kk) {
+        if (kk >= 0) {
+            cplx* dst = vbuf + (size_t)(kk % BR_RING) * n;
+            const int i = kk + 1 + tid;
+            if (i < n) __pipeline_memcpy_async(dst + i, (i == kk + 1) ? tau + kk : A + (long long)kk * n + i, sizeof(cplx));
+        }
+        __pipeline_commit();
+    };
+#pragma unroll
+    for (int a = 0; a < BR_AHEAD; ++a) stage(n - 3 - a);
+    __pipeline_wait_prior(BR_AHEAD - 1);
+    __syncthreads();
+    for (int kk = n - 3; kk >= 0; --kk) {
+        const cplx* vv = vbuf + (size_t)(kk % BR_RING) * n;
+        stage(kk - BR_AHEAD);
+        const cplx t = vv[kk + 1];
+        const bool skip = (t.x == 0.0 && t.y == 0.0);
+        if (!skip) {
+            cplx part = mk(0, 0);
+            // rows <= kk are untouched: jump over the register slots that hold none of the active rows
+            // (uniform switch with fall-through keeps the register indexing static)
+#define BR_DOT(q) { const int i = grp + 16 * (q); \
+                    if (i > kk && i < n) part = (i == kk + 1) ? cadd(part, x[q]) : cfmac(x[q], vv[i], part); }
+            switch ((kk + 1) >> 4) {
+                case 0: BR_DOT(0) case 1: BR_DOT(1) case 2: BR_DOT(2) case 3: BR_DOT(3) case 4: BR_DOT(4)
+                case 5: BR_DOT(5) case 6: BR_DOT(6) case 7: BR_DOT(7) case 8: BR_DOT(8) case 9: BR_DOT(9)
+                default: BR_DOT(10)
+            }
+#undef BR_DOT
+            part.x += __shfl_xor_sync(0xffffffffu, part.x, 16);
+            part.y += __shfl_xor_sync(0xffffffffu, part.y, 16);
+            if (lane < 16) red[(kk & 1) * 128 + warp * 16 + lane] = part;
+        }
+        __pipeline_wait_prior(BR_AHEAD - 1);               // reflector kk-1 has landed
+        __syncthreads();
+        if (!skip) {
+            const cplx* rd = red + (kk & 1) * 128 + col;
+            cplx dot = rd[0];
+#pragma unroll
+            for (int w = 1; w < 8; ++w) dot = cadd(dot, rd[w * 16]);
+            const cplx td = cmul(t, dot);
+#define BR_UPD(q) { const int i = grp + 16 * (q); \
+                    if (i > kk && i < n) x[q] = (i == kk + 1) ? csub(x[q], td) : cfms(td, vv[i], x[q]); }
+            switch ((kk + 1) >> 4) {
+                case 0: BR_UPD(0) case 1: BR_UPD(1) case 2: BR_UPD(2) case 3: BR_UPD(3) case 4: BR_UPD(4)
+                case 5: BR_UPD(5) case 6: BR_UPD(6) case 7: BR_UPD(7) case 8: BR_UPD(8) case 9: BR_UPD(9)
+                default: BR_UPD(10)
+            }
+#undef BR_UPD
+        }
+    }
+    // v = D y into shared memory, then B-normalise with u = v[N:]:  s = 2 k u^T K6 u + u^T C u
+#pragma unroll
+    for (int q = 0; q < BR_ROWS; ++q) {
+        const int i = grp + 16 * q;
+        if (i < n) Xs[i * BR_COLS + col] = cscale(x[q], dsc[i]);
+    }
+    __syncthreads();
+    const cplx lam = eig_all[(long long)f * n + (live ? mode : n - 1)];
+    const int W = 2 * hb + 1;
+    cplx s6 = mk(0, 0), sc = mk(0, 0);
+    for (int r = grp; r < N; r += 16) {
+        const cplx ur = Xs[(N + r) * BR_COLS + col];
+        s6 = cfma(cmul(ur, ur), K6d[r], s6);
+        cplx cu0 = mk(0, 0), cu1 = mk(0, 0);
+        const int c0 = max(0, r - hb), c1 = min(N - 1, r + hb);
+        const cplx* crow = Cb + (long long)r * W - r + hb;
+        int c = c0;
+        for (; c + 1 <= c1; c += 2) {
+            cu0 = cfma(crow[c], Xs[(N + c) * BR_COLS + col], cu0);
+            cu1 = cfma(crow[c + 1], Xs[(N + c + 1) * BR_COLS + col], cu1);
+        }
+        if (c <= c1) cu0 = cfma(crow[c], Xs[(N + c) * BR_COLS + col], cu0);
+        sc = cfma(ur, cadd(cu0, cu1), sc);
+    }
+    red[grp * 16 + col] = cadd(cscale(cmul(lam, s6), 2.0), sc);
+    __syncthreads();
+    cplx nrm = red[col];
+#pragma unroll
+    for (int g = 1; g < 16; ++g) nrm = cadd(nrm, red[g * 16 + col]);
+    const cplx inv = cdiv(mk(1.0, 0.0), csqrt_(nrm));
+    if (live) {
+        for (int r = grp; r < N; r += 16) {
+            const cplx u = cmul(Xs[(N + r) * BR_COLS + col], inv);
+            psi[(long long)(N + r) * n + mode] = u;
+            psi[(long long)r * n + mode] = cmul(lam, u);
+        }
+    }
+}
+
+static size_t backnorm_reg_smem(int n) { return ((size_t)BR_RING * n + 256 + (size_t)n * BR_COLS) * sizeof(cplx); }
+
+
 // =========================================================================================
 // debug accessor: dense H and scale factors out of the workspace
 // =========================================================================================
@@ -1161,6 +1292,9 @@ extern "C" int axs_launch_hqr_stages(int n, int nf, int m_first, cplx* Hp, cplx*
     return (int)cudaGetLastError();
 }
 
+extern "C" int axs_launch_hqr_window(int n, int nf, int m_stop, cplx* H, cplx* eig, int* info, int* ucur,
+                                     cudaStream_t st);
+
 extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, cudaStream_t st)
 {
     const char* mode = getenv("AXS_HQR_BULGES");
@@ -1188,6 +1322,16 @@ extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, c
     const int stages = st_env ? atoi(st_env) : 4;
     int m2 = (stages >= 2) ? axs_hqr_stage_capacity(2) : 0;
     if (m2 >= n || m2 < 8) m2 = 0;
+    const char* wf = getenv("AXS_HQR_WINDOW_FIRST");       // A/B: windowed global-memory QR as stage 1
+    if (wf && atoi(wf) && m2) {
+        int ms = atoi(wf) > 1 ? atoi(wf) : m2;
+        if (ms > m2) ms = m2;
+        AXS_CUDA_OK(cudaMemcpyAsync(wk.Hp, wk.Hc, (size_t)nf * hcol_size(n) * sizeof(cplx),
+                                    cudaMemcpyDeviceToDevice, st));       // Hc stays intact
+        int rc = axs_launch_hqr_window(n, nf, ms, wk.Hp, eig, info, wk.ucur, st);
+        if (rc) return rc;
+        return axs_launch_hqr_stages(n, nf, m2, wk.Hp, eig, info, wk.ucur, st);
+    }
     size_t smem = hqr_mb_smem(n);
     AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_hqr_mb<512, 1, 3><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
@@ -1207,9 +1351,18 @@ extern "C" int axs_launch_modes(int N, int hb, const cplx* Cb, const cplx* K6d, 
     k_modes<<<dim3((n + 8 * nw - 1) / (8 * nw), nf), 32 * nw, smem, st>>>(N, hb, Cb, K6d, eig, psi, wk);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    size_t smem2 = backnorm_smem(n);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_backnorm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    k_backnorm<<<dim3((n + BN_COLS - 1) / BN_COLS, nf), 256, smem2, st>>>(N, hb, Cb, K6d, eig, psi, wk);
+    // default: 64-mode slab in shared memory (7.0 ms / 2000 points); AXS_BACKNORM_REG=1 selects the
+    // register-resident variant (measured 7.7 ms: 4x more CTAs each streaming the reflectors)
+    const char* regv = getenv("AXS_BACKNORM_REG");
+    if (!(regv && atoi(regv))) {
+        size_t smem2 = backnorm_smem(n);
+        AXS_CUDA_OK(cudaFuncSetAttribute(k_backnorm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        k_backnorm<<<dim3((n + BN_COLS - 1) / BN_COLS, nf), 256, smem2, st>>>(N, hb, Cb, K6d, eig, psi, wk);
+        return (int)cudaGetLastError();
+    }
+    size_t smem2 = backnorm_reg_smem(n);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_backnorm_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    k_backnorm_reg<<<dim3((n + BR_COLS - 1) / BR_COLS, nf), 256, smem2, st>>>(N, hb, Cb, K6d, eig, psi, wk);
     return (int)cudaGetLastError();
 }
 

@@ -127,7 +127,7 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_track_mma(int n, const cplx* __restrict__ psi_all, const cplx* __restrict__ Y_all,
             int* __restrict__ arg_all, double* __restrict__ amax_all)
 {
