@@ -374,10 +374,14 @@ def _solve_pipelined(sol, torch, _native, ops, nf, n2, host_work=None):
     K = int(os.environ.get('AXS_PIPE_CHUNKS', 4 if nf >= 512 else 2))
     trace = os.environ.get('AXS_PIPE_TRACE')
     tl = [('start', time.perf_counter())]
-    if K == 4:
+    if os.environ.get('AXS_PIPE_BOUNDS'):               # e.g. "0.3,0.6,0.8,1" (A/B testing)
+        fr = [float(x) for x in os.environ['AXS_PIPE_BOUNDS'].split(',')]
+        bounds = [0] + [int(nf * x) for x in fr[:-1]] + [nf]
+        K = len(bounds) - 1
+    elif K == 4:
         # chunks run pairwise on two streams; the last pair is smaller so that the un-overlapped
         # tail (scan + gather + download of the final chunk) is short
-        bounds = [0, int(nf * 0.32), int(nf * 0.64), int(nf * 0.82), nf]
+        bounds = [0, int(nf * 0.4), int(nf * 0.8), int(nf * 0.9), nf]    # measured best of six splits
     else:
         bounds = [nf * c // K for c in range(K + 1)]
     nn = n2 * n2

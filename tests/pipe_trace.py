@@ -10,7 +10,11 @@ with contextlib.redirect_stdout(io.StringIO()):
     m.assemble_matrices(c['n'])
 sol = ax.solver.WaveElementAxisym(m)
 for K in (sys.argv[1:] or ['4']):
-    os.environ['AXS_PIPE_CHUNKS'] = K
+    if ',' in K:
+        os.environ['AXS_PIPE_BOUNDS'] = K
+    else:
+        os.environ.pop('AXS_PIPE_BOUNDS', None)
+        os.environ['AXS_PIPE_CHUNKS'] = K
     for rep in range(4):
         torch.cuda.synchronize(); t = time.perf_counter()
         with contextlib.redirect_stdout(io.StringIO()):
