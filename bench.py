@@ -268,12 +268,14 @@ def gpu_arm(args):
                    'l2': 'working set 1.5 GB per sweep >> 126 MB L2 (no flush needed)',
                    'parallelism': 'frequency axis sharded, %d rank(s), 1-point halo; 2 frequency chunks on 2 CUDA streams per rank (value); e2e = solve(): 4-chunk pipeline, psi_hat download overlapped with compute at N=1' % world},
         'kernel_ms': {k_: v / args.steps for k_, v in per_kernel.items()},
-        'roofline': {'bound': 'tensor', 'kernel': 'k_hqr_mb (3 stages)', 'achieved': achieved, 'peak': fp64_peak,
+        'roofline': {'bound': 'tensor', 'kernel': 'k_hqr_mb (4 stage launches)', 'achieved': achieved, 'peak': fp64_peak,
                      'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
-                     'traffic': {'dram_bytes_per_launch': int(nloc * 130112), 'unit': 'B',
-                                 'note': 'ncu --set full (profiles/r1_ncu_summary.csv): stage 1 reads 38.5 MB for 296 '
-                                         'matrices = the packed Hessenberg input once, writes ~0; stages 2/3 re-read the '
-                                         'parked leading block (33 + 22 MB)'},
+                     'traffic': int(nloc * 471.5e3),
+                     'traffic_note': 'DRAM bytes (read + write) of the QR cascade per sweep, from ncu --set full '
+                                     '(profiles/r1b_ncu_summary.csv): 130.9 + 112.8 + 74.7 + 55.9 MB read and 97 MB '
+                                     'written per 1000 matrices over its four stage launches; the algorithmic bytes '
+                                     'are the packed Hessenberg matrix once (130 KB per matrix) - the rest is the '
+                                     'leading block parked and re-read between stages',
                      'note': 'FP64 pipe (DFMA/DMMA share one roof on B200); algorithmic flops = 80*n2^3 per '
                              'point for the QR kernel (zhseqr share of F_alg = 100*n2^3); peak = ' + how,
                      'pipeline_frac': value / world * f_alg(n2) / 1e12 / fp64_peak},
@@ -281,7 +283,7 @@ def gpu_arm(args):
                 'h2d_bytes_per_step': int(8 * nloc),
                 'd2h_bytes_per_step': int(nloc * n2 * 16 + (nloc - 1) * n2 * 12 + nloc * 4 + POINTS_PER_GPU * n2 * n2 * 16),
                 'k_only': {'value': nf_total / e2e_k_s, 'note': 'solve() without reading psi_hat back'}},
-        'gpu_launches': (2 * 6 + 3) * args.steps,   # per chunk: reduce, hqr x3, modes, backnorm; then bpsi, track_gemm, apply_order
+        'gpu_launches': (2 * 7 + 3) * args.steps,   # per chunk: reduce, hqr x4, modes, backnorm; then bpsi, track_mma, apply_order
         'clocks': clocks.summary(),
         'hbm_peak_gbs': peaks.get('hbm_gbs'),
     }
