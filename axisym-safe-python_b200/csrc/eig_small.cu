@@ -1235,11 +1235,18 @@ __global__ void k_unpack_H(int n, AxsWork wk, cplx* __restrict__ Hd)
 }
 
 // ------------------------------------------------------------------------------ launchers
+extern "C" int axs_launch_reduce_oc(int N, int hb, const cplx* K0s, const cplx* Cb, const cplx* Mb,
+                                    const cplx* K1c, const cplx* K6d, const double* omega, int nf,
+                                    const cplx* S_in, AxsWork wk, cudaStream_t st);
+
 extern "C" int axs_launch_reduce(int N, int hb, const cplx* K0s, const cplx* Cb, const cplx* Mb,
                                  const cplx* K1c, const cplx* K6d, const double* omega, int nf,
                                  const cplx* S_in, AxsWork wk, cudaStream_t st)
 {
     const int n = 2 * N;
+    // 2N >= 96: trailing block on chip (eig_reduce.cu); smaller matrices stay L2-resident, 2 CTAs per SM
+    const int rc = axs_launch_reduce_oc(N, hb, K0s, Cb, Mb, K1c, K6d, omega, nf, S_in, wk, st);
+    if (rc != -1) return rc;
     size_t smem = reduce_smem(n);
     AXS_CUDA_OK(cudaFuncSetAttribute(k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_reduce<<<nf, RED_THREADS, smem, st>>>(N, hb, K0s, Cb, Mb, K1c, K6d, omega, S_in, wk);
@@ -1333,8 +1340,25 @@ extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, c
         return axs_launch_hqr_stages(n, nf, m2, wk.Hp, eig, info, wk.ucur, st);
     }
     size_t smem = hqr_mb_smem(n);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_hqr_mb<512, 1, 3><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
+    const char* lean = getenv("AXS_HQR_S1_LEAN");          // A/B: stage 1 capped at 64 registers (room for a co-resident CTA)
+    const char* wide = getenv("AXS_HQR_S1_WIDE");          // A/B: stage 1 with 1024 threads; value = bulges in flight
+    if (wide && atoi(wide)) {
+        int b1 = atoi(wide);
+        if (b1 > MB_MAX) b1 = MB_MAX;
+        if (b1 * (n + 1) <= 1024 - 32) {
+            AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<1024, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_hqr_mb<1024, 1, 1><<<nf, 1024, smem, st>>>(n, b1, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
+        } else {
+            AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<1024, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_hqr_mb<1024, 1, 2><<<nf, 1024, smem, st>>>(n, b1, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
+        }
+    } else if (lean && atoi(lean)) {
+        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hqr_mb<512, 2, 3><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
+    } else {
+        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hqr_mb<512, 1, 3><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || m2 == 0) return (int)e;
     return axs_launch_hqr_stages(n, nf, m2, wk.Hp, eig, info, wk.ucur, st);

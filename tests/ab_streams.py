@@ -38,5 +38,5 @@ def run(nchunks):
         e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return best
-for nch in (1, 2, 3, 4, 6, 8):
+for nch in [int(x) for x in (sys.argv[1:] or '1 2 3 4 6 8'.split())]:
     print('chunks/streams %d: eig_sweep %.2f ms' % (nch, run(nch)), flush=True)

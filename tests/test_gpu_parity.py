@@ -310,9 +310,14 @@ def test_energy_ratio_and_propagating_filter(name, n, kw):
             worst = max(worst, rel[ok].max())
     assert worst < 1e-5, worst
     # the filtered sets of propagating wavenumbers agree frequency by frequency
+    # (purely evanescent modes have Re k = 0 up to rounding: the reference's `Re k < 0` test then
+    # decides on the sign of noise ~1e-12 |k|, so those knife-edge entries are left out on both sides)
+    def decided(kk):
+        kk = kk[kk != 0]
+        return np.sort_complex(kk[np.abs(kk.real) > 1e-9 * np.abs(kk)])
     for i in range(1, len(c['f'])):
-        ref = np.sort_complex(g['k_ready'][i][g['k_ready'][i] != 0])
-        got = np.sort_complex(sol.k_ready[i][sol.k_ready[i] != 0])
+        ref = decided(g['k_ready'][i])
+        got = decided(sol.k_ready[i])
         assert len(ref) == len(got), (i, len(ref), len(got))
         if len(ref):
             assert np.abs(ref - got).max() <= 1e-6 * np.abs(ref).max()
