@@ -1364,6 +1364,9 @@ extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, c
     return axs_launch_hqr_stages(n, nf, m2, wk.Hp, eig, info, wk.ucur, st);
 }
 
+extern "C" int axs_launch_backnorm_wy(int N, int hb, const cplx* Cb, const cplx* K6d, int nf,
+                                      const cplx* eig, cplx* psi, AxsWork wk, cudaStream_t st);
+
 extern "C" int axs_launch_modes(int N, int hb, const cplx* Cb, const cplx* K6d, int nf,
                                 const cplx* eig, cplx* psi, AxsWork wk, cudaStream_t st)
 {
@@ -1377,6 +1380,11 @@ extern "C" int axs_launch_modes(int N, int hb, const cplx* Cb, const cplx* K6d, 
     if (e != cudaSuccess) return (int)e;
     // default: 64-mode slab in shared memory (7.0 ms / 2000 points); AXS_BACKNORM_REG=1 selects the
     // register-resident variant (measured 7.7 ms: 4x more CTAs each streaming the reflectors)
+    // 2N <= 128: blocked compact-WY back-transformation on DMMA tiles (eig_backx.cu)
+    {
+        const int rc = axs_launch_backnorm_wy(N, hb, Cb, K6d, nf, eig, psi, wk, st);
+        if (rc != -1) return rc;
+    }
     const char* regv = getenv("AXS_BACKNORM_REG");
     if (!(regv && atoi(regv))) {
         size_t smem2 = backnorm_smem(n);
