@@ -16,6 +16,7 @@
 // and the FP64 pipe.
 #include "common.cuh"
 #include <stdlib.h>
+#include <stdio.h>
 
 #define BAL_THREADS 256
 #define BAL_RQ 6                        // ceil(AXS_MAX_SMALL_N2 / 32) row slots per lane
@@ -179,6 +180,33 @@ __device__ __forceinline__ void oc_pair(int n, int lane, bool two, cplx* col0, c
     y0 = cadd(ya[0], ya[1]); y1 = cadd(yb[0], yb[1]);
 }
 
+// software-pipelined form of oc_pair for padded on-chip columns: the loads of the next pair are
+// issued before the arithmetic of the current one
+template <int R>
+__device__ __forceinline__ void oc_load(int lane, const cplx* col0, const cplx* col1, cplx (&e0)[R], cplx (&e1)[R]) {
+#pragma unroll
+    for (int q = 0; q < R; ++q) { e0[q] = col0[lane + 32 * q]; e1[q] = col1[lane + 32 * q]; }
+}
+template <int R>
+__device__ __forceinline__ void oc_apply(int lane, cplx* col0, cplx* col1, const cplx (&e0)[R], const cplx (&e1)[R],
+                                         const cplx (&wi)[R], const cplx (&vi)[R], const cplx (&vn)[R],
+                                         cplx t0, cplx t1, cplx z0, cplx z1, cplx n0, cplx n1,
+                                         cplx (&wacc)[R], cplx& y0, cplx& y1)
+{
+    cplx ya[2] = {mk(0, 0), mk(0, 0)}, yb[2] = {mk(0, 0), mk(0, 0)};
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+        const int i = lane + 32 * q;
+        const cplx a0 = cfms(vi[q], z0, cfms(wi[q], t0, e0[q]));
+        const cplx a1 = cfms(vi[q], z1, cfms(wi[q], t1, e1[q]));
+        col0[i] = a0; col1[i] = a1;
+        wacc[q] = cfma(a0, n0, cfma(a1, n1, wacc[q]));
+        ya[q & 1] = cfmac(a0, vn[q], ya[q & 1]);
+        yb[q & 1] = cfmac(a1, vn[q], yb[q & 1]);
+    }
+    y0 = cadd(ya[0], ya[1]); y1 = cadd(yb[0], yb[1]);
+}
+
 // two independent complex sums reduced together (6 shuffle rounds instead of 10):
 // on return lane 0 holds sum(a), lane 16 holds sum(b), both in `a`
 __device__ __forceinline__ void warp_csum2(cplx& a, cplx b, int lane) {
@@ -196,7 +224,7 @@ __device__ __forceinline__ void warp_csum2(cplx& a, cplx b, int lane) {
 
 // PAD: on-chip columns use the leading dimension 32 R (no row guards on chip); otherwise n.
 // Per reflector: pass -> barrier -> column step part 1 -> barrier -> part 2 -> barrier.
-template <int NWARP, int R, bool PAD>
+template <int NWARP, int R, bool PAD, bool PIPE>
 __global__ void __launch_bounds__(NWARP * 32, 1)
 k_reduce_oc(int n, int jg, AxsWork wk)
 {
@@ -237,6 +265,12 @@ k_reduce_oc(int n, int jg, AxsWork wk)
 
     cplx tau = mk(0, 0);
     const int nrw = (n + 31) >> 5;                   // warps that own rows in the column steps
+#ifdef OC_TIMING
+    long long tc[4] = {0, 0, 0, 0}, t0c = clock64();
+#define OC_MARK(i) { const long long t1c = clock64(); tc[i] += t1c - t0c; t0c = t1c; }
+#else
+#define OC_MARK(i)
+#endif
     for (int k = -1; k <= n - 3; ++k) {
         const bool has_next = (k + 1 < n - 2);
         const int c = k + 1;
@@ -268,6 +302,7 @@ k_reduce_oc(int n, int jg, AxsWork wk)
             }
         }
         __syncthreads();                                         // #1
+        OC_MARK(0)
         // ---- part 2: reflector k+1 from the updated column -----------------------------------
         cplx tau2 = mk(0, 0);
         if (has_next) {
@@ -300,6 +335,7 @@ k_reduce_oc(int n, int jg, AxsWork wk)
             A[(long long)c * n + tid] = a_i;
         }
         __syncthreads();                                         // #2
+        OC_MARK(1)
         if (has_next) tau2 = s_alpha[1];
         // ---- fused pass over the trailing columns j >= k+2 -----------------------------------
         const int j0 = k + 2;
@@ -337,6 +373,39 @@ k_reduce_oc(int n, int jg, AxsWork wk)
             const int nsp = (n - gend + 1) >> 1;                 // pairs in the on-chip range
             int wrot = warp - (ngp % NWARP);                     // warps without a global pair go first
             if (wrot < 0) wrot += NWARP;
+            if (PAD && PIPE) {
+                cplx e0[R], e1[R], f0[R], f1[R];
+                int p = wrot;
+                if (p < nsp) {
+                    const int j = gend + 2 * p;
+                    cplx* c0p = As + (j - jg) * ld;
+                    oc_load<R>(lane, c0p, (j + 1 < n) ? c0p + ld : dummy, e0, e1);
+                }
+                while (p < nsp) {
+                    const int j = gend + 2 * p;
+                    const bool two = (j + 1 < n);
+                    const int j1 = two ? j + 1 : j;
+                    const int pn = p + NWARP;
+                    if (pn < nsp) {                              // next pair's loads go out first
+                        const int jn = gend + 2 * pn;
+                        cplx* c0n = As + (jn - jg) * ld;
+                        oc_load<R>(lane, c0n, (jn + 1 < n) ? c0n + ld : dummy, f0, f1);
+                    }
+                    const cplx t0 = tj[j], z0 = zj[j], n0 = v2[j];
+                    cplx t1 = tj[j1], z1 = zj[j1], n1 = v2[j1];
+                    cplx* col0 = As + (j - jg) * ld;
+                    cplx* col1 = col0 + ld;
+                    if (!two) { t1 = z1 = n1 = mk(0, 0); col1 = dummy; }
+                    cplx y0, y1;
+                    oc_apply<R>(lane, col0, col1, e0, e1, wi, vi, vn, t0, t1, z0, z1, n0, n1, wacc, y0, y1);
+                    warp_csum2(y0, y1, lane);
+                    if (lane == 0) { y[j] = y0; alp = cfma(y0, n0, alp); }
+                    if (lane == 16 && two) { y[j + 1] = y0; alp = cfma(y0, n1, alp); }
+#pragma unroll
+                    for (int q = 0; q < R; ++q) { e0[q] = f0[q]; e1[q] = f1[q]; }
+                    p = pn;
+                }
+            } else
             for (int p = wrot; p < nsp; p += NWARP) {
                 const int j = gend + 2 * p;
                 const bool two = (j + 1 < n);
@@ -353,6 +422,7 @@ k_reduce_oc(int n, int jg, AxsWork wk)
                 if (lane == 16 && two) { y[j + 1] = y0; alp = cfma(y0, n1, alp); }
             }
         }
+        OC_MARK(2)
 #pragma unroll
         for (int q = 0; q < R; ++q) wpart[warp * LV + lane + 32 * q] = wacc[q];
         {
@@ -360,9 +430,14 @@ k_reduce_oc(int n, int jg, AxsWork wk)
             if (lane == 0) { red2[2 * warp] = alp.x + ox; red2[2 * warp + 1] = alp.y + oy; }
         }
         __syncthreads();                                         // #3
+        OC_MARK(3)
         { cplx* tp = v; v = v2; v2 = tp; }
         tau = tau2;
     }
+#ifdef OC_TIMING
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == NWARP - 1))
+        printf("oc timing warp %d: part1 %lld part2 %lld pass %lld wait3 %lld cycles\n", warp, tc[0], tc[1], tc[2], tc[3]);
+#endif
     // the last column never passes through the column step
     if (n - 1 >= jg) for (int i = tid; i < n; i += NT) A[(long long)(n - 1) * n + i] = As[(n - 1 - jg) * ld + i];
     __syncthreads();
@@ -385,7 +460,7 @@ static size_t reduce_oc_fixed() {
     return (size_t)(8 + NWARP) * 32 * R * sizeof(cplx) + (size_t)(3 * NWARP) * sizeof(double) + 2 * sizeof(cplx);
 }
 
-template <int NWARP, int R, bool PAD>
+template <int NWARP, int R, bool PAD, bool PIPE>
 static int launch_oc(int n, int nf, AxsWork wk, cudaStream_t st)
 {
     const size_t cap = 227 * 1024;
@@ -395,8 +470,8 @@ static int launch_oc(int n, int nf, AxsWork wk, cudaStream_t st)
     if (ncs > n - 1) ncs = n - 1;                    // column 0 never needs to be on chip
     const int jg = n - ncs;
     const size_t smem = fixed + (size_t)ncs * colb;
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_reduce_oc<NWARP, R, PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_reduce_oc<NWARP, R, PAD><<<nf, NWARP * 32, smem, st>>>(n, jg, wk);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_reduce_oc<NWARP, R, PAD, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_reduce_oc<NWARP, R, PAD, PIPE><<<nf, NWARP * 32, smem, st>>>(n, jg, wk);
     return (int)cudaGetLastError();
 }
 
@@ -415,8 +490,9 @@ extern "C" int axs_launch_reduce_oc(int N, int hb, const cplx* K0s, const cplx* 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (n <= 128) {
-        if (nw == 8) return launch_oc<8, 4, true>(n, nf, wk, st);
-        return launch_oc<12, 4, true>(n, nf, wk, st);
+        if (nw == 8) return launch_oc<8, 4, true, false>(n, nf, wk, st);
+        if (nw == 9) return launch_oc<8, 4, true, true>(n, nf, wk, st);     // 8 warps, software-pipelined pass
+        return launch_oc<12, 4, true, false>(n, nf, wk, st);
     }
-    return launch_oc<8, 6, false>(n, nf, wk, st);
+    return launch_oc<8, 6, false, false>(n, nf, wk, st);
 }

@@ -20,6 +20,7 @@
 //              store in the reference psi_hat layout.
 #include "common.cuh"
 #include <stdlib.h>
+#include <stdio.h>
 
 // =========================================================================================
 // k_reduce
@@ -479,7 +480,13 @@ static size_t hqr_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(c
 // shared-memory footprint each; a stage stops once the window is <= m_stop, parks the leading
 // block and its size in global memory, and the next stage resumes with more CTAs per SM
 // (the kernel is latency bound, so co-resident matrices translate into throughput).
-template <int NT, int MINB, int NITEMS>
+// OPT (stage 1, one CTA per SM, where phase R is bound by shared-memory bandwidth and the leader
+// chain by contention on its sub-partition):
+//   * the lower output of a row rotation is the upper input of the same (bulge, column) item one
+//     macro step later: it is carried in a register instead of a store + load whenever no column
+//     rotation of the intervening phase C touches it (columns k+3d, k+3d+1 of the bulges ahead);
+//   * the warps that share the leader warp's SM sub-partition take no phase-C items.
+template <int NT, int MINB, int NITEMS, bool OPT = false, bool CARRY = false>
 __global__ void __launch_bounds__(NT, MINB)
 k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ Hc_all, cplx* __restrict__ Hp_all,
          cplx* __restrict__ eig_all, int* __restrict__ info, int* __restrict__ ucur)
@@ -502,7 +509,14 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
     __syncthreads();
 
     int its = 0, failed = 0;
+#ifdef OC_TIMING
+    long long tq[5] = {0, 0, 0, 0, 0}, tq0 = clock64(); int nmacro = 0, nbatch = 0;
+#define HQ_MARK(i) { const long long t1c = clock64(); tq[i] += t1c - tq0; tq0 = t1c; }
+#else
+#define HQ_MARK(i)
+#endif
     while (u >= m_stop) {
+        HQ_MARK(4)
         // ---- deflation scan ----------------------------------------------------------------
         if (tid == 0) s_l = 0;
         __syncthreads();
@@ -575,21 +589,34 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
         // per-thread work items are fixed for the whole batch: (bulge, column) for the row
         // rotations, (bulge, row) for the column rotations; only k = k0 + t moves.
         int r_k0[NITEMS], r_col[NITEMS], r_off[NITEMS], c_k0[NITEMS], c_row[NITEMS];
+        cplx r_carry[NITEMS];
+        bool r_has[NITEMS];
+        // phase-C workers: all worker warps, or (OPT) only those on other sub-partitions than the leader's
+        const int wq = tid >> 5;
+        const int NCW = OPT ? (NT / 32 - NT / 128) * 32 : (NT - 32);
+        const int cidx = OPT ? (((wq & 3) == 3) ? (1 << 30) : (((wq >> 2) * 3 + (wq & 3)) * 32 + (tid & 31)))
+                             : ((tid < (NT - 32)) ? tid : (1 << 30));
 #pragma unroll
         for (int q = 0; q < NITEMS; ++q) {
             const int item = (tid < (NT - 32)) ? tid + q * (NT - 32) : (1 << 30);   // last warp: leaders only
             r_k0[q] = c_k0[q] = 1 << 28;                 // "never active"
             r_col[q] = 0; r_off[q] = 0; c_row[q] = 0;
+            r_has[q] = false; r_carry[q] = mk(0, 0);
             if (item < nb * CW) {
                 const int b = item / CW, col = l - 1 + (item - b * CW);
                 if (col >= l) { r_k0[q] = l - b * MB_D; r_col[q] = col; r_off[q] = hcol_off(col); }
                 // column l-1 never receives a rotation (k-1 >= l whenever the slot is used)
             }
-            if (item < nb * m) {
-                const int b = item / m;
-                c_k0[q] = l - b * MB_D; c_row[q] = l + (item - b * m);
+            const int citem = (cidx < (1 << 29)) ? cidx + q * NCW : (1 << 30);
+            if (citem < nb * m) {
+                const int b = citem / m;
+                c_k0[q] = l - b * MB_D; c_row[q] = l + (citem - b * m);
             }
         }
+        HQ_MARK(0)
+#ifdef OC_TIMING
+        nmacro += nsteps; ++nbatch;
+#endif
         for (int t = 0; t < nsteps; ++t) {
             const int cur = t & 1, nxt = cur ^ 1;
                 // ---- phase R: row rotations ---------------------------------------------------------
@@ -600,15 +627,31 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
                     const int b = (l - r_k0[q]) / MB_D;
                     cplx* pk = H + r_off[q] + k;
                     if (col == k - 1) { *pk = mk(s_rr[cur][b], 0.0); }
-                    else {
+                    else if (!CARRY) {
                         const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
                         const cplx p = pk[0], qv = pk[1];
                         pk[0] = cfma(ga, p, cmul(gb, qv));
                         pk[1] = csub(cmulc(qv, ga), cmulc(p, gb));
+                    } else {
+                        const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
+                        const cplx p = r_has[q] ? r_carry[q] : pk[0];
+                        const cplx qv = pk[1];
+                        pk[0] = cfma(ga, p, cmul(gb, qv));
+                        const cplx bot = csub(cmulc(qv, ga), cmulc(p, gb));
+                        // row k+1 of this column stays in a register if the item runs again next step
+                        // and no column rotation of this step's phase C touches it: the bulges ahead
+                        // (d = 1..b) rotate the columns k+3d, k+3d+1, this bulge the columns k, k+1
+                        const int dl = col - k;
+                        const int d3 = dl / 3;
+                        const bool keep = (k + 1 <= u - 1) && (dl >= 2) && ((dl - 3 * d3 == 2) || (d3 > b));
+                        if (keep) r_carry[q] = bot; else pk[1] = bot;
+                        r_has[q] = keep;
                     }
                 }
             }
+            HQ_MARK(1)
             __syncthreads();
+            HQ_MARK(2)
             // ---- phase C: column rotations, next rotation ---------------------------------------
             // The last warp owns the critical chain of every bulge (rows k+1, k+2 -> next rotation)
             // so that it overlaps with the bulk updates done by the other warps.
@@ -652,9 +695,16 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
                     *p1 = csub(cmul(c1, ga), cmul(c0, gb));                 // -c0 b + c1 a
                 }
             }
+            HQ_MARK(3)
             __syncthreads();
+            HQ_MARK(2)
         }
     }
+#ifdef OC_TIMING
+    if (f == 0 && first_stage && (tid == 0 || tid == NT - 32 || tid == 256))
+        printf("hqr stage1 tid %d: setup %lld phaseR %lld barrier %lld phaseC %lld other %lld cycles, %d macro steps, %d batches\n",
+               tid, tq[0], tq[1], tq[2], tq[3], tq[4], nmacro, nbatch);
+#endif
     if (tid == 0) { info[f] = first_stage ? failed : info[f] + failed; ucur[f] = u; }
     if (u >= 0)                                           // park the remaining leading block
         for (int i = tid; i < hcol_size(u + 1); i += NT) Hpark[i] = H[i];
@@ -1352,6 +1402,15 @@ extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, c
             AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<1024, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_hqr_mb<1024, 1, 2><<<nf, 1024, smem, st>>>(n, b1, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
         }
+    } else if (getenv("AXS_HQR_S1_OPT") && atoi(getenv("AXS_HQR_S1_OPT")) == 2) {
+        // A/B: register carry in phase R + leader sub-partition kept free in phase C
+        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 1, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hqr_mb<512, 1, 3, true, true><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
+    } else if (!(getenv("AXS_HQR_S1_OPT") && atoi(getenv("AXS_HQR_S1_OPT")) == 0)) {
+        // default: leader sub-partition kept free in phase C (36.5 -> 35.8 ms / 2000 points);
+        // AXS_HQR_S1_OPT=0 restores the plain mapping, =2 adds the phase-R register carry (39.3 ms)
+        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 1, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hqr_mb<512, 1, 3, true, false><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
     } else if (lean && atoi(lean)) {
         AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_hqr_mb<512, 2, 3><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);

@@ -132,8 +132,13 @@ def gpu_arm(args):
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
+    saved_stdout = None
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        # NCCL prints its version banner on stdout: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import axisafe_b200 as ax
     from axisafe_b200 import cases, _native as nat
@@ -166,7 +171,7 @@ def gpu_arm(args):
     per_kernel = {name: 0.0 for name in ev}
 
     def device_step(timed):
-        """Whole hot path with inputs resident in HBM: 9 kernel launches."""
+        """Whole hot path with inputs resident in HBM on one stream: 12 kernel launches."""
         P = nat._ptr
         ev['reduce'][0].record()
         nat.check(L.axs_reduce(N, ops.hb, P(ops.K0s), P(ops.Cb), P(ops.Mb), P(ops.K1c), P(ops.K6d), P(omega),
@@ -194,7 +199,7 @@ def gpu_arm(args):
         torch.cuda.synchronize()
 
     def product_step():
-        """The product path: frequency chunks on two streams (what solve() runs), 9 launches per chunk."""
+        """The product path: two frequency chunks on two streams (what solve() runs), 9 launches per chunk + 3."""
         P = nat._ptr
         kk, pp, ii, _ = nat.eig_sweep(ops, omega, want_modes=True, work=work)
         nat.check(L.axs_track_pairs(N, ops.hb, P(ops.Cb), P(ops.K6d), P(pp), nloc - 1, P(arg), P(amax),
@@ -283,12 +288,15 @@ def gpu_arm(args):
                 'h2d_bytes_per_step': int(8 * nloc),
                 'd2h_bytes_per_step': int(nloc * n2 * 16 + (nloc - 1) * n2 * 12 + nloc * 4 + POINTS_PER_GPU * n2 * n2 * 16),
                 'k_only': {'value': nf_total / e2e_k_s, 'note': 'solve() without reading psi_hat back'}},
-        'gpu_launches': (2 * 7 + 3) * args.steps,   # per chunk: reduce, hqr x4, modes, backnorm; then bpsi, track_mma, apply_order
+        'gpu_launches': (2 * 9 + 3) * args.steps,   # per chunk: balance, reduce_oc, hqr x4, modes, wy_tfactor, backnorm_wy; then bpsi, track_mma, apply_order
         'clocks': clocks.summary(),
         'hbm_peak_gbs': peaks.get('hbm_gbs'),
     }
     out['cpu_baseline'] = cpu_baseline() if world == 1 and not args.no_cpu else None
-    print(json.dumps(out))
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+    print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -7,7 +7,7 @@ python bench.py > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err ||
 python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/bench_${TAG}_short.json 2>/dev/null || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_${TAG}_list.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:"k_hqr_mb|k_reduce|k_modes|k_backnorm|k_track_mma" -c 9 \
+ncu --set full --import-source on --clock-control none -k regex:"k_balance|k_reduce_oc|k_hqr_mb|k_modes|k_wy_tfactor|k_backnorm_wy|k_bpsi|k_track_mma" -c 11 \
     -o gpurun_out/prof_${TAG} python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_${TAG}_full.log 2>&1
 python tests/bench_big.py 6:10:296 > gpurun_out/bench_big_${TAG}.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_big_${TAG}.csv \
