@@ -275,9 +275,9 @@ def gpu_arm(args):
         'kernel_ms': {k_: v / args.steps for k_, v in per_kernel.items()},
         'roofline': {'bound': 'tensor', 'kernel': 'k_hqr_mb (4 stage launches)', 'achieved': achieved, 'peak': fp64_peak,
                      'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
-                     'traffic': int(nloc * 471.5e3),
+                     'traffic': int(nloc * 472.4e3),
                      'traffic_note': 'DRAM bytes (read + write) of the QR cascade per sweep, from ncu --set full '
-                                     '(profiles/r1b_ncu_summary.csv): 130.9 + 112.8 + 74.7 + 55.9 MB read and 97 MB '
+                                     '(profiles/r1c_ncu_summary.csv): 130.7 + 112.5 + 74.6 + 55.9 MB read and 98.7 MB '
                                      'written per 1000 matrices over its four stage launches; the algorithmic bytes '
                                      'are the packed Hessenberg matrix once (130 KB per matrix) - the rest is the '
                                      'leading block parked and re-read between stages',
