@@ -480,13 +480,60 @@ static size_t hqr_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(c
 // shared-memory footprint each; a stage stops once the window is <= m_stop, parks the leading
 // block and its size in global memory, and the next stage resumes with more CTAs per SM
 // (the kernel is latency bound, so co-resident matrices translate into throughput).
+// Rotation with a REAL cosine (zlartg form): G = [c s; -conj(s) c], G [x; y] = [r; 0] with
+// c = |x| / n, s = (x / |x|) conj(y) / n, r = (x / |x|) n, n = sqrt(|x|^2 + |y|^2).  Applying it
+// costs 12 instead of 18 FP64 instructions per element pair; generating it needs two rsqrt.
+__device__ __forceinline__ void make_rot_rc(cplx x, cplx y, cplx& c, cplx& s, cplx& r) {
+    const double nx = cabs2(x), ny = cabs2(y), n2 = nx + ny;
+    if (nx > 0.0) {
+        const double irx = rsqrt(nx), irn = rsqrt(n2);
+        const cplx ph = mk(x.x * irx, x.y * irx);
+        c = mk((nx * irx) * irn, 0.0);
+        s = cscale(cmulc(ph, y), irn);
+        r = cscale(ph, n2 * irn);
+    } else if (ny > 0.0) {
+        const double iry = rsqrt(ny);
+        c = mk(0, 0); s = mk(y.x * iry, -y.y * iry); r = mk(ny * iry, 0.0);
+    } else { c = mk(1, 0); s = mk(0, 0); r = mk(0, 0); }
+}
+// acc - a * conj(b)
+__device__ __forceinline__ cplx cfmsc(cplx a, cplx b, cplx acc) {
+    return mk(fma(-a.x, b.x, fma(-a.y, b.y, acc.x)), fma(-a.y, b.x, fma(a.x, b.y, acc.y)));
+}
+// row rotation [p; q] <- G [p; q] and column rotation [c0 c1] <- [c0 c1] G^H, both variants
+template <bool RC>
+__device__ __forceinline__ void rot_rows(cplx ga, cplx gb, cplx p, cplx q, cplx& top, cplx& bot) {
+    if (RC) {
+        top = cfma(gb, q, cscale(p, ga.x));
+        bot = cfmsc(p, gb, cscale(q, ga.x));
+    } else {
+        top = cfma(ga, p, cmul(gb, q));
+        bot = csub(cmulc(q, ga), cmulc(p, gb));
+    }
+}
+template <bool RC>
+__device__ __forceinline__ void rot_cols(cplx ga, cplx gb, cplx c0, cplx c1, cplx& n0, cplx& n1) {
+    if (RC) {
+        n0 = cfmac(c1, gb, cscale(c0, ga.x));            // c c0 + conj(s) c1
+        n1 = cfms(gb, c0, cscale(c1, ga.x));             // -s c0 + c c1
+    } else {
+        n0 = cfmac(c0, ga, cmulc(c1, gb));               // c0 conj(a) + c1 conj(b)
+        n1 = csub(cmul(c1, ga), cmul(c0, gb));           // -c0 b + c1 a
+    }
+}
+template <bool RC>
+__device__ __forceinline__ void gen_rot(cplx x, cplx y, cplx& a, cplx& b, cplx& r) {
+    if (RC) make_rot_rc(x, y, a, b, r);
+    else { double rr; make_rot(x, y, a, b, rr); r = mk(rr, 0.0); }
+}
+
 // OPT (stage 1, one CTA per SM, where phase R is bound by shared-memory bandwidth and the leader
 // chain by contention on its sub-partition):
 //   * the lower output of a row rotation is the upper input of the same (bulge, column) item one
 //     macro step later: it is carried in a register instead of a store + load whenever no column
 //     rotation of the intervening phase C touches it (columns k+3d, k+3d+1 of the bulges ahead);
 //   * the warps that share the leader warp's SM sub-partition take no phase-C items.
-template <int NT, int MINB, int NITEMS, bool OPT = false, bool CARRY = false>
+template <int NT, int MINB, int NITEMS, bool OPT = false, bool CARRY = false, bool RC = false>
 __global__ void __launch_bounds__(NT, MINB)
 k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ Hc_all, cplx* __restrict__ Hp_all,
          cplx* __restrict__ eig_all, int* __restrict__ info, int* __restrict__ ucur)
@@ -498,7 +545,7 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
     __shared__ int s_l;
     __shared__ cplx s_shift[MB_MAX];
     __shared__ cplx s_ra[2][MB_MAX], s_rb[2][MB_MAX];
-    __shared__ double s_rr[2][MB_MAX];
+    __shared__ cplx s_rr[2][MB_MAX];
 
     const cplx* Hg = (first_stage ? Hc_all : Hp_all) + (long long)f * hsz;
     cplx* Hpark = Hp_all + (long long)f * hsz;
@@ -579,8 +626,8 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
         }
         __syncthreads();
         if (tid == 0) {                                  // rotation that introduces bulge 0
-            cplx a, b; double r;
-            make_rot(csub(HC(H, l, l), s_shift[0]), HC(H, l + 1, l), a, b, r);
+            cplx a, b, r;
+            gen_rot<RC>(csub(HC(H, l, l), s_shift[0]), HC(H, l + 1, l), a, b, r);
             s_ra[0][0] = a; s_rb[0][0] = b; s_rr[0][0] = r;
         }
         __syncthreads();
@@ -626,18 +673,20 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
                 if (k >= l && k <= u - 1 && col >= k - 1 && k < (1 << 27)) {
                     const int b = (l - r_k0[q]) / MB_D;
                     cplx* pk = H + r_off[q] + k;
-                    if (col == k - 1) { *pk = mk(s_rr[cur][b], 0.0); }
+                    if (col == k - 1) { *pk = s_rr[cur][b]; }
                     else if (!CARRY) {
                         const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
                         const cplx p = pk[0], qv = pk[1];
-                        pk[0] = cfma(ga, p, cmul(gb, qv));
-                        pk[1] = csub(cmulc(qv, ga), cmulc(p, gb));
+                        cplx top, bot;
+                        rot_rows<RC>(ga, gb, p, qv, top, bot);
+                        pk[0] = top; pk[1] = bot;
                     } else {
                         const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
                         const cplx p = r_has[q] ? r_carry[q] : pk[0];
                         const cplx qv = pk[1];
-                        pk[0] = cfma(ga, p, cmul(gb, qv));
-                        const cplx bot = csub(cmulc(qv, ga), cmulc(p, gb));
+                        cplx top, bot;
+                        rot_rows<RC>(ga, gb, p, qv, top, bot);
+                        pk[0] = top;
                         // row k+1 of this column stays in a register if the item runs again next step
                         // and no column rotation of this step's phase C touches it: the bulges ahead
                         // (d = 1..b) rotate the columns k+3d, k+3d+1, this bulge the columns k, k+1
@@ -663,22 +712,23 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
                     cplx* p0 = H + hcol_off(k) + k + 1;
                     cplx* p1 = H + hcol_off(k + 1) + k + 1;
                     const cplx c0 = *p0, c1 = *p1;
-                    const cplx n0 = cfmac(c0, ga, cmulc(c1, gb));
+                    cplx n0, n1;
+                    rot_cols<RC>(ga, gb, c0, c1, n0, n1);
                     *p0 = n0;
-                    *p1 = csub(cmul(c1, ga), cmul(c0, gb));
+                    *p1 = n1;
                     if (k + 2 <= u) {
                         const cplx h = p1[1];                               // H(k+2, k+1)
-                        const cplx y = cmulc(h, gb);                        // new bulge H(k+2, k)
-                        p1[1] = cmul(h, ga);
-                        cplx a2, b2; double r2;
-                        make_rot(n0, y, a2, b2, r2);
+                        const cplx y = cmulc(h, gb);                        // new bulge H(k+2, k) = h conj(b)
+                        p1[1] = RC ? cscale(h, ga.x) : cmul(h, ga);
+                        cplx a2, b2, r2;
+                        gen_rot<RC>(n0, y, a2, b2, r2);
                         s_ra[nxt][b] = a2; s_rb[nxt][b] = b2; s_rr[nxt][b] = r2;
                     }
                 }
                 if (b == nb && (t + 1) % MB_D == 0 && (t + 1) / MB_D < nb) {   // bulge (t+1)/D starts next step
                     const int bn = (t + 1) / MB_D;
-                    cplx a2, b2; double r2;
-                    make_rot(csub(HC(H, l, l), s_shift[bn]), HC(H, l + 1, l), a2, b2, r2);
+                    cplx a2, b2, r2;
+                    gen_rot<RC>(csub(HC(H, l, l), s_shift[bn]), HC(H, l + 1, l), a2, b2, r2);
                     s_ra[nxt][bn] = a2; s_rb[nxt][bn] = b2; s_rr[nxt][bn] = r2;
                 }
             }
@@ -691,8 +741,9 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
                     cplx* p0 = H + hcol_off(k) + r;
                     cplx* p1 = H + hcol_off(k + 1) + r;
                     const cplx c0 = *p0, c1 = *p1;
-                    *p0 = cfmac(c0, ga, cmulc(c1, gb));                     // c0 conj(a) + c1 conj(b)
-                    *p1 = csub(cmul(c1, ga), cmul(c0, gb));                 // -c0 b + c1 a
+                    cplx n0, n1;
+                    rot_cols<RC>(ga, gb, c0, c1, n0, n1);
+                    *p0 = n0; *p1 = n1;
                 }
             }
             HQ_MARK(3)
@@ -1303,6 +1354,22 @@ extern "C" int axs_launch_reduce(int N, int hb, const cplx* K0s, const cplx* Cb,
     return (int)cudaGetLastError();
 }
 
+// launch one k_hqr_mb stage; AXS_HQR_RC=0 selects the complex-cosine rotation form (A/B)
+template <int NT, int MINB, int NITEMS, bool OPT>
+static int launch_mb(int nf, size_t smem, cudaStream_t st, int n, int bmax, int first, int m_stop,
+                     const cplx* Hc, cplx* Hp, cplx* eig, int* info, int* ucur)
+{
+    const char* rc = getenv("AXS_HQR_RC");            // default: real-cosine rotations (35.9 -> 34.5 ms / 2000 points)
+    if (!(rc && !atoi(rc))) {
+        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<NT, MINB, NITEMS, OPT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hqr_mb<NT, MINB, NITEMS, OPT, false, true><<<nf, NT, smem, st>>>(n, bmax, first, m_stop, Hc, Hp, eig, info, ucur);
+    } else {
+        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<NT, MINB, NITEMS, OPT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hqr_mb<NT, MINB, NITEMS, OPT, false, false><<<nf, NT, smem, st>>>(n, bmax, first, m_stop, Hc, Hp, eig, info, ucur);
+    }
+    return (int)cudaGetLastError();
+}
+
 // Largest active window whose packed storage fits `per_sm` times into the shared memory of an SM.
 extern "C" int axs_hqr_stage_capacity(int per_sm)
 {
@@ -1324,9 +1391,7 @@ extern "C" int axs_launch_hqr_stages(int n, int nf, int m_first, cplx* Hp, cplx*
     int m3 = (stages >= 3) ? axs_hqr_stage_capacity(3) : 0;
     if (m3 >= m_first || m3 < 8) m3 = 0;
     size_t smem2 = hqr_mb_smem(m_first);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    k_hqr_mb<512, 2, 3><<<nf, 512, smem2, st>>>(n, bulges, 0, m3, Hp, Hp, eig, info, ucur);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = (cudaError_t)launch_mb<512, 2, 3, false>(nf, smem2, st, n, bulges, 0, m3, Hp, Hp, eig, info, ucur);
     if (e != cudaSuccess || m3 == 0) return (int)e;
     // stages 4 and 5 (AXS_HQR_STAGES >= 4 / 5): 256 threads, 4 and 5 CTAs per SM
     int m4 = (stages >= 4) ? axs_hqr_stage_capacity(4) : 0;
@@ -1334,19 +1399,13 @@ extern "C" int axs_launch_hqr_stages(int n, int nf, int m_first, cplx* Hp, cplx*
     int m5 = (stages >= 5 && m4) ? axs_hqr_stage_capacity(5) : 0;
     if (m5 >= m4 || m5 < 8) m5 = 0;
     size_t smem3 = hqr_mb_smem(m3);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<384, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    k_hqr_mb<384, 3, 3><<<nf, 384, smem3, st>>>(n, bulges, 0, m4, Hp, Hp, eig, info, ucur);
-    e = cudaGetLastError();
+    e = (cudaError_t)launch_mb<384, 3, 3, false>(nf, smem3, st, n, bulges, 0, m4, Hp, Hp, eig, info, ucur);
     if (e != cudaSuccess || m4 == 0) return (int)e;
     size_t smem4 = hqr_mb_smem(m4);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<256, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
-    k_hqr_mb<256, 4, 3><<<nf, 256, smem4, st>>>(n, bulges, 0, m5, Hp, Hp, eig, info, ucur);
-    e = cudaGetLastError();
+    e = (cudaError_t)launch_mb<256, 4, 3, false>(nf, smem4, st, n, bulges, 0, m5, Hp, Hp, eig, info, ucur);
     if (e != cudaSuccess || m5 == 0) return (int)e;
     size_t smem5 = hqr_mb_smem(m5);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<256, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
-    k_hqr_mb<256, 5, 3><<<nf, 256, smem5, st>>>(n, bulges, 0, 0, Hp, Hp, eig, info, ucur);
-    return (int)cudaGetLastError();
+    return launch_mb<256, 5, 3, false>(nf, smem5, st, n, bulges, 0, 0, Hp, Hp, eig, info, ucur);
 }
 
 extern "C" int axs_launch_hqr_window(int n, int nf, int m_stop, cplx* H, cplx* eig, int* info, int* ucur,
@@ -1402,21 +1461,22 @@ extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, c
             AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<1024, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_hqr_mb<1024, 1, 2><<<nf, 1024, smem, st>>>(n, b1, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
         }
-    } else if (getenv("AXS_HQR_S1_OPT") && atoi(getenv("AXS_HQR_S1_OPT")) == 2) {
+    } else if (getenv("AXS_HQR_S1_OPT") && atoi(getenv("AXS_HQR_S1_OPT")) == 2 && bulges * n <= 3 * 384) {
         // A/B: register carry in phase R + leader sub-partition kept free in phase C
         AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 1, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_hqr_mb<512, 1, 3, true, true><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
-    } else if (!(getenv("AXS_HQR_S1_OPT") && atoi(getenv("AXS_HQR_S1_OPT")) == 0)) {
+    } else if (!(getenv("AXS_HQR_S1_OPT") && atoi(getenv("AXS_HQR_S1_OPT")) == 0) && bulges * n <= 3 * 384) {
+        // (the 12 phase-C warps x 3 item slots must hold bulges x n column-rotation items: 2N <= 144)
         // default: leader sub-partition kept free in phase C (36.5 -> 35.8 ms / 2000 points);
         // AXS_HQR_S1_OPT=0 restores the plain mapping, =2 adds the phase-R register carry (39.3 ms)
-        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 1, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hqr_mb<512, 1, 3, true, false><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
+        const int rc1 = launch_mb<512, 1, 3, true>(nf, smem, st, n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
+        if (rc1) return rc1;
     } else if (lean && atoi(lean)) {
         AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_hqr_mb<512, 2, 3><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
     } else {
-        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hqr_mb<512, 1, 3><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
+        const int rc1 = launch_mb<512, 1, 3, false>(nf, smem, st, n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
+        if (rc1) return rc1;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || m2 == 0) return (int)e;

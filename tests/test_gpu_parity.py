@@ -137,6 +137,27 @@ def test_reduction_is_a_similarity(name, n, kw):
 
 
 @pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
+def test_balancing_equals_lapack_zgebal(name, n, kw):
+    """The scaling factors of k_balance / k_reduce are LAPACK's own: scipy.linalg.matrix_balance
+    (zgebal, scaling only) on the reference's S returns the same powers of two, entry for entry
+    (all three instances: L2-resident, on-chip padded, on-chip guarded)."""
+    import torch
+    import scipy.linalg as sla
+    g, c, m, ops, N, pick, omega, nat = _stages(name, n, kw)
+    Sd = torch.from_numpy(np.ascontiguousarray(g['S'].transpose(0, 2, 1))).cuda().reshape(-1)
+    work = nat.reduce_dense(Sd, N, len(pick))
+    scale, H = nat.get_reduction(N, len(pick), work)
+    for j in range(len(pick)):
+        _, (ref, _) = sla.matrix_balance(g['S'][j], permute=False, separate=True)
+        assert np.array_equal(scale[j], ref), (j, int((scale[j] != ref).sum()))
+        # and the Hessenberg form has the singular values of the balanced matrix (unitary similarity)
+        Sb = g['S'][j] * ref[None, :] / ref[:, None]
+        sv_ref = np.linalg.svd(Sb, compute_uv=False)
+        sv = np.linalg.svd(H[j], compute_uv=False)
+        assert np.abs(sv - sv_ref).max() <= 1e-11 * sv_ref[0]
+
+
+@pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
 def test_eigenvalues_vs_reference_zgeev(name, n, kw):
     """Solver-level (bijective) parity: GPU eigenvalues of the reference's own S against
     the untracked scipy.linalg.eig values stored in the fixture; bar 1e-8 relative
