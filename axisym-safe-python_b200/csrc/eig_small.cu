@@ -486,11 +486,11 @@ static size_t hqr_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(c
 __device__ __forceinline__ void make_rot_rc(cplx x, cplx y, cplx& c, cplx& s, cplx& r) {
     const double nx = cabs2(x), ny = cabs2(y), n2 = nx + ny;
     if (nx > 0.0) {
-        const double irx = rsqrt(nx), irn = rsqrt(n2);
-        const cplx ph = mk(x.x * irx, x.y * irx);
-        c = mk((nx * irx) * irn, 0.0);
-        s = cscale(cmulc(ph, y), irn);
-        r = cscale(ph, n2 * irn);
+        const cplx xy = cmulc(x, y);                 // off the rsqrt chain
+        const double w = rsqrt(nx) * rsqrt(n2);      // 1 / (|x| n)
+        c = mk(nx * w, 0.0);
+        s = cscale(xy, w);
+        r = cscale(x, n2 * w);
     } else if (ny > 0.0) {
         const double iry = rsqrt(ny);
         c = mk(0, 0); s = mk(y.x * iry, -y.y * iry); r = mk(ny * iry, 0.0);
@@ -712,12 +712,12 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
                     cplx* p0 = H + hcol_off(k) + k + 1;
                     cplx* p1 = H + hcol_off(k + 1) + k + 1;
                     const cplx c0 = *p0, c1 = *p1;
+                    const cplx h = (k + 2 <= u) ? p1[1] : mk(0, 0);         // H(k+2, k+1), before the stores
                     cplx n0, n1;
                     rot_cols<RC>(ga, gb, c0, c1, n0, n1);
                     *p0 = n0;
                     *p1 = n1;
                     if (k + 2 <= u) {
-                        const cplx h = p1[1];                               // H(k+2, k+1)
                         const cplx y = cmulc(h, gb);                        // new bulge H(k+2, k) = h conj(b)
                         p1[1] = RC ? cscale(h, ga.x) : cmul(h, ga);
                         cplx a2, b2, r2;
