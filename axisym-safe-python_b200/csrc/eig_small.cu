@@ -1009,9 +1009,9 @@ k_modes(int N, int hb, const cplx* __restrict__ Cb, const cplx* __restrict__ K6d
     // >= k+4, which are final (previous row iteration): they run as one tight loop for all four
     // groups at once.  The last three steps + the new column operation of row k need row k+1, i.e.
     // the previous group's result of this very iteration: the four tails run in group order.
-    auto step = [&](const cplx* row, int k, int j, cplx& carry, cplx& acc) {
+    auto step = [&](const cplx* row, int k, int j, cplx& carry, cplx& acc, bool diag) {
         cplx a = row[j];
-        if (j == k) a = csub(a, lam);
+        if (diag && j == k) a = csub(a, lam);
         const bool sw = swp[j * M + mcol] != 0;
         cplx a2 = sw ? carry : a;
         const cplx c2 = sw ? a : carry;
@@ -1033,12 +1033,12 @@ k_modes(int N, int hb, const cplx* __restrict__ Cb, const cplx* __restrict__ K6d
             carry = row[n - 1];
             if (k == n - 1) carry = csub(carry, lam);
 #pragma unroll 4
-            for (int j = n - 2; j >= k + 3; --j) step(row, k, j, carry, acc);
+            for (int j = n - 2; j >= k + 3; --j) step(row, k, j, carry, acc, false);   // j > k: no diagonal shift
         }
         for (int gg = 0; gg < MD_G; ++gg) {
             if (active && g == gg) {
                 const int jtop = (k + 2 < n - 2) ? k + 2 : n - 2;
-                for (int j = jtop; j >= k; --j) step(row, k, j, carry, acc);
+                for (int j = jtop; j >= k; --j) step(row, k, j, carry, acc, true);
                 cplx rkk, a2 = mk(0, 0);
                 bool sw = false;
                 if (k > 0) {
