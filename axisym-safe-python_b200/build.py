@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ['api.cu', 'assemble.cu', 'eig_small.cu', 'eig_reduce.cu', 'eig_backx.cu', 'eig_big.cu', 'track.cu']
+SOURCES = ['api.cu', 'assemble.cu', 'eig_small.cu', 'eig_reduce.cu', 'eig_backx.cu', 'eig_hqrwin.cu', 'eig_big.cu', 'track.cu']
 HEADERS = ['common.cuh', os.path.join('..', '..', 'include', 'axisafe_b200.h')]
 OUT = os.path.join(HERE, 'axisafe_b200', '_lib', 'libaxisafe_b200.so')
 FLAGS = (['-DOC_TIMING'] if os.environ.get('AXS_OC_TIMING') else []) + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

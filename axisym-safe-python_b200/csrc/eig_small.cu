@@ -480,53 +480,6 @@ static size_t hqr_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(c
 // shared-memory footprint each; a stage stops once the window is <= m_stop, parks the leading
 // block and its size in global memory, and the next stage resumes with more CTAs per SM
 // (the kernel is latency bound, so co-resident matrices translate into throughput).
-// Rotation with a REAL cosine (zlartg form): G = [c s; -conj(s) c], G [x; y] = [r; 0] with
-// c = |x| / n, s = (x / |x|) conj(y) / n, r = (x / |x|) n, n = sqrt(|x|^2 + |y|^2).  Applying it
-// costs 12 instead of 18 FP64 instructions per element pair; generating it needs two rsqrt.
-__device__ __forceinline__ void make_rot_rc(cplx x, cplx y, cplx& c, cplx& s, cplx& r) {
-    const double nx = cabs2(x), ny = cabs2(y), n2 = nx + ny;
-    if (nx > 0.0) {
-        const cplx xy = cmulc(x, y);                 // off the rsqrt chain
-        const double w = rsqrt(nx) * rsqrt(n2);      // 1 / (|x| n)
-        c = mk(nx * w, 0.0);
-        s = cscale(xy, w);
-        r = cscale(x, n2 * w);
-    } else if (ny > 0.0) {
-        const double iry = rsqrt(ny);
-        c = mk(0, 0); s = mk(y.x * iry, -y.y * iry); r = mk(ny * iry, 0.0);
-    } else { c = mk(1, 0); s = mk(0, 0); r = mk(0, 0); }
-}
-// acc - a * conj(b)
-__device__ __forceinline__ cplx cfmsc(cplx a, cplx b, cplx acc) {
-    return mk(fma(-a.x, b.x, fma(-a.y, b.y, acc.x)), fma(-a.y, b.x, fma(a.x, b.y, acc.y)));
-}
-// row rotation [p; q] <- G [p; q] and column rotation [c0 c1] <- [c0 c1] G^H, both variants
-template <bool RC>
-__device__ __forceinline__ void rot_rows(cplx ga, cplx gb, cplx p, cplx q, cplx& top, cplx& bot) {
-    if (RC) {
-        top = cfma(gb, q, cscale(p, ga.x));
-        bot = cfmsc(p, gb, cscale(q, ga.x));
-    } else {
-        top = cfma(ga, p, cmul(gb, q));
-        bot = csub(cmulc(q, ga), cmulc(p, gb));
-    }
-}
-template <bool RC>
-__device__ __forceinline__ void rot_cols(cplx ga, cplx gb, cplx c0, cplx c1, cplx& n0, cplx& n1) {
-    if (RC) {
-        n0 = cfmac(c1, gb, cscale(c0, ga.x));            // c c0 + conj(s) c1
-        n1 = cfms(gb, c0, cscale(c1, ga.x));             // -s c0 + c c1
-    } else {
-        n0 = cfmac(c0, ga, cmulc(c1, gb));               // c0 conj(a) + c1 conj(b)
-        n1 = csub(cmul(c1, ga), cmul(c0, gb));           // -c0 b + c1 a
-    }
-}
-template <bool RC>
-__device__ __forceinline__ void gen_rot(cplx x, cplx y, cplx& a, cplx& b, cplx& r) {
-    if (RC) make_rot_rc(x, y, a, b, r);
-    else { double rr; make_rot(x, y, a, b, rr); r = mk(rr, 0.0); }
-}
-
 // OPT (stage 1, one CTA per SM, where phase R is bound by shared-memory bandwidth and the leader
 // chain by contention on its sub-partition):
 //   * the lower output of a row rotation is the upper input of the same (bulge, column) item one
@@ -1411,6 +1364,9 @@ extern "C" int axs_launch_hqr_stages(int n, int nf, int m_first, cplx* Hp, cplx*
 extern "C" int axs_launch_hqr_window(int n, int nf, int m_stop, cplx* H, cplx* eig, int* info, int* ucur,
                                      cudaStream_t st);
 
+extern "C" int axs_launch_hqr_win(int n, int nf, int bulges, int m_stop, const cplx* Hc, cplx* Hp, cplx* eig,
+                                  int* info, int* ucur, cudaStream_t st);
+
 extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, cudaStream_t st)
 {
     const char* mode = getenv("AXS_HQR_BULGES");
@@ -1449,6 +1405,12 @@ extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, c
         return axs_launch_hqr_stages(n, nf, m2, wk.Hp, eig, info, wk.ucur, st);
     }
     size_t smem = hqr_mb_smem(n);
+    const char* win = getenv("AXS_HQR_WIN");               // warp-specialised windowed stage 1 (eig_hqrwin.cu)
+    if (win && atoi(win) && m2) {
+        const int rcw = axs_launch_hqr_win(n, nf, bulges, m2, wk.Hc, wk.Hp, eig, info, wk.ucur, st);
+        if (rcw > 0) return rcw;
+        if (rcw == 0) return axs_launch_hqr_stages(n, nf, m2, wk.Hp, eig, info, wk.ucur, st);
+    }
     const char* lean = getenv("AXS_HQR_S1_LEAN");          // A/B: stage 1 capped at 64 registers (room for a co-resident CTA)
     const char* wide = getenv("AXS_HQR_S1_WIDE");          // A/B: stage 1 with 1024 threads; value = bulges in flight
     if (wide && atoi(wide)) {
