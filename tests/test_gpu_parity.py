@@ -180,6 +180,36 @@ def test_eigenvalues_vs_reference_zgeev(name, n, kw):
         assert plain == 0                     # flagship: plain 1e-8 bar, no allowance needed
 
 
+VARIANTS = [('AXS_REDUCE_OC', '0'), ('AXS_REDUCE_OC', '8'), ('AXS_REDUCE_OC', '9'), ('AXS_BACKNORM_WY', '0'),
+            ('AXS_BACKNORM_WY_MODES', '32'), ('AXS_HQR_RC', '0'), ('AXS_HQR_S1_OPT', '0'), ('AXS_HQR_S1_OPT', '2'),
+            ('AXS_HQR_WIN', '1'), ('AXS_HQR_STAGES', '2'), ('AXS_HQR_BULGES', '5')]
+
+
+@pytest.mark.parametrize('var,val', VARIANTS, ids=['%s=%s' % v for v in VARIANTS])
+def test_kernel_variants_keep_parity(var, val, monkeypatch):
+    """Every A/B variant kept behind an environment switch meets the same bar
+    as the default kernels on the flagship case: eigenvalues vs zgeev, mode shapes vs the default."""
+    g, c, m, ops, N, pick, omega, nat = _stages('pipe_soil_pml', 0, {})
+    n2 = 2 * N
+    k0, psi0, info0, _ = nat.eig_sweep(ops, omega)
+    k0 = k0.cpu().numpy().reshape(len(pick), n2)
+    psi0 = psi0.cpu().numpy().reshape(len(pick), n2, n2)
+    monkeypatch.setenv(var, val)
+    k1, psi1, info1, _ = nat.eig_sweep(ops, omega)
+    assert not info1.cpu().numpy().any()
+    k1 = k1.cpu().numpy().reshape(len(pick), n2)
+    psi1 = psi1.cpu().numpy().reshape(len(pick), n2, n2)
+    for j in range(len(pick)):
+        ref = g['eig_untracked'][j]
+        perm, _ = so.match_eigenvalues(ref, k1[j])
+        assert np.all(np.abs(ref - k1[j][perm]) <= 1e-8 * np.abs(ref))
+        # columns of the variant against the default (same eigenvalue, sign free)
+        p01, _ = so.match_eigenvalues(k0[j], k1[j])
+        a, b = psi0[j][N:], psi1[j][N:, p01]
+        err = np.minimum(np.linalg.norm(a - b, axis=0), np.linalg.norm(a + b, axis=0)) / np.linalg.norm(a, axis=0)
+        assert err.max() <= 1e-6, (j, err.max())
+
+
 @pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
 def test_modes_vs_reference(name, n, kw):
     """Mode shapes (lower half, B-normalised, sign fixed) within 1e-6 of the reference psi_hat."""
