@@ -1331,34 +1331,51 @@ extern "C" int axs_hqr_stage_capacity(int per_sm)
     return m;
 }
 
-// Stages 2 and 3 of the QR cascade: resume from the leading blocks parked in Hp (active window
-// <= m_first, top index in ucur) with 2, then 3 CTAs per SM.  Also the tail of the large path.
-extern "C" int axs_launch_hqr_stages(int n, int nf, int m_first, cplx* Hp, cplx* eig, int* info, int* ucur,
-                                     cudaStream_t st)
+// The cascade below stage 1: starts with the instance whose occupancy fits the current window
+// (512 threads x 2 CTAs/SM above 95, 384 x 3 above 82, 256 x 4 above 73, 256 x 5, and 128 x 8 for
+// windows <= 35) and hands the shrinking window down.  Hc_first != nullptr: the matrices are the
+// un-parked packed Hessenberg matrices of size n (small problems that skip stage 1); otherwise the
+// leading blocks parked in Hp (window <= m_cur, top index in ucur).  Also the tail of the large path.
+static int hqr_cascade(int n, int nf, int m_cur, const cplx* Hc_first, cplx* Hp, cplx* eig, int* info, int* ucur,
+                       cudaStream_t st)
 {
     const char* st_env = getenv("AXS_HQR_STAGES");
     const int stages = st_env ? atoi(st_env) : 4;      // 4 stages measured fastest on B200 (36.3 vs 37.7 ms)
     const char* mode = getenv("AXS_HQR_BULGES");
     int bulges = mode ? atoi(mode) : MB_MAX;
     if (bulges < 1 || bulges > MB_MAX) bulges = MB_MAX;
-    int m3 = (stages >= 3) ? axs_hqr_stage_capacity(3) : 0;
-    if (m3 >= m_first || m3 < 8) m3 = 0;
-    size_t smem2 = hqr_mb_smem(m_first);
-    cudaError_t e = (cudaError_t)launch_mb<512, 2, 3, false>(nf, smem2, st, n, bulges, 0, m3, Hp, Hp, eig, info, ucur);
-    if (e != cudaSuccess || m3 == 0) return (int)e;
-    // stages 4 and 5 (AXS_HQR_STAGES >= 4 / 5): 256 threads, 4 and 5 CTAs per SM
-    int m4 = (stages >= 4) ? axs_hqr_stage_capacity(4) : 0;
-    if (m4 >= m3 || m4 < 8) m4 = 0;
-    int m5 = (stages >= 5 && m4) ? axs_hqr_stage_capacity(5) : 0;
-    if (m5 >= m4 || m5 < 8) m5 = 0;
-    size_t smem3 = hqr_mb_smem(m3);
-    e = (cudaError_t)launch_mb<384, 3, 3, false>(nf, smem3, st, n, bulges, 0, m4, Hp, Hp, eig, info, ucur);
-    if (e != cudaSuccess || m4 == 0) return (int)e;
-    size_t smem4 = hqr_mb_smem(m4);
-    e = (cudaError_t)launch_mb<256, 4, 3, false>(nf, smem4, st, n, bulges, 0, m5, Hp, Hp, eig, info, ucur);
-    if (e != cudaSuccess || m5 == 0) return (int)e;
-    size_t smem5 = hqr_mb_smem(m5);
-    return launch_mb<256, 5, 3, false>(nf, smem5, st, n, bulges, 0, 0, Hp, Hp, eig, info, ucur);
+    const int m3 = (stages >= 3) ? axs_hqr_stage_capacity(3) : 0;
+    const int m4 = (stages >= 4) ? axs_hqr_stage_capacity(4) : 0;
+    const int m5 = (stages >= 5 || Hc_first) ? axs_hqr_stage_capacity(5) : 0;
+    int first = Hc_first ? 1 : 0;
+    const cplx* src = Hc_first ? Hc_first : Hp;
+    if (m_cur <= 35 && bulges * (m_cur + 1) <= 3 * (128 - 32) && stages >= 4)
+        return launch_mb<128, 8, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, 0, src, Hp, eig, info, ucur);
+    if (m3 == 0 || m_cur > m3) {
+        const int stop = (m3 >= 8 && m3 < m_cur) ? m3 : 0;
+        const int rc = launch_mb<512, 2, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, stop, src, Hp, eig, info, ucur);
+        if (rc || !stop) return rc;
+        first = 0; src = Hp; m_cur = stop;
+    }
+    if (m4 == 0 || m_cur > m4) {
+        const int stop = (m4 >= 8 && m4 < m_cur) ? m4 : 0;
+        const int rc = launch_mb<384, 3, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, stop, src, Hp, eig, info, ucur);
+        if (rc || !stop) return rc;
+        first = 0; src = Hp; m_cur = stop;
+    }
+    if (!(m5 >= 8 && m_cur <= m5)) {
+        const int stop = (m5 >= 8 && m5 < m_cur) ? m5 : 0;
+        const int rc = launch_mb<256, 4, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, stop, src, Hp, eig, info, ucur);
+        if (rc || !stop) return rc;
+        first = 0; src = Hp; m_cur = stop;
+    }
+    return launch_mb<256, 5, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, 0, src, Hp, eig, info, ucur);
+}
+
+extern "C" int axs_launch_hqr_stages(int n, int nf, int m_first, cplx* Hp, cplx* eig, int* info, int* ucur,
+                                     cudaStream_t st)
+{
+    return hqr_cascade(n, nf, m_first, nullptr, Hp, eig, info, ucur, st);
 }
 
 extern "C" int axs_launch_hqr_window(int n, int nf, int m_stop, cplx* H, cplx* eig, int* info, int* ucur,
@@ -1405,6 +1422,10 @@ extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, c
         return axs_launch_hqr_stages(n, nf, m2, wk.Hp, eig, info, wk.ucur, st);
     }
     size_t smem = hqr_mb_smem(n);
+    // problems that fit into the shared memory of an SM at least twice (2N <= 117) skip stage 1 and
+    // enter the cascade at the instance that fits (AXS_HQR_SMALL_DIRECT=0: one 512-thread CTA per SM)
+    if (m2 == 0 && !(getenv("AXS_HQR_SMALL_DIRECT") && !atoi(getenv("AXS_HQR_SMALL_DIRECT"))))
+        return hqr_cascade(n, nf, n, wk.Hc, wk.Hp, eig, info, wk.ucur, st);
     const char* win = getenv("AXS_HQR_WIN");               // warp-specialised windowed stage 1 (eig_hqrwin.cu)
     if (win && atoi(win) && m2) {
         const int rcw = axs_launch_hqr_win(n, nf, bulges, m2, wk.Hc, wk.Hp, eig, info, wk.ucur, st);
