@@ -475,6 +475,17 @@ static int launch_oc(int n, int nf, AxsWork wk, cudaStream_t st)
     return (int)cudaGetLastError();
 }
 
+extern "C" int axs_launch_balance(int N, int hb, const cplx* K0s, const cplx* Cb, const cplx* Mb,
+                                  const cplx* K1c, const cplx* K6d, const double* omega, int nf,
+                                  const cplx* S_in, AxsWork wk, cudaStream_t st)
+{
+    const int n = 2 * N;
+    size_t smem = balance_smem(n);
+    AXS_CUDA_OK(cudaFuncSetAttribute(k_balance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_balance<<<nf, BAL_THREADS, smem, st>>>(N, hb, K0s, Cb, Mb, K1c, K6d, omega, S_in, wk);
+    return (int)cudaGetLastError();
+}
+
 // returns -1 if this instance does not apply (caller falls back to k_reduce)
 extern "C" int axs_launch_reduce_oc(int N, int hb, const cplx* K0s, const cplx* Cb, const cplx* Mb,
                                     const cplx* K1c, const cplx* K6d, const double* omega, int nf,

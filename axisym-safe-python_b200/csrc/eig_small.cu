@@ -32,7 +32,7 @@
 __global__ void __launch_bounds__(RED_THREADS, 2)
 k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ Cb,
          const cplx* __restrict__ Mb, const cplx* __restrict__ K1c, const cplx* __restrict__ K6d,
-         const double* __restrict__ omega, const cplx* __restrict__ S_in, AxsWork wk)
+         const double* __restrict__ omega, const cplx* __restrict__ S_in, AxsWork wk, int prebal)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = 2 * N;
@@ -51,6 +51,8 @@ k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ C
     float* di2 = d2 + n;                             // [n] 1/d^2
     float* Wn = di2 + n;                             // [n*n] |a_ij|^2 (fp32 is enough to pick powers of 2)
 
+    // prebal: k_balance (eig_reduce.cu) has already left the balanced matrix in A and D in wk.scale
+    if (!prebal) {
     // ---- phase A: build S(w) (or copy the given dense matrix) --------------------------
     const double w = omega ? omega[f] : 0.0;
     const cplx* Sf = S_in ? S_in + (long long)f * n * n : nullptr;
@@ -103,6 +105,7 @@ k_reduce(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ C
         A[idx] = mk(a.x * sc, a.y * sc);
     }
     for (int i = tid; i < n; i += RED_THREADS) wk.scale[(long long)f * n + i] = d[i];
+    }
     __syncthreads();
 
     // ---- phase C: Householder reduction to Hessenberg form ------------------------------
@@ -1293,6 +1296,10 @@ extern "C" int axs_launch_reduce_oc(int N, int hb, const cplx* K0s, const cplx* 
                                     const cplx* K1c, const cplx* K6d, const double* omega, int nf,
                                     const cplx* S_in, AxsWork wk, cudaStream_t st);
 
+extern "C" int axs_launch_balance(int N, int hb, const cplx* K0s, const cplx* Cb, const cplx* Mb,
+                                  const cplx* K1c, const cplx* K6d, const double* omega, int nf,
+                                  const cplx* S_in, AxsWork wk, cudaStream_t st);
+
 extern "C" int axs_launch_reduce(int N, int hb, const cplx* K0s, const cplx* Cb, const cplx* Mb,
                                  const cplx* K1c, const cplx* K6d, const double* omega, int nf,
                                  const cplx* S_in, AxsWork wk, cudaStream_t st)
@@ -1301,9 +1308,17 @@ extern "C" int axs_launch_reduce(int N, int hb, const cplx* K0s, const cplx* Cb,
     // 2N >= 96: trailing block on chip (eig_reduce.cu); smaller matrices stay L2-resident, 2 CTAs per SM
     const int rc = axs_launch_reduce_oc(N, hb, K0s, Cb, Mb, K1c, K6d, omega, nf, S_in, wk, st);
     if (rc != -1) return rc;
+    // small matrices: the short-chain balancing kernel first (AXS_REDUCE_PREBAL=0: the fused one-warp loop)
+    int prebal = 0;
+    const char* pb = getenv("AXS_REDUCE_PREBAL");
+    if (!(pb && !atoi(pb))) {
+        const int rb = axs_launch_balance(N, hb, K0s, Cb, Mb, K1c, K6d, omega, nf, S_in, wk, st);
+        if (rb) return rb;
+        prebal = 1;
+    }
     size_t smem = reduce_smem(n);
     AXS_CUDA_OK(cudaFuncSetAttribute(k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_reduce<<<nf, RED_THREADS, smem, st>>>(N, hb, K0s, Cb, Mb, K1c, K6d, omega, S_in, wk);
+    k_reduce<<<nf, RED_THREADS, smem, st>>>(N, hb, K0s, Cb, Mb, K1c, K6d, omega, S_in, wk, prebal);
     return (int)cudaGetLastError();
 }
 
