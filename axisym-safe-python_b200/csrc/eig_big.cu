@@ -377,7 +377,7 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
     __shared__ cplx s_rec[HB_S][HB_NB][2];
     __shared__ cplx s_shift[HB_NB];
     __shared__ cplx s_ra[2][HB_NB], s_rb[2][HB_NB];
-    __shared__ double s_rr[2][HB_NB];
+    __shared__ cplx s_rr[2][HB_NB];
     __shared__ int s_l;
     const int f = blockIdx.x, tid = threadIdx.x;
     cplx* Hg = H_all + (long long)f * hcol_size(n);
@@ -448,8 +448,8 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
         }
         __syncthreads();
         if (tid == 0) {                                  // rotation that introduces bulge 0
-            cplx a, b; double r;
-            make_rot(csub(GH(l, l), s_shift[0]), GH(l + 1, l), a, b, r);
+            cplx a, b, r;
+            make_rot_rc(csub(GH(l, l), s_shift[0]), GH(l + 1, l), a, b, r);
             s_ra[0][0] = a; s_rb[0][0] = b; s_rr[0][0] = r;
         }
         __syncthreads();
@@ -486,12 +486,14 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
                     const int b = it_b[q], col = it_x[q];
                     const int k = l + t - b * HB_D;
                     if (b >= 0 && k >= l && k <= u - 1 && col >= k - 1) {
-                        if (col == k - 1) WH(k, col) = mk(s_rr[cur][b], 0.0);
+                        if (col == k - 1) WH(k, col) = s_rr[cur][b];
                         else {
                             const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
                             const cplx p = WH(k, col), qv = WH(k + 1, col);
-                            WH(k, col) = cfma(ga, p, cmul(gb, qv));
-                            WH(k + 1, col) = csub(cmulc(qv, ga), cmulc(p, gb));
+                            cplx top, bot;
+                            rot_rows<true>(ga, gb, p, qv, top, bot);
+                            WH(k, col) = top;
+                            WH(k + 1, col) = bot;
                         }
                     }
                 }
@@ -504,22 +506,23 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
                         const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
                         s_rec[t - t0][b][0] = ga; s_rec[t - t0][b][1] = gb;
                         const cplx c0 = WH(k + 1, k), c1 = WH(k + 1, k + 1);
-                        const cplx n0 = cfmac(c0, ga, cmulc(c1, gb));
+                        cplx n0, n1;
+                        rot_cols<true>(ga, gb, c0, c1, n0, n1);
                         WH(k + 1, k) = n0;
-                        WH(k + 1, k + 1) = csub(cmul(c1, ga), cmul(c0, gb));
+                        WH(k + 1, k + 1) = n1;
                         if (k + 2 <= u) {
                             const cplx h = WH(k + 2, k + 1);
                             const cplx y = cmulc(h, gb);                    // new bulge H(k+2, k)
-                            WH(k + 2, k + 1) = cmul(h, ga);
-                            cplx a2, b2; double r2;
-                            make_rot(n0, y, a2, b2, r2);
+                            WH(k + 2, k + 1) = cscale(h, ga.x);
+                            cplx a2, b2, r2;
+                            make_rot_rc(n0, y, a2, b2, r2);
                             s_ra[nxt][b] = a2; s_rb[nxt][b] = b2; s_rr[nxt][b] = r2;
                         }
                     }
                     if (b == nb && (t + 1) % HB_D == 0 && (t + 1) / HB_D < nb) {   // next bulge starts
                         const int bn = (t + 1) / HB_D;
-                        cplx a2, b2; double r2;
-                        make_rot(csub(WH(l, l), s_shift[bn]), WH(l + 1, l), a2, b2, r2);
+                        cplx a2, b2, r2;
+                        make_rot_rc(csub(WH(l, l), s_shift[bn]), WH(l + 1, l), a2, b2, r2);
                         s_ra[nxt][bn] = a2; s_rb[nxt][bn] = b2; s_rr[nxt][bn] = r2;
                     }
                 }
@@ -530,8 +533,10 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
                     if (b >= 0 && k >= l && k <= u - 1 && r <= k) {
                         const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
                         const cplx c0 = WH(r, k), c1 = WH(r, k + 1);
-                        WH(r, k) = cfmac(c0, ga, cmulc(c1, gb));
-                        WH(r, k + 1) = csub(cmul(c1, ga), cmul(c0, gb));
+                        cplx n0, n1;
+                        rot_cols<true>(ga, gb, c0, c1, n0, n1);
+                        WH(r, k) = n0;
+                        WH(r, k + 1) = n1;
                     }
                 }
                 __syncthreads();
@@ -560,8 +565,10 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
                         for (int tt = ta; tt <= tb; ++tt) {
                             const cplx ga = s_rec[tt][b][0], gb = s_rec[tt][b][1];
                             const cplx low = p[HB_TLD];
-                            *p = cfma(ga, carry, cmul(gb, low));
-                            carry = csub(cmulc(low, ga), cmulc(carry, gb));
+                            cplx top, bot;
+                            rot_rows<true>(ga, gb, carry, low, top, bot);
+                            *p = top;
+                            carry = bot;
                             p += HB_TLD;
                         }
                         *p = carry;
@@ -592,8 +599,10 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
                         for (int tt = ta; tt <= tb; ++tt) {
                             const cplx ga = s_rec[tt][b][0], gb = s_rec[tt][b][1];
                             const cplx right = p[HB_TLD];
-                            *p = cfmac(carry, ga, cmulc(right, gb));
-                            carry = csub(cmul(right, ga), cmul(carry, gb));
+                            cplx n0, n1;
+                            rot_cols<true>(ga, gb, carry, right, n0, n1);
+                            *p = n0;
+                            carry = n1;
                             p += HB_TLD;
                         }
                         *p = carry;

@@ -1467,7 +1467,10 @@ extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, c
         // (the 12 phase-C warps x 3 item slots must hold bulges x n column-rotation items: 2N <= 144)
         // default: leader sub-partition kept free in phase C (36.5 -> 35.8 ms / 2000 points);
         // AXS_HQR_S1_OPT=0 restores the plain mapping, =2 adds the phase-R register carry (39.3 ms)
-        const int rc1 = launch_mb<512, 1, 3, true>(nf, smem, st, n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
+        const char* nt1 = getenv("AXS_HQR_S1_THREADS");
+        const int rc1 = (nt1 && atoi(nt1) == 640)
+            ? launch_mb<640, 1, 3, true>(nf, smem, st, n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur)
+            : launch_mb<512, 1, 3, true>(nf, smem, st, n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
         if (rc1) return rc1;
     } else if (lean && atoi(lean)) {
         AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
