@@ -381,7 +381,15 @@ def _solve_pipelined(sol, torch, _native, ops, nf, n2, host_work=None):
     elif K == 4:
         # chunks run pairwise on two streams; the last pair is smaller so that the un-overlapped
         # tail (scan + gather + download of the final chunk) is short
-        bounds = [0, int(nf * 0.4), int(nf * 0.8), int(nf * 0.9), nf]    # measured best of six splits
+        # (44 / 44 / 7 / 5 % rounded to whole waves of one CTA per SM: 888 / 888 / 148 / 76 points at
+        # nf = 2000 on 148 SMs; within noise of 40 / 40 / 10 / 10 %: 61.5-62.7 ms end to end)
+        unit = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        b1 = max(unit, int(round(0.444 * nf / unit)) * unit)
+        b3 = 2 * b1 + max(unit, int(round(0.074 * nf / unit)) * unit)
+        if nf >= 8 * unit and b3 < nf:
+            bounds = [0, b1, 2 * b1, b3, nf]
+        else:
+            bounds = [0, int(nf * 0.4), int(nf * 0.8), int(nf * 0.9), nf]
     else:
         bounds = [nf * c // K for c in range(K + 1)]
     nn = n2 * n2
@@ -465,17 +473,21 @@ def _solve_pipelined(sol, torch, _native, ops, nf, n2, host_work=None):
             psi_h[lo:hi].copy_(psi_sorted[lo * nn:hi * nn].view(hi - lo, n2, n2), non_blocking=True)
             ev_done[c].record(xs)
 
+    # AXS_PIPE_LAG=2: queue the kernels of chunk c+2 (same stream and workspace as chunk c, so in order
+    # behind it) before the host blocks on the small tables of chunk c
+    lag = max(1, int(os.environ.get('AXS_PIPE_LAG', 1)))      # 2 measured equal (62.0-62.7 ms either way)
     for c in range(K):
         compute(c)
         tl.append(('enq%d' % c, time.perf_counter()))
         if c == min(1, K - 1) and host_work is not None:
             host_work()                                  # sparse host by-products, hidden behind the kernels
             tl.append(('host', time.perf_counter()))
-        if c >= 1:
-            finish(c - 1)
-            tl.append(('fin%d' % (c - 1), time.perf_counter()))
-    finish(K - 1)
-    tl.append(('fin%d' % (K - 1), time.perf_counter()))
+        if c >= lag:
+            finish(c - lag)
+            tl.append(('fin%d' % (c - lag), time.perf_counter()))
+    for c in range(max(K - lag, 0), K):
+        finish(c)
+        tl.append(('fin%d' % c, time.perf_counter()))
     xs.synchronize()
     tl.append(('sync', time.perf_counter()))
     if trace:
