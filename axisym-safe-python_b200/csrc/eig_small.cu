@@ -489,7 +489,10 @@ static size_t hqr_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(c
 //     macro step later: it is carried in a register instead of a store + load whenever no column
 //     rotation of the intervening phase C touches it (columns k+3d, k+3d+1 of the bulges ahead);
 //   * the warps that share the leader warp's SM sub-partition take no phase-C items.
-template <int NT, int MINB, int NITEMS, bool OPT = false, bool CARRY = false, bool RC = false>
+// LDG: the leader lane of a bulge owns the whole 2 x 2 diagonal block (rows / columns k, k+1) plus
+// H(k+2, k+1): it applies the row AND the column rotation there and generates the next rotation
+// already during phase R, so the chain overlaps both bulk phases instead of only phase C.
+template <int NT, int MINB, int NITEMS, bool OPT = false, bool CARRY = false, bool RC = false, bool LDG = false>
 __global__ void __launch_bounds__(NT, MINB)
 k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ Hc_all, cplx* __restrict__ Hp_all,
          cplx* __restrict__ eig_all, int* __restrict__ info, int* __restrict__ ucur)
@@ -622,11 +625,41 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
 #endif
         for (int t = 0; t < nsteps; ++t) {
             const int cur = t & 1, nxt = cur ^ 1;
+            if (LDG && tid >= (NT - 32)) {
+                const int b = tid - ((NT - 32));
+                const int k = l + t - b * MB_D;
+                if (b < nb && k >= l && k <= u - 1) {
+                    const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
+                    cplx* p0 = H + hcol_off(k) + k;          // (k, k), (k+1, k)
+                    cplx* p1 = H + hcol_off(k + 1) + k;      // (k, k+1), (k+1, k+1), (k+2, k+1)
+                    const cplx a00 = p0[0], a10 = p0[1], a01 = p1[0], a11 = p1[1];
+                    const cplx h = (k + 2 <= u) ? p1[2] : mk(0, 0);
+                    cplx t00, t10, t01, t11, n00, n01, n10, n11;
+                    rot_rows<RC>(ga, gb, a00, a10, t00, t10);
+                    rot_rows<RC>(ga, gb, a01, a11, t01, t11);
+                    rot_cols<RC>(ga, gb, t10, t11, n10, n11);   // row k+1 first: it feeds the next rotation
+                    if (k + 2 <= u) {
+                        const cplx y = cmulc(h, gb);
+                        cplx a2, b2, r2;
+                        gen_rot<RC>(n10, y, a2, b2, r2);
+                        s_ra[nxt][b] = a2; s_rb[nxt][b] = b2; s_rr[nxt][b] = r2;
+                        p1[2] = RC ? cscale(h, ga.x) : cmul(h, ga);
+                    }
+                    rot_cols<RC>(ga, gb, t00, t01, n00, n01);
+                    p0[0] = n00; p0[1] = n10; p1[0] = n01; p1[1] = n11;
+                }
+                if (b == nb && (t + 1) % MB_D == 0 && (t + 1) / MB_D < nb) {   // bulge (t+1)/D starts next step
+                    const int bn = (t + 1) / MB_D;
+                    cplx a2, b2, r2;
+                    gen_rot<RC>(csub(HC(H, l, l), s_shift[bn]), HC(H, l + 1, l), a2, b2, r2);
+                    s_ra[nxt][bn] = a2; s_rb[nxt][bn] = b2; s_rr[nxt][bn] = r2;
+                }
+            }
                 // ---- phase R: row rotations ---------------------------------------------------------
 #pragma unroll
             for (int q = 0; q < NITEMS; ++q) {
                 const int k = r_k0[q] + t, col = r_col[q];
-                if (k >= l && k <= u - 1 && col >= k - 1 && k < (1 << 27)) {
+                if (k >= l && k <= u - 1 && col >= k - 1 && k < (1 << 27) && !(LDG && (col == k || col == k + 1))) {
                     const int b = (l - r_k0[q]) / MB_D;
                     cplx* pk = H + r_off[q] + k;
                     if (col == k - 1) { *pk = s_rr[cur][b]; }
@@ -660,7 +693,7 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
             // ---- phase C: column rotations, next rotation ---------------------------------------
             // The last warp owns the critical chain of every bulge (rows k+1, k+2 -> next rotation)
             // so that it overlaps with the bulk updates done by the other warps.
-            if (tid >= (NT - 32)) {
+            if (!LDG && tid >= (NT - 32)) {
                 const int b = tid - ((NT - 32));
                 const int k = l + t - b * MB_D;
                 if (b < nb && k >= l && k <= u - 1) {
@@ -691,7 +724,7 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
 #pragma unroll
             for (int q = 0; q < NITEMS; ++q) {
                 const int k = c_k0[q] + t, r = c_row[q];
-                if (k >= l && k <= u - 1 && r <= k) {
+                if (k >= l && k <= u - 1 && r <= k - (LDG ? 1 : 0)) {
                     const int b = (l - c_k0[q]) / MB_D;
                     const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
                     cplx* p0 = H + hcol_off(k) + r;
@@ -1328,7 +1361,11 @@ static int launch_mb(int nf, size_t smem, cudaStream_t st, int n, int bmax, int 
                      const cplx* Hc, cplx* Hp, cplx* eig, int* info, int* ucur)
 {
     const char* rc = getenv("AXS_HQR_RC");            // default: real-cosine rotations (35.9 -> 34.5 ms / 2000 points)
-    if (!(rc && !atoi(rc))) {
+    const char* ldg = getenv("AXS_HQR_LDG");
+    if (ldg && atoi(ldg)) {
+        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<NT, MINB, NITEMS, OPT, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_hqr_mb<NT, MINB, NITEMS, OPT, false, true, true><<<nf, NT, smem, st>>>(n, bmax, first, m_stop, Hc, Hp, eig, info, ucur);
+    } else if (!(rc && !atoi(rc))) {
         AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<NT, MINB, NITEMS, OPT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_hqr_mb<NT, MINB, NITEMS, OPT, false, true><<<nf, NT, smem, st>>>(n, bmax, first, m_stop, Hc, Hp, eig, info, ucur);
     } else {

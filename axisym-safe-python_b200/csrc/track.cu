@@ -36,6 +36,54 @@ k_bpsi(int N, int hb, const cplx* __restrict__ Cb, const cplx* __restrict__ K6d,
     }
 }
 
+// Tiled form of k_bpsi: CTA = one frequency x 64 modes.  The lower half of the mode block (63 x 64
+// at 2N = 126) is staged in shared memory once and reused by every row of the banded C, which is
+// streamed through shared memory in row chunks; thread = (mode, row group).
+#define BP_COLS 64
+__global__ void __launch_bounds__(256, 2)
+k_bpsi_tiled(int N, int hb, int crows, const cplx* __restrict__ Cb, const cplx* __restrict__ K6d,
+             const cplx* __restrict__ psi_all, cplx* __restrict__ Y_all)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = 2 * N, W = 2 * hb + 1;
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const int col = tid & (BP_COLS - 1), grp = tid >> 6;
+    const int mode = blockIdx.x * BP_COLS + col;
+    const bool live = mode < n;
+    cplx* U = (cplx*)smem_raw;                        // [N][BP_COLS] lower half of the block
+    cplx* Cs = U + (size_t)N * BP_COLS;               // [crows][W]
+    const cplx* psi = psi_all + (long long)f * n * n;
+    cplx* Y = Y_all + (long long)f * n * n;
+    for (int idx = tid; idx < N * BP_COLS; idx += 256) {
+        const int r = idx / BP_COLS, c = idx - r * BP_COLS;
+        const int m = blockIdx.x * BP_COLS + c;
+        U[idx] = (m < n) ? psi[(long long)(N + r) * n + m] : mk(0, 0);
+    }
+    for (int r0 = 0; r0 < N; r0 += crows) {
+        const int r1 = min(N, r0 + crows);
+        __syncthreads();                              // U staged / previous chunk consumed
+        for (int idx = tid; idx < (r1 - r0) * W; idx += 256) Cs[idx] = Cb[(long long)r0 * W + idx];
+        __syncthreads();
+        int r = r0 + ((grp - r0) & 3);
+        for (; r < r1; r += 4) {
+            const cplx k6 = K6d[r];
+            cplx acc0 = live ? cmul(k6, psi[(long long)r * n + mode]) : mk(0, 0), acc1 = mk(0, 0);
+            const int c0 = max(0, r - hb), c1 = min(N - 1, r + hb);
+            const cplx* crow = Cs + (r - r0) * W - r + hb;
+            int c = c0;
+            for (; c + 1 <= c1; c += 2) {
+                acc0 = cfma(crow[c], U[c * BP_COLS + col], acc0);
+                acc1 = cfma(crow[c + 1], U[(c + 1) * BP_COLS + col], acc1);
+            }
+            if (c <= c1) acc0 = cfma(crow[c], U[c * BP_COLS + col], acc0);
+            if (live) {
+                Y[(long long)(N + r) * n + mode] = cadd(acc0, acc1);
+                Y[(long long)r * n + mode] = cmul(k6, U[r * BP_COLS + col]);
+            }
+        }
+    }
+}
+
 // P[a][b] = sum_r psiP[r][a] * Y[r][b];  CTA = 32 rows a x all b (<= 192), 256 threads,
 // thread tile 4 (a) x TB (b) with b strided by 64 so shared reads stay conflict-free.
 #define TR_TA 32
@@ -339,9 +387,26 @@ extern "C" int axs_launch_track(int N, int hb, const cplx* Cb, const cplx* K6d, 
                                 int npairs, cplx* Y, int* arg, double* amax, cudaStream_t st)
 {
     const int n = 2 * N;
-    int bx = (n * n + 255) / 256; if (bx > 64) bx = 64;
-    k_bpsi<<<dim3(bx, npairs + 1), 256, 0, st>>>(N, hb, Cb, K6d, psi, Y);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    {
+        // tiled kernel when the lower half of a 64-mode block + a chunk of the band fit twice per SM
+        const int W = 2 * hb + 1;
+        const size_t ubytes = (size_t)N * BP_COLS * sizeof(cplx);
+        const size_t budget = (size_t)110 * 1024;
+        int crows = ubytes < budget ? (int)((budget - ubytes) / ((size_t)W * sizeof(cplx))) : 0;
+        if (crows > N) crows = N;
+        const char* tl = getenv("AXS_BPSI_TILED");
+        if (crows >= 8 && !(tl && !atoi(tl))) {
+            const size_t smemb = ubytes + (size_t)crows * W * sizeof(cplx);
+            e = cudaFuncSetAttribute(k_bpsi_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemb);
+            if (e != cudaSuccess) return (int)e;
+            k_bpsi_tiled<<<dim3((n + BP_COLS - 1) / BP_COLS, npairs + 1), 256, smemb, st>>>(N, hb, crows, Cb, K6d, psi, Y);
+        } else {
+            int bx = (n * n + 255) / 256; if (bx > 64) bx = 64;
+            k_bpsi<<<dim3(bx, npairs + 1), 256, 0, st>>>(N, hb, Cb, K6d, psi, Y);
+        }
+    }
+    e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     const char* env = getenv("AXS_TRACK_FMA");
     if (env && atoi(env) && n <= TR_BMAX) {                // scalar-FMA tiles (kept for A/B)
