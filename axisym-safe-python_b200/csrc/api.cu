@@ -258,8 +258,9 @@ extern "C" int axs_track_scan(const int* h_arg, const double* h_amax, int nf, in
         for (int r = 0; r < n2; ++r) {
             const int src = prev[r];
             cur[r] = a[src];
-            // np.round(x, 2) > 0.9   (numpy: rint(x * 100) / 100)
-            if (!(rint(m[src] * 100.0) / 100.0 > 0.9)) all_valid = false;
+            // np.round(x, 2) > 0.9   (numpy: rint(x * 100) / 100; q / 100.0 > 0.9 <=> q >= 91 for integral q,
+            // because 90 / 100.0 is the double 0.9 itself) - no division in the loop
+            if (!(rint(m[src] * 100.0) >= 91.0)) all_valid = false;
         }
         if (!all_valid) return i;      // caller applies the reference's set-based fix-up to row i
     }
