@@ -355,6 +355,22 @@ def track_pairs_into(ops, psi, npairs, arg, amax, scratch):
                                 _ptr(amax), _ptr(scratch), need, _stream(torch)), 'axs_track_pairs')
 
 
+def fixup_row(prev, a, m, n2):
+    """One tracking step with the reference's re-seating of weakly matched modes (solver.py:159-175):
+    ``prev`` = column order at the previous frequency, ``a``/``m`` = arg-max / max tables of the pair.
+    The very same Python set expression as the reference, so CPython's set iteration order is kept."""
+    new_order = a[prev].copy()
+    valid = np.round(m[prev], 2) > 0.9
+    valid_entries = np.delete(new_order, np.where(valid == False))   # noqa: E712 (as the reference)
+    unassigned = list(set(range(n2)) - set(valid_entries))
+    j = 0
+    for ii in range(n2):
+        if not valid[ii]:
+            new_order[ii] = unassigned[j]
+            j += 1
+    return new_order
+
+
 def track_scan_range(arg, amax, order, start, stop, n2):
     """Rows [start, stop) of the reference column order (see track_scan); ``order`` [nf, n2] int32 is
     updated in place and must already hold rows < start.  ``arg``/``amax`` are the full host tables."""
@@ -363,17 +379,7 @@ def track_scan_range(arg, amax, order, start, stop, n2):
         i = L.axs_track_scan(arg.ctypes.data, amax.ctypes.data, stop, n2, start, order.ctypes.data)
         if i >= stop:
             return
-        prev = order[i - 1]
-        new_order = arg[i - 1][prev].copy()
-        valid = np.round(amax[i - 1][prev], 2) > 0.9
-        valid_entries = np.delete(new_order, np.where(valid == False))   # noqa: E712 (as the reference)
-        unassigned = list(set(range(n2)) - set(valid_entries))
-        j = 0
-        for ii in range(n2):
-            if not valid[ii]:
-                new_order[ii] = unassigned[j]
-                j += 1
-        order[i] = new_order
+        order[i] = fixup_row(order[i - 1], arg[i - 1], amax[i - 1], n2)
         start = i + 1
 
 
@@ -388,24 +394,61 @@ def track_scan(arg, amax, nf, n2):
     arg = np.ascontiguousarray(arg, dtype=np.int32)
     amax = np.ascontiguousarray(amax, dtype=np.float64)
     order = np.zeros([nf, n2], dtype=np.int32)
+    track_scan_range(arg, amax, order, 0, nf, n2)
+    return order
+
+
+def track_scan_segments(arg, amax, n2):
+    """Relative tracking scan of one rank's frequency block (sharded sweep).
+
+    ``arg``/``amax`` [P, n2]: the block's pairs; row j of the result belongs to the frequency j
+    steps after the block's base frequency.  The scan o_j = a_j[o_{j-1}] is a composition of maps,
+    so a block can be scanned from the identity without knowing the absolute column order sigma at
+    its base: order_j = rel_j[sigma].  That holds up to the first frequency where a visited mode
+    falls below the 0.9 threshold - there the reference re-seats modes by their *position*
+    (fixup_row), which needs the absolute order - so the block is cut into segments at those rows
+    and every segment restarts from the identity.  Returns (rel [P+1, n2] int32, starts): segment s
+    covers rows starts[s] .. starts[s+1]-1 (starts[0] = 0; every later start is a fix-up row).
+    A row that is clean for the identity start is clean for every sigma (the visited set can only
+    shrink), so no fix-up is ever missed; a row flagged here but clean under sigma goes through
+    fixup_row with all modes valid, which is the plain composition again.
+    """
+    arg = np.ascontiguousarray(arg, dtype=np.int32).reshape(-1, n2)
+    amax = np.ascontiguousarray(amax, dtype=np.float64).reshape(-1, n2)
+    P = arg.shape[0]
+    rel = np.empty([P + 1, n2], dtype=np.int32)
+    ident = np.arange(n2, dtype=np.int32)
+    rel[0] = ident
+    starts = [0]
     L = lib()
     start = 0
     while True:
-        i = L.axs_track_scan(arg.ctypes.data, amax.ctypes.data, nf, n2, start, order.ctypes.data)
-        if i >= nf:
-            return order
-        prev = order[i - 1]
-        new_order = arg[i - 1][prev].copy()
-        valid = np.round(amax[i - 1][prev], 2) > 0.9
-        valid_entries = np.delete(new_order, np.where(valid == False))   # noqa: E712 (as the reference)
-        unassigned = list(set(range(n2)) - set(valid_entries))
-        j = 0
-        for ii in range(n2):
-            if not valid[ii]:
-                new_order[ii] = unassigned[j]
-                j += 1
-        order[i] = new_order
+        i = L.axs_track_scan(arg.ctypes.data, amax.ctypes.data, P + 1, n2, start, rel.ctypes.data)
+        if i >= P + 1:
+            return rel, starts
+        rel[i] = ident
+        starts.append(i)
         start = i + 1
+
+
+def chain_segments(payloads, n2):
+    """Absolute column order at the start of every segment of every rank.
+
+    ``payloads[r]`` = (comps [S_r, n2], d_arg [S_r - 1, n2], d_amax [S_r - 1, n2]) as produced from
+    track_scan_segments: the last relative row of each segment and the pair tables of the fix-up
+    row that ends it.  Returns ``sigma[r][s]`` (int32 [n2]); cost O(total segments * n2).
+    """
+    sigma = np.arange(n2, dtype=np.int32)
+    out = []
+    for comps, d_arg, d_amax in payloads:
+        mine = []
+        S = comps.shape[0]
+        for s in range(S):
+            mine.append(sigma)
+            prev = comps[s][sigma]                      # order at the last frequency of the segment
+            sigma = fixup_row(prev, d_arg[s], d_amax[s], n2) if s < S - 1 else prev
+        out.append(mine)
+    return out
 
 
 def apply_order(n2, nf, order, k, psi):

@@ -60,7 +60,7 @@ class WaveElementAxisym(object):
         self.propagating_indices = None
         self.info = None                 # per-frequency count of unconverged eigenvalues
         self.order = None                # tracked column order per frequency
-        self.k_native = None             # eigenvalues before tracking (native order)
+        self._k_native = None            # eigenvalues before tracking (native order)
         self.local_range = None          # (first, last+1) frequencies solved by this rank
         self.timings = {}
 
@@ -74,6 +74,18 @@ class WaveElementAxisym(object):
     @psi_hat.setter
     def psi_hat(self, value):
         self._psi = value
+
+    @property
+    def k_native(self):
+        """Untracked spectra [nf, 2N] in the solver's native column order (a sharded sweep keeps the
+        gathered table on the device until it is read)."""
+        if self._k_native is not None and not isinstance(self._k_native, np.ndarray):
+            self._k_native = self._k_native.cpu().numpy()
+        return self._k_native
+
+    @k_native.setter
+    def k_native(self, value):
+        self._k_native = value
 
     @property
     def psi_hat_device(self):
@@ -145,7 +157,8 @@ class WaveElementAxisym(object):
             self.evaluated = True
             self.k_ready = 0
             return
-        host_attributes()
+        if not small:
+            host_attributes()
         # host -> device: this rank's angular frequencies (with the halo point in front)
         omega = torch.from_numpy(self.w[lo - halo:hi].copy()).cuda()
         nloc = hi - lo + halo
@@ -162,23 +175,25 @@ class WaveElementAxisym(object):
         k_loc = k_nat.view(nloc, n2)[halo:]
         info_loc = info[halo:]
         if world > 1:
-            k_all, arg_all, amax_all, info_all = _gather_blocks(torch, bounds, rank, n2, k_loc,
-                                                                arg.view(-1, n2), amax.view(-1, n2), info_loc)
+            # sharded sweep: every rank scans and reorders its own block, O(nf / world) host work
+            if small:
+                host_attributes()                        # while the kernels above run
+            order_loc, order_dev = _track_sharded(self, torch, _native, bounds, rank, n2, k_loc,
+                                                  arg.view(-1, n2), amax.view(-1, n2), info_loc)
         else:
-            k_all, arg_all, amax_all, info_all = k_loc, arg.view(-1, n2), amax.view(-1, n2), info_loc
-        # device -> host: the small tables
-        k_host = k_all.cpu().numpy().reshape(nf, n2)
-        arg_h = arg_all.cpu().numpy().reshape(max(nf - 1, 0), n2)
-        amax_h = amax_all.cpu().numpy().reshape(max(nf - 1, 0), n2)
-        self.info = info_all.cpu().numpy()
-        if self.info.any():
-            bad = int(np.count_nonzero(self.info))
-            raise np.linalg.LinAlgError('eig algorithm (QR) did not converge at %d frequencies' % bad)
-        self.k_native = k_host           # untracked spectra, solver's native column order
-        self.order = _native.track_scan(arg_h, amax_h, nf, n2)
-        self.k = np.take_along_axis(k_host, self.order.astype(np.int64), axis=1)
+            if small:
+                host_attributes()                        # while the kernels above run
+            # device -> host: the small tables
+            k_host = k_nat.view(nloc, n2).cpu().numpy()
+            arg_h = arg.cpu().numpy().reshape(max(nf - 1, 0), n2)
+            amax_h = amax.cpu().numpy().reshape(max(nf - 1, 0), n2)
+            self.info = info_loc.cpu().numpy()
+            _raise_unconverged(self.info)
+            self.k_native = k_host       # untracked spectra, solver's native column order
+            self.order = _native.track_scan(arg_h, amax_h, nf, n2)
+            self.k = np.take_along_axis(k_host, self.order.astype(np.int64), axis=1)
+            order_loc = order_dev = self.order
         # reorder this rank's mode shapes on the device; they are copied out lazily
-        order_loc = np.ascontiguousarray(self.order[lo:hi])
         if psi_nat is None:
             # the mode shapes of the whole block do not fit in HBM (the reference's psi_hat would be
             # nf x 2N x 2N x 16 B of host memory): eigenvalues and tracking are complete, shapes are not kept
@@ -188,7 +203,7 @@ class WaveElementAxisym(object):
                                    (hi - lo, n2, n2), lo, nf)
         else:
             psi_loc = psi_nat.view(nloc, n2 * n2)[halo:].reshape(-1)
-            _, psi_sorted = _native.apply_order(n2, hi - lo, order_loc,
+            _, psi_sorted = _native.apply_order(n2, hi - lo, order_dev,
                                                 k_nat.view(nloc, n2)[halo:].reshape(-1), psi_loc)
             self._psi = _LazyModes(psi_sorted, (hi - lo, n2, n2), lo, nf)
         self.evaluated = True
@@ -409,12 +424,13 @@ def _solve_pipelined(sol, torch, _native, ops, nf, n2, host_work=None):
     arg = torch.empty((nf - 1) * n2, dtype=torch.int32, device=dev)
     amax = torch.empty((nf - 1) * n2, dtype=torch.float64, device=dev)
     order_d = torch.empty(nf * n2, dtype=torch.int32, device=dev)
-    k_dummy = torch.empty(cmax * n2, dtype=torch.complex128, device=dev)
+    k_sorted = torch.empty(nf * n2, dtype=torch.complex128, device=dev)
     works = [_native.EigWorkspace(ops.N, cmax) for _ in range(2)]
     ybuf = [torch.empty(int(_native.lib().axs_track_worksize(ops.N, cmax)), dtype=torch.uint8, device=dev)
             for _ in range(2)]
     pin = lambda *shape, dtype: torch.empty(*shape, dtype=dtype, pin_memory=True)
     k_h = pin(nf, n2, dtype=torch.complex128)
+    ks_h = pin(nf, n2, dtype=torch.complex128)
     arg_h = pin(max(nf - 1, 1), n2, dtype=torch.int32)
     amax_h = pin(max(nf - 1, 1), n2, dtype=torch.float64)
     info_h = pin(nf, dtype=torch.int32)
@@ -467,9 +483,10 @@ def _solve_pipelined(sol, torch, _native, ops, nf, n2, host_work=None):
             xs.wait_event(ev_track[c])
             order_d[lo * n2:hi * n2].copy_(order_h[lo:hi].view(-1), non_blocking=True)
             _native.check(_native.lib().axs_apply_order(
-                n2, hi - lo, _native._ptr(order_d[lo * n2:hi * n2]), _native._ptr(k_dummy),
-                _native._ptr(psi_nat[lo * nn:hi * nn]), _native._ptr(k_dummy[:(hi - lo) * n2]),
+                n2, hi - lo, _native._ptr(order_d[lo * n2:hi * n2]), _native._ptr(k_nat[lo * n2:hi * n2]),
+                _native._ptr(psi_nat[lo * nn:hi * nn]), _native._ptr(k_sorted[lo * n2:hi * n2]),
                 _native._ptr(psi_sorted[lo * nn:hi * nn]), _native._stream(torch)), 'axs_apply_order')
+            ks_h[lo:hi].copy_(k_sorted[lo * n2:hi * n2].view(hi - lo, n2), non_blocking=True)
             psi_h[lo:hi].copy_(psi_sorted[lo * nn:hi * nn].view(hi - lo, n2, n2), non_blocking=True)
             ev_done[c].record(xs)
 
@@ -503,7 +520,7 @@ def _solve_pipelined(sol, torch, _native, ops, nf, n2, host_work=None):
     sol.info = info_h.numpy().copy()
     sol.k_native = k_h.numpy()
     sol.order = order.copy()
-    sol.k = np.take_along_axis(sol.k_native, sol.order.astype(np.int64), axis=1)
+    sol.k = ks_h.numpy()                                 # tracked on the device by k_apply_order
     sol.local_range = (0, nf)
     modes = _LazyModes(psi_sorted, (nf, n2, n2), 0, nf)
     modes.host = psi_h.numpy()
@@ -575,37 +592,108 @@ def _reorder_in_place(torch, _native, n2, order_loc, psi_nat, halo):
     return psi
 
 
-def _gather_blocks(torch, bounds, rank, n2, k_loc, arg_loc, amax_loc, info_loc):
-    """All-gather the per-rank eigenvalue / tracking tables (NCCL); blocks are padded to equal size."""
+def _raise_unconverged(info):
+    if info.any():
+        bad = int(np.count_nonzero(info))
+        raise np.linalg.LinAlgError('eig algorithm (QR) did not converge at %d frequencies' % bad)
+
+
+_PINNED = {}
+
+
+def _pinned(torch, name, shape, dtype):
+    """Pinned host staging buffer, kept between sweeps of the same shape."""
+    key = (name, tuple(shape), dtype)
+    if key not in _PINNED:
+        for old in [k for k in _PINNED if k[0] == name]:
+            del _PINNED[old]
+        _PINNED[key] = torch.empty(*shape, dtype=dtype, pin_memory=torch.cuda.is_available())
+    return _PINNED[key]
+
+
+def _track_sharded(sol, torch, _native, bounds, rank, n2, k_loc, arg_loc, amax_loc, info_loc):
+    """Tracking tail of a sharded sweep: sets ``k, order, info, k_native`` on ``sol`` (full tables,
+    identical on every rank) and returns this rank's rows of the column order (host, device).
+
+    The reference's scan (solver.py:159-182) is sequential over the frequencies.  Here every rank
+    scans its own block relative to the block's base frequency (_native.track_scan_segments), the
+    ranks exchange one small object each - the composed map of every segment plus the pair tables
+    of the fix-up rows - every rank replays the chain over those (O(segments), not O(nf)), applies
+    its absolute start order to its own rows, reorders its own k / psi on the device, and the
+    tracked k and the order are all-gathered over NCCL.  Host work and PCIe traffic per rank are
+    O(nf / world) apart from the final [nf, 2N] tables the API exposes on every rank.
+    """
+    import torch.distributed as dist
+    world = len(bounds) - 1
+    nf = bounds[-1]
+    lo, hi = bounds[rank], bounds[rank + 1]
+    halo = 1 if lo > 0 else 0
+    P = arg_loc.shape[0]                                    # pairs of this block (halo pair included)
+    on_gpu = k_loc.is_cuda
+    if on_gpu:
+        arg_h = _pinned(torch, 'arg', (max(P, 1), n2), torch.int32)[:P]
+        amax_h = _pinned(torch, 'amax', (max(P, 1), n2), torch.float64)[:P]
+        info_h = _pinned(torch, 'info', (hi - lo,), torch.int32)
+        arg_h.copy_(arg_loc, non_blocking=True)
+        amax_h.copy_(amax_loc, non_blocking=True)
+        info_h.copy_(info_loc, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    else:
+        arg_h, amax_h, info_h = arg_loc, amax_loc, info_loc
+    arg_n, amax_n = arg_h.numpy(), amax_h.numpy()
+    rel, starts = _native.track_scan_segments(arg_n, amax_n, n2)
+    ends = starts[1:] + [P + 1]
+    comps = np.stack([rel[e - 1] for e in ends])
+    fix = np.asarray(starts[1:], dtype=np.int64) - 1        # pair index of every fix-up row
+    payload = (comps, arg_n[fix].copy(), amax_n[fix].copy(), info_h.numpy().copy())
+    gathered = [None] * world
+    dist.all_gather_object(gathered, payload)
+    sol.info = np.concatenate([g[3] for g in gathered])
+    _raise_unconverged(sol.info)
+    sigma = _native.chain_segments([g[:3] for g in gathered], n2)[rank]
+    order_rows = np.empty([P + 1, n2], dtype=np.int32)
+    for s, (a, e) in enumerate(zip(starts, ends)):
+        np.take(rel[a:e], sigma[s], axis=1, out=order_rows[a:e])
+    order_loc = np.ascontiguousarray(order_rows[halo:])     # frequencies lo .. hi-1
+    # tracked k of this block on the device, then the full tables over NCCL
+    dev = k_loc.device
+    order_dev = torch.from_numpy(order_loc).to(dev, non_blocking=True)
+    if on_gpu:
+        k_sorted, _ = _native.apply_order(n2, hi - lo, order_dev.reshape(-1), k_loc.reshape(-1), None)
+        k_sorted = k_sorted.view(hi - lo, n2)
+    else:
+        k_sorted = torch.gather(k_loc.reshape(hi - lo, n2), 1, order_dev.long())
+    k_all, order_all, k_nat_all = _gather_rows(torch, bounds, rank, n2, [k_sorted, order_dev, k_loc.reshape(hi - lo, n2)])
+    if on_gpu:
+        k_h = _pinned(torch, 'k', (nf, n2), torch.complex128)
+        o_h = _pinned(torch, 'order', (nf, n2), torch.int32)
+        k_h.copy_(k_all, non_blocking=True)
+        o_h.copy_(order_all, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        sol.k, sol.order = k_h.numpy().copy(), o_h.numpy().copy()
+    else:
+        sol.k, sol.order = k_all.numpy(), order_all.numpy()
+    sol.k_native = k_nat_all                                # stays on the device until it is read
+    return order_loc, order_dev.reshape(-1)
+
+
+def _gather_rows(torch, bounds, rank, n2, tensors):
+    """All-gather [rows_r, n2] blocks of the ranks (padded to equal size) into [nf, n2] tables."""
     import torch.distributed as dist
     world = len(bounds) - 1
     size = max(bounds[r + 1] - bounds[r] for r in range(world))
-    nf = bounds[-1]
-
-    dev = k_loc.device
-
-    def gather(t, rows, dtype):
-        pad = torch.zeros(size, n2, dtype=dtype, device=dev) if t.dim() == 2 else \
-            torch.zeros(size, dtype=dtype, device=dev)
-        pad[:rows] = t[:rows]
-        out = [torch.empty_like(pad) for _ in range(world)]
-        if dtype.is_complex:
-            dist.all_gather([torch.view_as_real(o) for o in out], torch.view_as_real(pad))
+    rows = bounds[rank + 1] - bounds[rank]
+    out = []
+    for t in tensors:
+        pad = torch.zeros(size, n2, dtype=t.dtype, device=t.device)
+        pad[:rows] = t
+        full = torch.empty(world * size, n2, dtype=t.dtype, device=t.device)
+        if t.dtype.is_complex:
+            dist.all_gather_into_tensor(torch.view_as_real(full), torch.view_as_real(pad))
         else:
-            dist.all_gather(out, pad)
-        return out
-
-    nk = bounds[rank + 1] - bounds[rank]
-    ks = gather(k_loc.reshape(nk, n2), nk, torch.complex128)
-    infos = gather(info_loc, nk, torch.int32)
-    # rank r > 0 owns pairs (lo-1, lo) .. (hi-2, hi-1) = nk pairs; rank 0 owns nk - 1 pairs
-    npairs = arg_loc.shape[0]
-    args = gather(arg_loc, npairs, torch.int32)
-    amaxs = gather(amax_loc, npairs, torch.float64)
-    k_all = torch.cat([ks[r][:bounds[r + 1] - bounds[r]] for r in range(world)])
-    info_all = torch.cat([infos[r][:bounds[r + 1] - bounds[r]] for r in range(world)])
-    counts = [(bounds[r + 1] - bounds[r]) - (1 if r == 0 else 0) for r in range(world)]
-    arg_all = torch.cat([args[r][:counts[r]] for r in range(world)])
-    amax_all = torch.cat([amaxs[r][:counts[r]] for r in range(world)])
-    assert arg_all.shape[0] == nf - 1
-    return k_all, arg_all, amax_all, info_all
+            dist.all_gather_into_tensor(full, pad)
+        if all(bounds[r + 1] - bounds[r] == size for r in range(world)):
+            out.append(full)
+        else:
+            out.append(torch.cat([full[r * size:r * size + bounds[r + 1] - bounds[r]] for r in range(world)]))
+    return out

@@ -271,7 +271,7 @@ def gpu_arm(args):
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'points_per_gpu': POINTS_PER_GPU, 'n2': n2,
                    'l2': 'working set 1.5 GB per sweep >> 126 MB L2 (no flush needed)',
-                   'parallelism': 'frequency axis sharded, %d rank(s), 1-point halo; 2 frequency chunks on 2 CUDA streams per rank (value); e2e = solve(): 4-chunk pipeline, psi_hat download overlapped with compute at N=1' % world},
+                   'parallelism': 'frequency axis sharded, %d rank(s), 1-point halo; 2 frequency chunks on 2 CUDA streams per rank (value); e2e = solve(): 4-chunk pipeline with psi_hat download overlapped at N=1; at N>1 per-rank segmented tracking scan + NCCL all-gather of k / order, psi_hat block read after solve()' % world},
         'kernel_ms': {k_: v / args.steps for k_, v in per_kernel.items()},
         'roofline': {'bound': 'tensor', 'kernel': 'k_hqr_mb (4 stage launches)', 'achieved': achieved, 'peak': fp64_peak,
                      'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,
@@ -285,8 +285,12 @@ def gpu_arm(args):
                              'point for the QR kernel (zhseqr share of F_alg = 100*n2^3); peak = ' + how,
                      'pipeline_frac': value / world * f_alg(n2) / 1e12 / fp64_peak},
         'e2e': {'value': nf_total / e2e_s, 'unit': UNIT,
-                'h2d_bytes_per_step': int(8 * nloc),
-                'd2h_bytes_per_step': int(nloc * n2 * 16 + (nloc - 1) * n2 * 12 + nloc * 4 + POINTS_PER_GPU * n2 * n2 * 16),
+                # per rank.  up: omega + the tracked column order of the rank's block; down: tracking tables
+                # (arg int32 + amax f64) + info + psi_hat block, and k: native + tracked table at N=1,
+                # the tracked [nf_total, 2N] table + the order table at N>1 (k_native stays on the device)
+                'h2d_bytes_per_step': int(8 * nloc + POINTS_PER_GPU * n2 * 4),
+                'd2h_bytes_per_step': int((nloc - 1) * n2 * 12 + POINTS_PER_GPU * 4 + POINTS_PER_GPU * n2 * n2 * 16
+                                          + (2 * nloc * n2 * 16 if world == 1 else nf_total * n2 * 20)),
                 'k_only': {'value': nf_total / e2e_k_s, 'note': 'solve() without reading psi_hat back'}},
         'gpu_launches': (2 * 9 + 3) * args.steps,   # per chunk: balance, reduce_oc, hqr x4, modes, wy_tfactor, backnorm_wy; then bpsi, track_mma, apply_order
         'clocks': clocks.summary(),

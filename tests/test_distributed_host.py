@@ -23,8 +23,15 @@ def _global_tables(nf, n2, seed=3):
     k = rng.standard_normal([nf, n2]) + 1j * rng.standard_normal([nf, n2])
     arg = np.array([rng.permutation(n2) for _ in range(nf - 1)], dtype=np.int32)
     amax = 0.93 + 0.07 * rng.random([nf - 1, n2])
-    amax[5, 3] = 0.4
-    amax[17, 1] = amax[17, 6] = 0.2
+    amax[5, 3] = 0.4                                   # one weak mode
+    amax[17, 1] = amax[17, 6] = 0.2                    # two weak modes: re-seated by position
+    amax[18, 2] = amax[18, 7] = amax[18, 9] = 0.1      # consecutive fix-up rows
+    amax[nf // 2 - 1, 4] = amax[nf // 2 - 1, 5] = 0.3  # fix-up on the pair at a block seam (world 2)
+    amax[nf - 2, 0] = amax[nf - 2, 8] = 0.5            # fix-up on the very last frequency
+    arg[11] = arg[11][0]                               # a non-injective arg-max row (duplicates)
+    arg[11, 3] = (arg[11, 0] + 1) % n2
+    amax[12, :] = 0.95
+    amax[12, (arg[11, 0] + 2) % n2] = 0.1              # weak, but not visited after the collapse
     info = np.zeros(nf, np.int32)
     return k, arg, amax, info
 
@@ -46,23 +53,55 @@ def _worker(rank, world, port, nf, n2, out_dir):
     arg_loc = torch.from_numpy(arg[lo - halo:hi - 1].copy())
     amax_loc = torch.from_numpy(amax[lo - halo:hi - 1].copy())
     info_loc = torch.from_numpy(info[lo:hi].copy())
-    k_all, arg_all, amax_all, info_all = solver._gather_blocks(torch, bounds, rank, n2, k_loc, arg_loc,
-                                                               amax_loc, info_loc)
-    assert np.array_equal(k_all.numpy(), k)
-    assert np.array_equal(arg_all.numpy(), arg)
-    assert np.array_equal(amax_all.numpy(), amax)
-    order = _native.track_scan(arg_all.numpy(), amax_all.numpy(), nf, n2)
-    np.save(os.path.join(out_dir, 'order_%d.npy' % rank), order)
+    sol = solver.WaveElementAxisym(None)
+    order_loc, _ = solver._track_sharded(sol, torch, _native, bounds, rank, n2, k_loc, arg_loc, amax_loc, info_loc)
+    assert np.array_equal(order_loc, sol.order[lo:hi])
+    assert np.array_equal(sol.k_native, k)
+    np.save(os.path.join(out_dir, 'order_%d.npy' % rank), sol.order)
+    np.save(os.path.join(out_dir, 'k_%d.npy' % rank), sol.k)
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('nf', [41, 64])
-def test_two_rank_gather_and_scan(tmp_path, built_lib, nf):
-    n2, world = 12, 2
+@pytest.mark.parametrize('nf,world', [(41, 2), (64, 2), (50, 3), (37, 4)])
+def test_sharded_tracking_matches_sequential_scan(tmp_path, built_lib, nf, world):
+    """Segmented relative scan + chain + NCCL-style gathers == the sequential reference scan."""
+    n2 = 12
     port = _free_port()
     mp.spawn(_worker, args=(world, port, nf, n2, str(tmp_path)), nprocs=world, join=True)
     from axisafe_b200 import _native
     k, arg, amax, info = _global_tables(nf, n2)
     ref = _native.track_scan(arg, amax, nf, n2)
+    ref_k = np.take_along_axis(k, ref.astype(np.int64), axis=1)
     for r in range(world):
         assert np.array_equal(np.load(os.path.join(str(tmp_path), 'order_%d.npy' % r)), ref)
+        assert np.array_equal(np.load(os.path.join(str(tmp_path), 'k_%d.npy' % r)), ref_k)
+
+
+def test_segmented_scan_random(built_lib):
+    """Host-only: any cut of the frequency axis into blocks reproduces the sequential scan."""
+    from axisafe_b200 import _native
+    rng = np.random.default_rng(11)
+    n2 = 9
+    for trial in range(40):
+        nf = int(rng.integers(2, 60))
+        arg = np.array([rng.permutation(n2) for _ in range(nf - 1)], dtype=np.int32)
+        for i in rng.integers(0, nf - 1, size=3):
+            arg[i, rng.integers(0, n2)] = rng.integers(0, n2)          # duplicates
+        amax = np.where(rng.random([nf - 1, n2]) < 0.04, 0.5, 0.97)
+        ref = _native.track_scan(arg, amax, nf, n2)
+        world = int(rng.integers(1, min(nf, 6) + 1))
+        bounds = [(nf * r) // world for r in range(world + 1)]
+        parts, payloads = [], []
+        for r in range(world):
+            lo, hi = bounds[r], bounds[r + 1]
+            halo = 1 if lo > 0 else 0
+            a, m = arg[lo - halo:hi - 1], amax[lo - halo:hi - 1]
+            rel, starts = _native.track_scan_segments(a, m, n2)
+            ends = starts[1:] + [a.shape[0] + 1]
+            fix = np.asarray(starts[1:], dtype=np.int64) - 1
+            payloads.append((np.stack([rel[e - 1] for e in ends]), a[fix], m[fix]))
+            parts.append((rel, starts, ends, halo))
+        sig = _native.chain_segments(payloads, n2)
+        got = np.concatenate([np.concatenate([rel[a:e][:, sig[r][s]] for s, (a, e) in enumerate(zip(starts, ends))])[halo:]
+                              for r, (rel, starts, ends, halo) in enumerate(parts)])
+        assert np.array_equal(got, ref), trial
