@@ -39,6 +39,8 @@ _SIGNATURES = {
                         [ctypes.c_void_p] * 3 + [ctypes.c_longlong, ctypes.c_void_p]),
     'axs_track_scan': (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p]),
     'axs_apply_order': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 6),
+    'axs_select_modes': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 2 + [ctypes.c_int] +
+                         [ctypes.c_void_p] * 3),
     'axs_energy_ratio': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 2 +
                          [ctypes.c_int] + [ctypes.c_void_p] * 3 + [ctypes.c_int] + [ctypes.c_void_p] * 5),
     'axs_quadratic_forms': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 2 + [ctypes.c_int, ctypes.c_void_p,
@@ -449,6 +451,17 @@ def chain_segments(payloads, n2):
             sigma = fixup_row(prev, d_arg[s], d_amax[s], n2) if s < S - 1 else prev
         out.append(mine)
     return out
+
+
+def select_modes(n2, nf, k, sigma, m, psi, rank=None):
+    """axs_select_modes: rank of every native mode by |k - sigma| (device int32 [nf, n2]); the
+    mode-shape columns of rank >= m are zeroed in ``psi`` (in place, may be None)."""
+    torch = torch_cuda()
+    if rank is None:
+        rank = torch.empty(nf * n2, dtype=torch.int32, device='cuda')
+    check(lib().axs_select_modes(n2, nf, _ptr(k), _ptr(sigma), int(m), _ptr(rank), _ptr(psi), _stream(torch)),
+          'axs_select_modes')
+    return rank
 
 
 def apply_order(n2, nf, order, k, psi):

@@ -28,8 +28,9 @@ import scipy.sparse as sps
 class _LazyModes(object):
     """Device-resident ``psi_hat`` block that is copied to the host on first use."""
 
-    def __init__(self, tensor, shape, first, total):
+    def __init__(self, tensor, shape, first, total, ncols=None):
         self.tensor, self.shape, self.first, self.total = tensor, shape, first, total
+        self.ncols = ncols               # subset mode: only the first ncols columns are modes
         self.host = None
 
     def materialise(self):
@@ -39,6 +40,8 @@ class _LazyModes(object):
             # rank's frequencies [first, first + shape[0]) exist here (see local_range); the full
             # array (0.5 GB .. TBs) is never gathered.
             self.host = _native.download(self.tensor).reshape(self.shape)
+            if self.ncols is not None:
+                self.host = np.ascontiguousarray(self.host[:, :, :self.ncols])
         return self.host
 
 
@@ -62,6 +65,7 @@ class WaveElementAxisym(object):
         self.order = None                # tracked column order per frequency
         self._k_native = None            # eigenvalues before tracking (native order)
         self.local_range = None          # (first, last+1) frequencies solved by this rank
+        self._ncols = None               # subset mode: number of kept waves (device arrays stay 2N wide)
         self.timings = {}
 
     # psi_hat lives on the GPU until somebody reads it ------------------------------------
@@ -106,8 +110,10 @@ class WaveElementAxisym(object):
     def solve(self, f, no_of_waves='full', central_wavespeed=0, distributed='auto', pipeline=True):
         """All wavenumbers and mode shapes at every frequency of ``f`` (ref solver.py:76-184).
 
-        ``no_of_waves`` other than 'full' (the reference's sparse shift-invert mode,
-        solver.py:137-140) is outside the accelerated path and raises.
+        ``no_of_waves`` = m (the reference's sparse shift-invert mode, solver.py:137-140) keeps the m
+        wavenumbers nearest to ``w / central_wavespeed`` per frequency, tracked among themselves:
+        ``k`` is [nf, m], ``psi_hat`` [nf, 2N, m].  The GPU computes the whole spectrum anyway, so the
+        subset is a selection (axs_select_modes), not an Arnoldi iteration.
         ``distributed``: 'auto' shards the frequency axis over the ranks of an initialised
         ``torch.distributed`` process group; False forces a single-GPU sweep.
         ``pipeline``: single-GPU sweeps of >= 128 points run as a 4-chunk pipeline that copies the
@@ -116,8 +122,16 @@ class WaveElementAxisym(object):
         """
         from . import _native
         print('Calculating dispersion curves...')
-        if no_of_waves != 'full':
-            raise NotImplementedError('only the dense "full" solution (scipy.linalg.eig path) is accelerated')
+        subset = None
+        if not (isinstance(no_of_waves, str) and no_of_waves == 'full'):
+            # the reference's shift-invert mode (solver.py:137-140): the no_of_waves eigenvalues nearest
+            # to sigma = w / central_wavespeed.  Here: full spectrum on the GPU, then a selection.
+            subset = int(no_of_waves)
+            if subset < 1 or subset > 2 * self.Mesh.no_of_dofs - 2:
+                raise ValueError('no_of_waves must be between 1 and 2N - 2 (ARPACK: k < n - 1)')
+            if central_wavespeed == 0:
+                raise ZeroDivisionError('central_wavespeed must be non-zero for a subset solution')
+            distributed = False                          # every rank solves the whole (small) sweep
         torch = _native.torch_cuda()
         mesh = self.Mesh
         ops = mesh._device_ops
@@ -150,6 +164,12 @@ class WaveElementAxisym(object):
         self.local_range = (lo, hi)
 
         small = n2 <= _native.lib().axs_max_small_n2()
+        self._ncols = subset
+        if subset is not None:
+            _solve_subset(self, torch, _native, ops, n2, subset, central_wavespeed, small, host_attributes)
+            self.evaluated = True
+            self.k_ready = 0
+            return
         if small and world == 1 and pipeline and nf >= 128:
             # single GPU, shared-memory kernels: chunk pipeline (compute of chunk c+1 overlaps the
             # host scan, the column gather and the psi_hat download of chunk c)
@@ -246,10 +266,12 @@ class WaveElementAxisym(object):
             raise RuntimeError('mode shapes are no longer on the device; call solve() again')
         er_loc = _native.energy_ratio(mesh.no_of_dofs, hi - lo, self.psi_hat_device.reshape(-1), tclass,
                                       triplets(M_tot), triplets(M_pml))
+        if self._ncols is not None:
+            er_loc = er_loc[:, :self._ncols]                  # the padding columns are not modes
         if hi - lo == len(self.w):
             self.er = er_loc
         else:
-            self.er = np.full([len(self.w), 2 * mesh.no_of_dofs], np.nan)   # other ranks' frequencies
+            self.er = np.full([len(self.w), er_loc.shape[1]], np.nan)   # other ranks' frequencies
             self.er[lo:hi] = er_loc
 
     def k_propagating(self, imag_threshold=10, ER_threshold=0.9):
@@ -314,7 +336,7 @@ class WaveElementAxisym(object):
                 self.k_propagating()
             sel = np.asarray(self.propagating_indices, dtype=np.int32)
         else:
-            sel = None
+            sel = None if self._ncols is None else np.arange(self._ncols, dtype=np.int32)
         if self.psi_hat_device is None:
             raise RuntimeError('mode shapes are no longer on the device; call solve() again')
         lo, hi = self.local_range
@@ -356,8 +378,10 @@ class WaveElementAxisym(object):
                 raise RuntimeError('mode shapes are no longer on the device; call solve() again')
             lo, hi = self.local_range
             proj = _native.modal_projection(N, hi - lo, self.psi_hat_device.reshape(-1), force_vector)
+            if self._ncols is not None:
+                proj = proj[:, :self._ncols]
             if hi - lo != len(self.w):
-                full = np.full([len(self.w), 2 * N], np.nan + 0j)              # other ranks' frequencies
+                full = np.full([len(self.w), proj.shape[1]], np.nan + 0j)      # other ranks' frequencies
                 full[lo:hi] = proj
                 proj = full
             return (1j * np.sinc(self.Mesh.n * theta_0 / np.pi) / (2 * np.pi * r_f) * proj)[:, :, np.newaxis]
@@ -527,7 +551,79 @@ def _solve_pipelined(sol, torch, _native, ops, nf, n2, host_work=None):
     sol._psi = modes
 
 
-def _sweep_large(torch, _native, ops, omega, halo):
+def _subset_scan(arg, amax, rank, m):
+    """Tracked native column per (frequency, wave) for the subset mode.
+
+    The reference tracks the m columns ARPACK returned (solver.py:151-182): biorth is m x m,
+    ``new_order`` holds *positions* in the current column list, and weakly matched modes are
+    re-seated from ``set(range(m))``.  Here position p at frequency i is the selected mode of
+    rank p (distance to sigma); ``arg``/``amax`` are the native tables of axs_track_pairs computed
+    with the unselected columns zeroed, so ``rank[i][arg]`` is the position the reference's arg-max
+    would return.  Returns cols [nf, m] (native column of every tracked wave).
+    """
+    from . import _native
+    nf, n2 = rank.shape
+    sel = np.argsort(rank, axis=1, kind='stable')[:, :m].astype(np.int32)     # native index by position
+    cols = np.empty([nf, m], dtype=np.int32)
+    cols[0] = sel[0]
+    for i in range(1, nf):
+        prev = cols[i - 1]
+        pos = np.minimum(rank[i][arg[i - 1][prev]], m - 1)        # (an all-zero row cannot occur)
+        if not (np.rint(amax[i - 1][prev] * 100.0) >= 91.0).all():
+            ident = np.arange(m, dtype=np.int32)
+            pos = _native.fixup_row(ident, pos.astype(np.int32), amax[i - 1][prev], m)
+        cols[i] = sel[i][pos]
+    return cols
+
+
+def _solve_subset(sol, torch, _native, ops, n2, m, central_wavespeed, small, host_attributes):
+    """solve(f, no_of_waves=m, central_wavespeed=c): whole spectrum on the GPU, the m wavenumbers
+    nearest to w / c selected per frequency (axs_select_modes), tracked among themselves.
+
+    Device arrays keep their [nf, 2N(, 2N)] shape with the tracked waves in the first m columns
+    (the remaining mode-shape columns are zero), so the energy-ratio / energy-velocity / forced
+    response kernels run unchanged; the host attributes are cut to m columns like the reference's.
+    """
+    nf = len(sol.w)
+    sigma = torch.from_numpy(sol.w / float(central_wavespeed)).cuda()
+    omega = torch.from_numpy(sol.w.copy()).cuda()
+    if small:
+        k_nat, psi_nat, info, work = _native.eig_sweep(ops, omega, want_modes=True)
+        rank = _native.select_modes(n2, nf, k_nat, sigma, m, psi_nat)
+        if nf > 1:
+            arg, amax = _native.track_pairs(ops, psi_nat, nf - 1, scratch=work.buf)
+        else:
+            arg = torch.empty(0, dtype=torch.int32, device='cuda')
+            amax = torch.empty(0, dtype=torch.float64, device='cuda')
+        host_attributes()                                # while the kernels above run
+    else:
+        host_attributes()
+        rank = torch.empty(nf * n2, dtype=torch.int32, device='cuda')
+        k_nat, psi_nat, info, arg, amax = _sweep_large(torch, _native, ops, omega, 0, select=(sigma, m, rank))
+    sol.info = info.cpu().numpy()
+    _raise_unconverged(sol.info)
+    k_host = k_nat.view(nf, n2).cpu().numpy()
+    rank_h = rank.view(nf, n2).cpu().numpy()
+    arg_h = arg.cpu().numpy().reshape(max(nf - 1, 0), n2)
+    amax_h = amax.cpu().numpy().reshape(max(nf - 1, 0), n2)
+    cols = _subset_scan(arg_h, amax_h, rank_h, m)
+    # full-width order rows: the tracked waves first, then the unselected (zeroed) native columns
+    rest = np.argsort(rank_h, axis=1, kind='stable')[:, m:].astype(np.int32)
+    order = np.ascontiguousarray(np.concatenate([cols, rest], axis=1))
+    sol.k_native = k_host
+    sol.order = cols
+    sol.k = np.take_along_axis(k_host, cols.astype(np.int64), axis=1)
+    sol.local_range = (0, nf)
+    if psi_nat is None:
+        sol._psi = None
+    elif not small:
+        sol._psi = _LazyModes(_reorder_in_place(torch, _native, n2, order, psi_nat, 0), (nf, n2, n2), 0, nf, ncols=m)
+    else:
+        _, psi_sorted = _native.apply_order(n2, nf, order, k_nat, psi_nat)
+        sol._psi = _LazyModes(psi_sorted, (nf, n2, n2), 0, nf, ncols=m)
+
+
+def _sweep_large(torch, _native, ops, omega, halo, select=None):
     """Chunked sweep for 2N above the shared-memory kernels (eig_big.cu).
 
     The per-frequency workspace is ~32 (2N)^2 bytes, so the frequency block is processed in
@@ -562,6 +658,9 @@ def _sweep_large(torch, _native, ops, omega, halo):
         c1 = min(c0 + C, nloc)
         cur = slots[nn:(c1 - c0 + 1) * nn]
         _native.eig_sweep_into(ops, omega[c0:c1], k[c0 * n2:c1 * n2], cur, info[c0:c1], work)
+        if select is not None:                        # subset mode: unselected mode columns zeroed before tracking
+            sigma, m_sel, rank = select
+            _native.select_modes(n2, c1 - c0, k[c0 * n2:c1 * n2], sigma[c0:c1], m_sel, cur, rank[c0 * n2:c1 * n2])
         first = 0 if c0 > 0 else 1                    # slot 0 holds the last frequency of the previous chunk
         npairs = (c1 - c0) - first
         if npairs > 0:

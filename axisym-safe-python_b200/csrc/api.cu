@@ -17,6 +17,7 @@ int axs_launch_modes(int, int, const cplx*, const cplx*, int, const cplx*, cplx*
 int axs_launch_unpack(int, int, AxsWork, cplx*, cudaStream_t);
 int axs_launch_track(int, int, const cplx*, const cplx*, const cplx*, int, cplx*, int*, double*, cudaStream_t);
 int axs_launch_apply_order(int, int, const int*, const cplx*, const cplx*, cplx*, cplx*, cudaStream_t);
+int axs_launch_select_modes(int, int, const cplx*, const double*, int, int*, cplx*, cudaStream_t);
 int axs_launch_reduce_big(int, int, const cplx*, const cplx*, const cplx*, const cplx*, const cplx*,
                           const double*, int, const cplx*, AxsWorkBig, cudaStream_t);
 int axs_launch_hqr_big(int, int, cplx*, int*, AxsWorkBig, cudaStream_t);
@@ -277,6 +278,18 @@ extern "C" int axs_apply_order(int n2, int nf, const int* order, const axs_cplx*
     if (!k_out) return -6;
     return axs_launch_apply_order(n2, nf, order, (const cplx*)k, (const cplx*)psi, (cplx*)k_out,
                                   (cplx*)psi_out, (cudaStream_t)stream);
+}
+
+extern "C" int axs_select_modes(int n2, int nf, const axs_cplx* k, const double* sigma, int m, int* rank,
+                                axs_cplx* psi, void* stream)
+{
+    if (n2 <= 0) return -1;
+    if (nf <= 0) return -2;
+    if (!k) return -3;
+    if (!sigma) return -4;
+    if (m <= 0 || m > n2) return -5;
+    if (!rank) return -6;
+    return axs_launch_select_modes(n2, nf, (const cplx*)k, sigma, m, rank, (cplx*)psi, (cudaStream_t)stream);
 }
 
 extern "C" int axs_energy_ratio(int N, int nf, const axs_cplx* psi, const int* tclass,

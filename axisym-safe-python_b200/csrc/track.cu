@@ -420,6 +420,67 @@ extern "C" int axs_launch_track(int N, int hb, const cplx* Cb, const cplx* K6d, 
     return (int)cudaGetLastError();
 }
 
+// -----------------------------------------------------------------------------------------
+// Subset mode of solve() (solver.py:137-140: scipy.sparse.linalg.eigs(S, k=m, sigma=w/c, which='LM'),
+// i.e. the m eigenvalues nearest to sigma).  The whole spectrum is already on the device, so the
+// subset is a selection:  k_rank_modes ranks the modes of one frequency by |k - sigma| (counting
+// rank, ties by native index; CTA = one frequency, the spectrum staged in shared memory in tiles),
+// k_zero_unselected clears the mode-shape columns of rank >= m so that the tracking arg-max
+// (k_track_mma) only ever sees the selected columns.
+__global__ void __launch_bounds__(256)
+k_rank_modes(int n, const cplx* __restrict__ k_all, const double* __restrict__ sigma, int* __restrict__ rank_all)
+{
+    __shared__ double sd[1024];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const cplx* k = k_all + (long long)f * n;
+    const double sg = sigma[f];
+    for (int j0 = 0; j0 < n; j0 += 256) {
+        const int j = j0 + tid;
+        double dj = 0.0;
+        if (j < n) { const double dx = k[j].x - sg, dy = k[j].y; dj = dx * dx + dy * dy; }
+        int cnt = 0;
+        for (int l0 = 0; l0 < n; l0 += 1024) {
+            __syncthreads();
+            for (int l = tid; l < 1024 && l0 + l < n; l += 256) {
+                const double dx = k[l0 + l].x - sg, dy = k[l0 + l].y;
+                sd[l] = dx * dx + dy * dy;
+            }
+            __syncthreads();
+            const int lim = (n - l0 < 1024) ? n - l0 : 1024;
+            if (j < n)
+                for (int l = 0; l < lim; ++l) {
+                    const double dl = sd[l];
+                    cnt += (dl < dj || (dl == dj && l0 + l < j)) ? 1 : 0;
+                }
+        }
+        if (j < n) rank_all[(long long)f * n + j] = cnt;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_zero_unselected(int n, int m, const int* __restrict__ rank_all, cplx* __restrict__ psi_all)
+{
+    const int f = blockIdx.y;
+    const int* rank = rank_all + (long long)f * n;
+    cplx* psi = psi_all + (long long)f * n * n;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n * n; idx += gridDim.x * blockDim.x) {
+        const int c = idx % n;
+        if (rank[c] >= m) psi[idx] = mk(0, 0);
+    }
+}
+
+extern "C" int axs_launch_select_modes(int n, int nf, const cplx* k, const double* sigma, int m, int* rank,
+                                       cplx* psi, cudaStream_t st)
+{
+    k_rank_modes<<<nf, 256, 0, st>>>(n, k, sigma, rank);
+    if (psi && m < n) {
+        long long cells = (long long)n * n;
+        int bx = (int)((cells + 255) / 256); if (bx > 64) bx = 64;
+        k_zero_unselected<<<dim3(bx, nf), 256, 0, st>>>(n, m, rank, psi);
+    }
+    return (int)cudaGetLastError();
+}
+
 extern "C" int axs_launch_apply_order(int n, int nf, const int* order, const cplx* k_in, const cplx* psi_in,
                                       cplx* k_out, cplx* psi_out, cudaStream_t st)
 {

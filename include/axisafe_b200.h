@@ -142,6 +142,17 @@ int axs_track_scan(const int* h_arg, const double* h_amax, int nf, int n2, int s
 int axs_apply_order(int n2, int nf, const int* order, const axs_cplx* k, const axs_cplx* psi,
                     axs_cplx* k_out, axs_cplx* psi_out, void* stream);
 
+/* ---- subset of the spectrum (the no_of_waves != 'full' mode) -------
+ * Replaces scipy.sparse.linalg.eigs(S, k=m, sigma=w/central_wavespeed, which='LM') of
+ * solver.py:137-140 - shift-invert Arnoldi returns the m eigenvalues nearest to sigma; with the
+ * whole spectrum already on the device that is a selection:
+ *     rank[f][j] = position of native mode j of frequency f when sorted by |k[f][j] - sigma[f]|
+ *                  (ties by native index),
+ * and, when psi != NULL, the mode-shape columns of rank >= m are zeroed in place so that
+ * axs_track_pairs (arg-max over columns) only sees the selected modes.  psi is [nf][n2][n2]. */
+int axs_select_modes(int n2, int nf, const axs_cplx* k, const double* sigma, int m, int* rank,
+                     axs_cplx* psi, void* stream);
+
 /* ---- energy ratio ------------------------------------------
  * Replaces the dense batched products of WaveElementAxisym.energy_ratio, solver.py:248-266:
  *     q = conj(T) psi[N:],  E_tot = q^H M_total q,  E_pml = q^H M_pml q,  er = |E_pml| / |E_tot|

@@ -150,9 +150,48 @@ def energy_velocity_fixtures():
                                                os.path.getsize(path) / 1024))
 
 
+SUBSET_CASES = [('free_steel_pipe', 0, {'nf': 24}, 3, 3000.0), ('pipe_soil_pml', 0, {'nf': 16}, 8, 1200.0),
+                ('gravenkamp', 1, {'nf': 16}, 10, 2500.0)]
+
+
+def subset_fixtures():
+    """tests/golden/subset_*.npz: the reference's shift-invert mode (solver.py:137-140),
+    ``solve(f, no_of_waves=m, central_wavespeed=c)``: tracked k [nf, m] and the lower halves of
+    psi_hat [nf, N, m].  ARPACK starts from a random vector, so only the per-frequency SET of
+    wavenumbers (and each mode shape up to sign) is reproducible; the column order at the first
+    frequency is ARPACK's.  Also stored: the margin between the m-th and (m+1)-th nearest
+    eigenvalue of the dense spectrum (a selection is only well defined when that is not tiny).
+    """
+    ref = refshim.load()
+    from axisafe_b200 import cases
+    outdir = os.path.join(ROOT, 'tests', 'golden')
+    for name, n, kw, m, c0 in SUBSET_CASES:
+        c = cases.ALL[name](n=n, **kw)
+        with refshim.quiet():
+            mesh = ref.mesh.Mesh()
+            mesh.create(c['sets'], c['fmax'], PML=c['PML'], PML_props=c['PML_props'])
+            mesh.assemble_matrices(n)
+            sol = ref.solver.WaveElementAxisym(mesh)
+            sol.solve(c['f'], no_of_waves=m, central_wavespeed=c0)
+            margin = []
+            for i in range(len(c['f'])):
+                ev = la.eig(reference_S(sol, mesh, n, sol.w[i]))[0]
+                d = np.sort(abs(ev - sol.w[i] / c0))
+                margin.append((d[m] - d[m - 1]) / d[m])
+        N = mesh.no_of_dofs
+        path = os.path.join(outdir, 'subset_%s_n%d.npz' % (name, n))
+        np.savez_compressed(path, f=c['f'], k=sol.k, psi_low=sol.psi_hat[:, N:, :], m=m, c0=c0,
+                            margin=np.array(margin))
+        print('%-32s nf=%3d 2N=%3d m=%2d min margin %.2e %6.0f KB' % (
+            os.path.basename(path), len(c['f']), 2 * N, m, min(margin), os.path.getsize(path) / 1024))
+
+
 if __name__ == '__main__':
-    if 'envel' in sys.argv[1:]:
+    if 'subset' in sys.argv[1:]:
+        subset_fixtures()
+    elif 'envel' in sys.argv[1:]:
         energy_velocity_fixtures()
     else:
         main()
         energy_velocity_fixtures()
+        subset_fixtures()

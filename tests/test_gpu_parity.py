@@ -453,3 +453,67 @@ def test_forced_response_vs_reference(name, n, kw):
             assert err < 1e-5, (i, a, err)
             checked += 1
     assert checked > 5
+
+
+# ------------------------------------------------- subset of the spectrum (row N4, shift-invert mode)
+SUBSET = [('free_steel_pipe', 0, {'nf': 24}), ('pipe_soil_pml', 0, {'nf': 16}), ('gravenkamp', 1, {'nf': 16})]
+
+
+@pytest.mark.parametrize('name,n,kw', SUBSET, ids=['%s-n%d' % (c[0], c[1]) for c in SUBSET])
+def test_subset_solution_vs_reference_eigs(name, n, kw):
+    """solve(f, no_of_waves=m, central_wavespeed=c) against the reference's ARPACK shift-invert run
+    (tests/golden/subset_*.npz): same set of wavenumbers at every frequency (1e-8), same mode shapes
+    (1e-6, up to sign), reference shapes of the result arrays; and the downstream energy ratio of the
+    kept waves equals that of the same waves in a full solution."""
+    import os
+    import axisafe_b200 as ax
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'subset_%s_n%d.npz' % (name, n)))
+    c = make_case(name, n, kw)
+    assert np.array_equal(c['f'], g['f'])
+    mw, c0 = int(g['m']), float(g['c0'])
+    mesh = _mesh(c)
+    N = mesh.no_of_dofs
+    with contextlib.redirect_stdout(io.StringIO()):
+        sol = ax.solver.WaveElementAxisym(mesh)
+        sol.solve(c['f'], no_of_waves=mw, central_wavespeed=c0)
+        full = ax.solver.WaveElementAxisym(mesh)
+        full.solve(c['f'])
+    assert sol.k.shape == g['k'].shape == (len(c['f']), mw)
+    assert sol.psi_hat.shape == (len(c['f']), 2 * N, mw)
+    for i in range(len(c['f'])):
+        sigma = sol.w[i] / c0
+        # the kept waves are the m nearest of the full spectrum ...
+        near = np.sort(np.abs(full.k_native[i] - sigma))[:mw]
+        assert np.allclose(np.sort(np.abs(sol.k[i] - sigma)), near, rtol=1e-12, atol=0)
+        # ... and the ones ARPACK returned
+        perm, err = so.match_eigenvalues(g['k'][i], sol.k[i])
+        scale = np.maximum(np.abs(g['k'][i]), abs(sigma))       # shift-invert resolves |k - sigma| relative to sigma
+        assert np.all(np.abs(g['k'][i] - sol.k[i][perm]) <= 1e-8 * scale), (i, err)
+        errs = so.mode_shape_error(g['psi_low'][i], sol.psi_hat[i][N:, perm])
+        assert np.max(errs) <= 1e-6, (i, errs)
+    # tracked among themselves: consecutive frequencies keep the wave in its column (smooth branches)
+    jump = np.abs(np.diff(sol.k, axis=0)) / np.abs(sol.k[1:])
+    assert np.median(jump) < 0.5
+    if c['PML'] != 0:
+        with contextlib.redirect_stdout(io.StringIO()):
+            sol.energy_ratio()
+            full.energy_ratio()
+        assert sol.er.shape == sol.k.shape
+        for i in range(len(c['f'])):
+            perm, _ = so.match_eigenvalues(sol.k[i], full.k[i])
+            assert np.allclose(sol.er[i], full.er[i][perm], rtol=1e-9, atol=1e-12)
+    amps = sol.point_excited_waves(0.01, 0.05, np.ones(N))
+    assert amps.shape == (len(c['f']), mw, 1)
+
+
+def test_subset_arguments():
+    import axisafe_b200 as ax
+    c = make_case('free_steel_pipe', 0, {'nf': 4})
+    mesh = _mesh(c)
+    sol = ax.solver.WaveElementAxisym(mesh)
+    with contextlib.redirect_stdout(io.StringIO()):
+        with pytest.raises(ValueError):
+            sol.solve(c['f'], no_of_waves=2 * mesh.no_of_dofs, central_wavespeed=3000.)
+        with pytest.raises(ZeroDivisionError):
+            sol.solve(c['f'], no_of_waves=3)

@@ -162,3 +162,44 @@ def test_track_scan_matches_python_semantics(built_lib):
         arg[i, rows[0]] = arg[i, rows[1]]
     got = _native.track_scan(arg, amax, nf, n2)
     assert np.array_equal(got, _python_scan(arg, amax, n2))
+
+
+def test_subset_scan_matches_reference_semantics(built_lib):
+    """no_of_waves = m: the position-based tracking of solver.py:151-182 on the m selected
+    columns, restated literally from |biorth| matrices, against _subset_scan on native tables."""
+    from axisafe_b200 import solver
+    rng = np.random.default_rng(5)
+    n2, m, nf = 14, 5, 40
+    rank = np.array([rng.permutation(n2) for _ in range(nf)], dtype=np.int32)
+    sel = np.argsort(rank, axis=1)[:, :m]                       # native column of position p
+    P = rng.random([nf - 1, n2, n2]) * 0.85                     # |biorth| in native indices
+    for i in range(nf - 1):                                     # one dominant entry per row
+        for a, b in zip(rng.permutation(n2), rng.permutation(n2)):
+            P[i, a, b] = 0.97 if rng.random() > 0.08 else 0.5
+    # device tables: arg-max over the SELECTED columns only (the others are zeroed)
+    arg = np.zeros([nf - 1, n2], np.int32)
+    amax = np.zeros([nf - 1, n2])
+    for i in range(nf - 1):
+        masked = np.zeros_like(P[i])
+        masked[:, sel[i + 1]] = P[i][:, sel[i + 1]]
+        arg[i], amax[i] = masked.argmax(1), masked.max(1)
+    got = solver._subset_scan(arg, amax, rank, m)
+    cols = np.empty([nf, m], np.int64)
+    cols[0] = sel[0]
+    fixups = 0
+    for i in range(1, nf):
+        biorth = P[i - 1][np.ix_(cols[i - 1], sel[i])]
+        new_order = np.argmax(abs(biorth), axis=1)
+        valid = np.round(abs(biorth[range(len(biorth)), list(new_order)]), 2) > 0.9
+        valid_entries = np.delete(new_order, np.where(valid == False))   # noqa: E712
+        if not valid.all():
+            fixups += 1
+            unassigned = list(set(range(len(biorth))) - set(valid_entries))
+            j = 0
+            for ii in range(len(valid)):
+                if not valid[ii]:
+                    new_order[ii] = unassigned[j]
+                    j += 1
+        cols[i] = sel[i][new_order]
+    assert fixups > 3
+    assert np.array_equal(got, cols)
