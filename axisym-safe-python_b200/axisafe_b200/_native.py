@@ -433,14 +433,17 @@ def track_scan_segments(arg, amax, n2):
         start = i + 1
 
 
-def chain_segments(payloads, n2):
+def chain_segments(payloads, n2, sigma0=None, return_final=False):
     """Absolute column order at the start of every segment of every rank.
 
     ``payloads[r]`` = (comps [S_r, n2], d_arg [S_r - 1, n2], d_amax [S_r - 1, n2]) as produced from
     track_scan_segments: the last relative row of each segment and the pair tables of the fix-up
-    row that ends it.  Returns ``sigma[r][s]`` (int32 [n2]); cost O(total segments * n2).
+    row that ends it.  ``sigma0`` = absolute order at the base frequency of the first block
+    (identity when the first block starts at frequency 0).  Returns ``sigma[r][s]`` (int32 [n2]) -
+    and the order at the last frequency of the last block with ``return_final``; cost
+    O(total segments * n2).
     """
-    sigma = np.arange(n2, dtype=np.int32)
+    sigma = np.arange(n2, dtype=np.int32) if sigma0 is None else np.asarray(sigma0, dtype=np.int32)
     out = []
     for comps, d_arg, d_amax in payloads:
         mine = []
@@ -450,7 +453,7 @@ def chain_segments(payloads, n2):
             prev = comps[s][sigma]                      # order at the last frequency of the segment
             sigma = fixup_row(prev, d_arg[s], d_amax[s], n2) if s < S - 1 else prev
         out.append(mine)
-    return out
+    return (out, sigma) if return_final else out
 
 
 def select_modes(n2, nf, k, sigma, m, psi, rank=None):

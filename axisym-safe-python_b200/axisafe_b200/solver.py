@@ -21,6 +21,8 @@ eigenvalue / arg-max tables are all-gathered (NCCL).  No CPU fallback.
 """
 from __future__ import print_function
 
+import os
+
 import numpy as np
 import scipy.sparse as sps
 
@@ -64,7 +66,8 @@ class WaveElementAxisym(object):
         self.info = None                 # per-frequency count of unconverged eigenvalues
         self.order = None                # tracked column order per frequency
         self._k_native = None            # eigenvalues before tracking (native order)
-        self.local_range = None          # (first, last+1) frequencies solved by this rank
+        self.local_range = None          # (first, last+1) frequencies solved by this rank (contiguous block)
+        self.local_index = None          # global indices of the frequencies whose mode shapes this rank holds
         self._ncols = None               # subset mode: number of kept waves (device arrays stay 2N wide)
         self.timings = {}
 
@@ -170,6 +173,13 @@ class WaveElementAxisym(object):
             self.evaluated = True
             self.k_ready = 0
             return
+        self.local_index = np.arange(lo, hi)
+        if small and world > 1 and pipeline and nf // world >= 128 and os.environ.get('AXS_SHARD_PIPE', '1') != '0':
+            # sharded + pipelined: interleaved pieces, order fixed chunk by chunk (see the function)
+            _solve_sharded_pipelined(self, torch, _native, ops, nf, n2, rank, world, host_attributes)
+            self.evaluated = True
+            self.k_ready = 0
+            return
         if small and world == 1 and pipeline and nf >= 128:
             # single GPU, shared-memory kernels: chunk pipeline (compute of chunk c+1 overlaps the
             # host scan, the column gather and the psi_hat download of chunk c)
@@ -261,18 +271,18 @@ class WaveElementAxisym(object):
             keep = coo.data != 0
             return coo.row[keep], coo.col[keep], (coo.data * mult[coo.col])[keep]
         tclass = [0 if t == 1 else 1 for t in mesh.Tdiag]
-        lo, hi = self.local_range
+        loc = self.local_index
         if self.psi_hat_device is None:
             raise RuntimeError('mode shapes are no longer on the device; call solve() again')
-        er_loc = _native.energy_ratio(mesh.no_of_dofs, hi - lo, self.psi_hat_device.reshape(-1), tclass,
+        er_loc = _native.energy_ratio(mesh.no_of_dofs, len(loc), self.psi_hat_device.reshape(-1), tclass,
                                       triplets(M_tot), triplets(M_pml))
         if self._ncols is not None:
             er_loc = er_loc[:, :self._ncols]                  # the padding columns are not modes
-        if hi - lo == len(self.w):
+        if len(loc) == len(self.w):
             self.er = er_loc
         else:
             self.er = np.full([len(self.w), er_loc.shape[1]], np.nan)   # other ranks' frequencies
-            self.er[lo:hi] = er_loc
+            self.er[loc] = er_loc
 
     def k_propagating(self, imag_threshold=10, ER_threshold=0.9):
         """Positive-going propagating solutions (ref solver.py:271-299); host, O(nf * 2N)."""
@@ -339,12 +349,12 @@ class WaveElementAxisym(object):
             sel = None if self._ncols is None else np.arange(self._ncols, dtype=np.int32)
         if self.psi_hat_device is None:
             raise RuntimeError('mode shapes are no longer on the device; call solve() again')
-        lo, hi = self.local_range
+        loc = self.local_index
         tclass = [0 if t == 1 else 1 for t in mesh.Tdiag]
-        forms = _native.quadratic_forms(mesh.no_of_dofs, hi - lo, self.psi_hat_device.reshape(-1), tclass, sel, mats)
+        forms = _native.quadratic_forms(mesh.no_of_dofs, len(loc), self.psi_hat_device.reshape(-1), tclass, sel, mats)
         fM, fK1, fK2, fK5, fKF, fKFT, fKFtT, fKFt, fK6 = (forms[:, :, i] for i in range(9))
-        k = self.k[lo:hi] if sel is None else self.k[lo:hi][:, sel]
-        w = self.w[lo:hi].reshape(-1, 1)
+        k = self.k[loc] if sel is None else self.k[loc][:, sel]
+        w = self.w[loc].reshape(-1, 1)
         n = mesh.n
         e_k = w ** 2 / 4 * fM
         e_p = 0.25 * (fK1 + 1j * n * fK2 + n ** 2 * fK5 + 1j * k.conj() * fKF - 1j * k * fKFT +
@@ -352,10 +362,10 @@ class WaveElementAxisym(object):
         p = -w / 2 * np.imag(fKF - 1j * n * fKFt - 1j * k * fK6)
 
         def full(a):
-            if hi - lo == len(self.w):
+            if len(loc) == len(self.w):
                 return a
             out = np.full([len(self.w), a.shape[1]], np.nan, dtype=a.dtype)   # other ranks' frequencies
-            out[lo:hi] = a
+            out[loc] = a
             return out
         self.e_k, self.e_p, self.p = full(e_k), full(e_p), full(p)
         with np.errstate(divide='ignore', invalid='ignore'):
@@ -376,13 +386,13 @@ class WaveElementAxisym(object):
             force_vector = np.r_[np.zeros(N), np.asarray(f_ext).reshape(-1)]
             if self.psi_hat_device is None:
                 raise RuntimeError('mode shapes are no longer on the device; call solve() again')
-            lo, hi = self.local_range
-            proj = _native.modal_projection(N, hi - lo, self.psi_hat_device.reshape(-1), force_vector)
+            loc = self.local_index
+            proj = _native.modal_projection(N, len(loc), self.psi_hat_device.reshape(-1), force_vector)
             if self._ncols is not None:
                 proj = proj[:, :self._ncols]
-            if hi - lo != len(self.w):
+            if len(loc) != len(self.w):
                 full = np.full([len(self.w), proj.shape[1]], np.nan + 0j)      # other ranks' frequencies
-                full[lo:hi] = proj
+                full[loc] = proj
                 proj = full
             return (1j * np.sinc(self.Mesh.n * theta_0 / np.pi) / (2 * np.pi * r_f) * proj)[:, :, np.newaxis]
 
@@ -546,6 +556,7 @@ def _solve_pipelined(sol, torch, _native, ops, nf, n2, host_work=None):
     sol.order = order.copy()
     sol.k = ks_h.numpy()                                 # tracked on the device by k_apply_order
     sol.local_range = (0, nf)
+    sol.local_index = np.arange(nf)
     modes = _LazyModes(psi_sorted, (nf, n2, n2), 0, nf)
     modes.host = psi_h.numpy()
     sol._psi = modes
@@ -614,6 +625,7 @@ def _solve_subset(sol, torch, _native, ops, n2, m, central_wavespeed, small, hos
     sol.order = cols
     sol.k = np.take_along_axis(k_host, cols.astype(np.int64), axis=1)
     sol.local_range = (0, nf)
+    sol.local_index = np.arange(nf)
     if psi_nat is None:
         sol._psi = None
     elif not small:
@@ -621,6 +633,199 @@ def _solve_subset(sol, torch, _native, ops, n2, m, central_wavespeed, small, hos
     else:
         _, psi_sorted = _native.apply_order(n2, nf, order, k_nat, psi_nat)
         sol._psi = _LazyModes(psi_sorted, (nf, n2, n2), 0, nf, ncols=m)
+
+
+_GLOO = {}
+
+
+def _host_group(dist):
+    """CPU (gloo) process group for the small per-chunk object exchange of the sharded pipeline:
+    it must not queue behind (or wait for) the compute streams like an NCCL collective would."""
+    if 'g' not in _GLOO:
+        _GLOO['g'] = dist.new_group(backend='gloo')
+    return _GLOO['g']
+
+
+def _shard_plan(nf, world, unit, K=None):
+    """Interleaved sharding of the frequency axis: the axis is cut into K global chunks and every
+    chunk into ``world`` contiguous pieces, so that all ranks finish chunk c together and its tracked
+    column order can be fixed (and its mode shapes downloaded) while chunk c+1 computes.
+    Returns pieces[c][r] = (lo, hi).  Chunk sizes follow the single-GPU pipeline (44/44/7/5 % in
+    whole waves of ``unit`` matrices per rank when the sweep is long enough)."""
+    per = nf // world
+    if K is None:
+        K = 4 if per >= 512 else 2
+    if K == 4:
+        b1 = max(unit, int(round(0.444 * per / unit)) * unit)
+        b3 = 2 * b1 + max(unit, int(round(0.074 * per / unit)) * unit)
+        if per >= 8 * unit and b3 * world < nf:
+            # every piece carries one halo frequency: b1 - 1 kept points + halo = whole waves
+            p01, p2 = b1 - 1, b3 - 2 * b1 - 1
+            gb = [0, p01 * world, 2 * p01 * world, (2 * p01 + p2) * world, nf]
+        else:
+            gb = [0, int(nf * 0.4), int(nf * 0.8), int(nf * 0.9), nf]
+    else:
+        gb = [nf * c // K for c in range(K + 1)]
+    pieces = []
+    for c in range(K):
+        L = gb[c + 1] - gb[c]
+        pieces.append([(gb[c] + (L * r) // world, gb[c] + (L * (r + 1)) // world) for r in range(world)])
+    return pieces
+
+
+def _solve_sharded_pipelined(sol, torch, _native, ops, nf, n2, rank, world, host_work=None):
+    """Sharded sweep as a chunk pipeline (one process per GPU, torch.distributed).
+
+    With one contiguous block per rank the absolute column order of a block is only known once
+    every earlier rank has finished, i.e. at the very end, and the 0.5 GB psi_hat download of every
+    rank is exposed.  Here the axis is interleaved (_shard_plan): all ranks work on pieces of the
+    same global chunk, after chunk c they exchange the segment composites of their pieces
+    (track_scan_segments / chain_segments, a few KB over a gloo group), fix the order of chunk c,
+    gather the columns and download that part of psi_hat while chunk c+1 computes - the structure
+    of _solve_pipelined with the host scan replaced by the cross-rank chain.  Every piece recomputes
+    one halo frequency (the last point of the piece before it) so no eigenvector crosses a link.
+    Results are bit-identical to the single-GPU sweep; the rank keeps the mode shapes of the
+    frequencies ``sol.local_index``.
+    """
+    import torch.distributed as dist
+    group = _host_group(dist)
+    unit = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    pieces = _shard_plan(nf, world, unit)
+    K = len(pieces)
+    mine = [pieces[c][rank] for c in range(K)]
+    halo = [1 if lo > 0 else 0 for lo, hi in mine]
+    S = [h + hi - lo for h, (lo, hi) in zip(halo, mine)]            # slots per chunk (halo first)
+    so = [0] + list(np.cumsum(S))                                   # slot offsets
+    cnt = [hi - lo for lo, hi in mine]
+    ko = [0] + list(np.cumsum(cnt))                                 # offsets of the kept rows
+    slots, kept = int(so[-1]), int(ko[-1])
+    nn = n2 * n2
+    if not _PIPE:
+        _PIPE['cs'] = [torch.cuda.Stream(), torch.cuda.Stream()]
+        _PIPE['xs'] = torch.cuda.Stream()
+        _PIPE['ss'] = torch.cuda.Stream()
+    cs, xs, ss = _PIPE['cs'], _PIPE['xs'], _PIPE['ss']
+    main = torch.cuda.current_stream()
+    dev = 'cuda'
+    w_loc = np.concatenate([sol.w[lo - h:hi] for h, (lo, hi) in zip(halo, mine)])
+    omega = torch.from_numpy(w_loc).cuda()
+    k_nat = torch.empty(slots * n2, dtype=torch.complex128, device=dev)
+    psi_nat = torch.empty(slots * nn, dtype=torch.complex128, device=dev)
+    info = torch.zeros(slots, dtype=torch.int32, device=dev)
+    arg = torch.empty(slots * n2, dtype=torch.int32, device=dev)
+    amax = torch.empty(slots * n2, dtype=torch.float64, device=dev)
+    k_sorted = torch.empty(kept * n2, dtype=torch.complex128, device=dev)
+    psi_sorted = torch.empty(kept * nn, dtype=torch.complex128, device=dev)
+    order_d = torch.empty(kept * n2, dtype=torch.int32, device=dev)
+    smax = max(S)
+    works = [_native.EigWorkspace(ops.N, smax) for _ in range(2)]
+    ybuf = [torch.empty(int(_native.lib().axs_track_worksize(ops.N, max(smax - 1, 1))), dtype=torch.uint8, device=dev)
+            for _ in range(2)]
+    pin = lambda *shape, dtype: torch.empty(*shape, dtype=dtype, pin_memory=True)
+    arg_h = pin(slots, n2, dtype=torch.int32)
+    amax_h = pin(slots, n2, dtype=torch.float64)
+    info_h = pin(slots, dtype=torch.int32)
+    order_h = pin(kept, n2, dtype=torch.int32)
+    psi_h = pin(kept, n2, n2, dtype=torch.complex128)
+    ev_track = [torch.cuda.Event() for _ in range(K)]
+    ev_small = [torch.cuda.Event() for _ in range(K)]
+    for s_ in cs + [xs, ss]:
+        s_.wait_stream(main)
+
+    def compute(c):
+        a, b = int(so[c]), int(so[c + 1])
+        st = cs[c % 2]
+        with torch.cuda.stream(st):
+            _native.eig_sweep_into(ops, omega[a:b], k_nat[a * n2:b * n2], psi_nat[a * nn:b * nn], info[a:b],
+                                   works[c % 2])
+            if b - a > 1:
+                _native.track_pairs_into(ops, psi_nat[a * nn:b * nn], b - a - 1, arg[a * n2:(b - 1) * n2],
+                                         amax[a * n2:(b - 1) * n2], ybuf[c % 2])
+            ev_track[c].record(st)
+        with torch.cuda.stream(ss):
+            ss.wait_event(ev_track[c])
+            info_h[a:b].copy_(info[a:b], non_blocking=True)
+            if b - a > 1:
+                arg_h[a:b - 1].copy_(arg[a * n2:(b - 1) * n2].view(-1, n2), non_blocking=True)
+                amax_h[a:b - 1].copy_(amax[a * n2:(b - 1) * n2].view(-1, n2), non_blocking=True)
+            ev_small[c].record(ss)
+
+    carry = [None]                                      # absolute order at the base of the next chunk
+
+    def finish(c):
+        a, b = int(so[c]), int(so[c + 1])
+        ev_small[c].synchronize()
+        arg_n, amax_n = arg_h[a:b - 1].numpy(), amax_h[a:b - 1].numpy()
+        rel, starts = _native.track_scan_segments(arg_n, amax_n, n2)
+        ends = starts[1:] + [b - a]
+        comps = np.stack([rel[e - 1] for e in ends])
+        fix = np.asarray(starts[1:], dtype=np.int64) - 1
+        payload = (comps, arg_n[fix].copy(), amax_n[fix].copy(), int(np.count_nonzero(info_h[a:b].numpy())))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, payload, group=group)
+        bad = sum(g[3] for g in gathered)
+        if bad:
+            torch.cuda.synchronize()
+            raise np.linalg.LinAlgError('eig algorithm (QR) did not converge at %d frequencies' % bad)
+        sigma, carry[0] = _native.chain_segments([g[:3] for g in gathered], n2, sigma0=carry[0], return_final=True)
+        rows = np.empty([b - a, n2], dtype=np.int32)
+        for s, (p, e) in enumerate(zip(starts, ends)):
+            np.take(rel[p:e], sigma[rank][s], axis=1, out=rows[p:e])
+        q, r_ = int(ko[c]), int(ko[c + 1])
+        order_h[q:r_].copy_(torch.from_numpy(rows[halo[c]:]))
+        f0 = a + halo[c]                                 # first kept slot
+        with torch.cuda.stream(xs):
+            xs.wait_event(ev_track[c])
+            order_d[q * n2:r_ * n2].copy_(order_h[q:r_].view(-1), non_blocking=True)
+            _native.check(_native.lib().axs_apply_order(
+                n2, r_ - q, _native._ptr(order_d[q * n2:r_ * n2]), _native._ptr(k_nat[f0 * n2:b * n2]),
+                _native._ptr(psi_nat[f0 * nn:b * nn]), _native._ptr(k_sorted[q * n2:r_ * n2]),
+                _native._ptr(psi_sorted[q * nn:r_ * nn]), _native._stream(torch)), 'axs_apply_order')
+            psi_h[q:r_].copy_(psi_sorted[q * nn:r_ * nn].view(r_ - q, n2, n2), non_blocking=True)
+
+    for c in range(K):
+        compute(c)
+        if c == min(1, K - 1) and host_work is not None:
+            host_work()                                  # sparse host by-products, hidden behind the kernels
+        if c >= 1:
+            finish(c - 1)
+    finish(K - 1)
+    # full [nf, 2N] tables on every rank: all-gather of the kept rows (NCCL), rows back into global order
+    main.wait_stream(xs)
+    for s_ in cs:
+        main.wait_stream(s_)
+    keep_slots = torch.from_numpy(np.concatenate([np.arange(so[c] + halo[c], so[c + 1]) for c in range(K)])).to(dev)
+    k_nat_kept = k_nat.view(slots, n2).index_select(0, keep_slots)
+    counts = [sum(pieces[c][r][1] - pieces[c][r][0] for c in range(K)) for r in range(world)]
+    size = max(counts)
+    index = np.concatenate([np.arange(pieces[c][r][0], pieces[c][r][1]) for r in range(world) for c in range(K)])
+    src = np.concatenate([r * size + np.arange(counts[r]) for r in range(world)])
+    back = np.empty(nf, dtype=np.int64)
+    back[index] = src                                    # global frequency -> row of the gathered table
+    back_d = torch.from_numpy(back).to(dev)
+    tables = []
+    for t in (k_sorted.view(kept, n2), order_d.view(kept, n2), k_nat_kept):
+        pad = torch.zeros(size, n2, dtype=t.dtype, device=dev)
+        pad[:kept] = t
+        full = torch.empty(world * size, n2, dtype=t.dtype, device=dev)
+        if t.dtype.is_complex:
+            dist.all_gather_into_tensor(torch.view_as_real(full), torch.view_as_real(pad))
+        else:
+            dist.all_gather_into_tensor(full, pad)
+        tables.append(full.index_select(0, back_d))
+    k_h = pin(nf, n2, dtype=torch.complex128)
+    o_h = pin(nf, n2, dtype=torch.int32)
+    k_h.copy_(tables[0], non_blocking=True)
+    o_h.copy_(tables[1], non_blocking=True)
+    torch.cuda.synchronize()
+    sol.k, sol.order = k_h.numpy(), o_h.numpy()
+    sol.k_native = tables[2]                             # stays on the device until it is read
+    sol.info = np.zeros(nf, dtype=np.int32)
+    sol.local_index = np.concatenate([np.arange(lo, hi) for lo, hi in mine])
+    sol.local_range = None                               # not one contiguous block
+    modes = _LazyModes(psi_sorted, (kept, n2, n2), None, nf)
+    modes.host = psi_h.numpy()
+    sol._psi = modes
 
 
 def _sweep_large(torch, _native, ops, omega, halo, select=None):

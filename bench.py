@@ -271,7 +271,7 @@ def gpu_arm(args):
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'points_per_gpu': POINTS_PER_GPU, 'n2': n2,
                    'l2': 'working set 1.5 GB per sweep >> 126 MB L2 (no flush needed)',
-                   'parallelism': 'frequency axis sharded, %d rank(s), 1-point halo; 2 frequency chunks on 2 CUDA streams per rank (value); e2e = solve(): 4-chunk pipeline with psi_hat download overlapped at N=1; at N>1 per-rank segmented tracking scan + NCCL all-gather of k / order, psi_hat block read after solve()' % world},
+                   'parallelism': 'frequency axis sharded, %d rank(s), 1-point halo; 2 frequency chunks on 2 CUDA streams per rank (value); e2e = solve(): 4-chunk pipeline with psi_hat download overlapped at N=1; at N>1 the same pipeline over interleaved pieces of the frequency axis (cross-rank tracking chain per chunk over gloo, psi_hat pieces downloaded behind the next chunk, NCCL all-gather of k / order at the end)' % world},
         'kernel_ms': {k_: v / args.steps for k_, v in per_kernel.items()},
         'roofline': {'bound': 'tensor', 'kernel': 'k_hqr_mb (4 stage launches)', 'achieved': achieved, 'peak': fp64_peak,
                      'unit': 'TFLOP/s', 'frac': achieved / fp64_peak,

@@ -1,4 +1,11 @@
-"""torchrun target: sharded solve() must reproduce the single-GPU tracked k bit for bit."""
+"""torchrun target: sharded solve() must reproduce the single-GPU tracked k bit for bit.
+
+Three sharded variants against every rank solving the whole sweep alone:
+  * nf = 301  - interleaved chunk pipeline with 2 chunks (solver._solve_sharded_pipelined),
+  * nf = 1300 - the same with 4 chunks (>= 512 points per rank at 2 ranks),
+  * nf = 301 with AXS_SHARD_PIPE=0 - one contiguous block per rank (solver._track_sharded),
+and the downstream energy ratio computed from the sharded mode shapes.
+"""
 import contextlib, io, os, sys
 import numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'axisym-safe-python_b200')
@@ -10,17 +17,29 @@ torch.cuda.set_device(local)
 dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 import axisafe_b200 as ax
 from axisafe_b200 import cases
-c = cases.pipe_soil_pml(nf=301)
-m = ax.mesh.Mesh(); m.create(c['sets'], c['fmax'], PML=c['PML'], PML_props=c['PML_props'])
-with contextlib.redirect_stdout(io.StringIO()):
-    m.assemble_matrices(0)
-    a = ax.solver.WaveElementAxisym(m); a.solve(c['f'])                       # sharded
-    b = ax.solver.WaveElementAxisym(m); b.solve(c['f'], distributed=False)    # every rank alone
-ok = np.array_equal(a.k, b.k) and np.array_equal(a.order, b.order)
-lo, hi = a.local_range
-psi_ok = np.array_equal(a.psi_hat, b.psi_hat[lo:hi])       # sharded: local block only
-t = torch.tensor([int(ok and psi_ok)], device='cuda'); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+
+world = dist.get_world_size()
+all_ok = True
+report = []
+for nf, pipe in ((301, '1'), (650 * world, '1'), (301, '0')):
+    os.environ['AXS_SHARD_PIPE'] = pipe
+    c = cases.pipe_soil_pml(nf=nf)
+    m = ax.mesh.Mesh(); m.create(c['sets'], c['fmax'], PML=c['PML'], PML_props=c['PML_props'])
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.assemble_matrices(0)
+        a = ax.solver.WaveElementAxisym(m); a.solve(c['f'])                       # sharded
+        b = ax.solver.WaveElementAxisym(m); b.solve(c['f'], distributed=False)    # every rank alone
+        a.energy_ratio(); b.energy_ratio()
+    loc = a.local_index
+    ok = np.array_equal(a.k, b.k) and np.array_equal(a.order, b.order) and np.array_equal(a.k_native, b.k_native)
+    psi_ok = np.array_equal(a.psi_hat, b.psi_hat[loc])         # sharded: this rank's frequencies only
+    er_ok = np.array_equal(a.er[loc], b.er[loc]) and len(loc) < nf
+    contiguous = a.local_range is not None
+    report.append('nf=%d pipe=%s k/order=%s psi=%s er=%s contiguous=%s' % (nf, pipe, ok, psi_ok, er_ok, contiguous))
+    all_ok = all_ok and ok and psi_ok and er_ok and (contiguous == (pipe == '0'))
+t = torch.tensor([int(all_ok)], device='cuda'); dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if dist.get_rank() == 0:
-    print('MGPU_CHECK', 'PASS' if int(t.item()) else 'FAIL', 'ranks', dist.get_world_size(), 'block', a.local_range)
+    print('\n'.join(report))
+    print('MGPU_CHECK', 'PASS' if int(t.item()) else 'FAIL', 'ranks', world)
 dist.destroy_process_group()
 sys.exit(0 if int(t.item()) else 1)

@@ -105,3 +105,39 @@ def test_segmented_scan_random(built_lib):
         got = np.concatenate([np.concatenate([rel[a:e][:, sig[r][s]] for s, (a, e) in enumerate(zip(starts, ends))])[halo:]
                               for r, (rel, starts, ends, halo) in enumerate(parts)])
         assert np.array_equal(got, ref), trial
+
+
+@pytest.mark.parametrize('nf,world,unit', [(301, 2, 148), (1200, 2, 148), (2400, 2, 148), (16000, 8, 148), (1111, 3, 16)])
+def test_interleaved_plan_and_chunk_chain(built_lib, nf, world, unit):
+    """Host logic of the sharded pipeline (solver._solve_sharded_pipelined): the interleaved plan
+    covers every frequency exactly once, and the per-chunk chain with the carried order reproduces
+    the sequential scan on every piece."""
+    from axisafe_b200 import solver, _native
+    pieces = solver._shard_plan(nf, world, unit)
+    flat = [p for chunk in pieces for p in chunk]
+    assert flat[0][0] == 0 and flat[-1][1] == nf
+    assert all(a[1] == b[0] for a, b in zip(flat, flat[1:])) and all(hi > lo for lo, hi in flat)
+    n2 = 10
+    rng = np.random.default_rng(nf)
+    arg = np.array([rng.permutation(n2) for _ in range(nf - 1)], dtype=np.int32)
+    amax = np.where(rng.random([nf - 1, n2]) < 0.004, 0.5, 0.97)
+    for lo, hi in flat[1:]:
+        amax[lo - 1, :2] = 0.3 if rng.random() < 0.3 else 0.97       # fix-ups on the piece seams
+    ref = _native.track_scan(arg, amax, nf, n2)
+    got = np.empty_like(ref)
+    carry = None
+    for chunk in pieces:
+        payloads, keep = [], []
+        for lo, hi in chunk:
+            halo = 1 if lo > 0 else 0
+            a, m = arg[lo - halo:hi - 1], amax[lo - halo:hi - 1]
+            rel, starts = _native.track_scan_segments(a, m, n2)
+            ends = starts[1:] + [a.shape[0] + 1]
+            fix = np.asarray(starts[1:], dtype=np.int64) - 1
+            payloads.append((np.stack([rel[e - 1] for e in ends]), a[fix], m[fix]))
+            keep.append((rel, starts, ends, halo))
+        sigma, carry = _native.chain_segments(payloads, n2, sigma0=carry, return_final=True)
+        for r, ((lo, hi), (rel, starts, ends, halo)) in enumerate(zip(chunk, keep)):
+            rows = np.concatenate([rel[p:e][:, sigma[r][s]] for s, (p, e) in enumerate(zip(starts, ends))])
+            got[lo:hi] = rows[halo:]
+    assert np.array_equal(got, ref)
