@@ -481,17 +481,34 @@ def test_subset_solution_vs_reference_eigs(name, n, kw):
         full.solve(c['f'])
     assert sol.k.shape == g['k'].shape == (len(c['f']), mw)
     assert sol.psi_hat.shape == (len(c['f']), 2 * N, mw)
+    bijective = 0
     for i in range(len(c['f'])):
         sigma = sol.w[i] / c0
-        # the kept waves are the m nearest of the full spectrum ...
-        near = np.sort(np.abs(full.k_native[i] - sigma))[:mw]
-        assert np.allclose(np.sort(np.abs(sol.k[i] - sigma)), near, rtol=1e-12, atol=0)
-        # ... and the ones ARPACK returned
-        perm, err = so.match_eigenvalues(g['k'][i], sol.k[i])
-        scale = np.maximum(np.abs(g['k'][i]), abs(sigma))       # shift-invert resolves |k - sigma| relative to sigma
-        assert np.all(np.abs(g['k'][i] - sol.k[i][perm]) <= 1e-8 * scale), (i, err)
-        errs = so.mode_shape_error(g['psi_low'][i], sol.psi_hat[i][N:, perm])
-        assert np.max(errs) <= 1e-6, (i, errs)
+        # the m nearest of the full spectrum are what shift-invert Arnoldi converges to ...
+        near = full.k_native[i][np.argsort(np.abs(full.k_native[i] - sigma), kind='stable')[:mw]]
+        scale = lambda v: np.maximum(np.abs(v), abs(sigma))     # shift-invert resolves |k - sigma| relative to sigma
+        # ... every kept wave is one of them, and so is every wave the reference (ARPACK) returned
+        assert np.all(np.abs(sol.k[i][:, None] - near[None, :]).min(axis=1) == 0)
+        d = np.abs(g['k'][i][:, None] - near[None, :])
+        assert np.all(d.min(axis=1) <= 1e-8 * scale(g['k'][i])), i
+        # The tracking may map two waves of frequency i-1 onto the same column (both |biorth| > 0.9 after
+        # a large frequency step) - the reference does the same (its own k[i] then holds duplicates, e.g.
+        # gravenkamp n=1 from the second point on), and which wave is lost depends on ARPACK's column
+        # order at the first frequency.  Where both rows are duplicate-free they must agree one to one.
+        distinct = lambda v: len(np.unique(np.round(v / abs(sigma), 9))) == mw
+        if distinct(g['k'][i]) and distinct(sol.k[i]):
+            bijective += 1
+            perm, err = so.match_eigenvalues(g['k'][i], sol.k[i])
+            assert np.all(np.abs(g['k'][i] - sol.k[i][perm]) <= 1e-8 * scale(g['k'][i])), (i, err)
+            errs = so.mode_shape_error(g['psi_low'][i], sol.psi_hat[i][N:, perm])
+            assert np.max(errs) <= 1e-6, (i, errs)
+        else:
+            # mode shapes of the waves present on both sides
+            for col in range(mw):
+                j = int(np.argmin(np.abs(sol.k[i] - g['k'][i][col])))
+                if abs(sol.k[i][j] - g['k'][i][col]) <= 1e-8 * scale(g['k'][i][col]):
+                    assert so.mode_shape_error(g['psi_low'][i][:, [col]], sol.psi_hat[i][N:, [j]])[0] <= 1e-6, (i, col)
+    assert bijective >= 1 and (bijective == len(c['f']) or name == 'gravenkamp')
     # tracked among themselves: consecutive frequencies keep the wave in its column (smooth branches)
     jump = np.abs(np.diff(sol.k, axis=0)) / np.abs(sol.k[1:])
     assert np.median(jump) < 0.5
@@ -501,7 +518,8 @@ def test_subset_solution_vs_reference_eigs(name, n, kw):
             full.energy_ratio()
         assert sol.er.shape == sol.k.shape
         for i in range(len(c['f'])):
-            perm, _ = so.match_eigenvalues(sol.k[i], full.k[i])
+            perm = np.abs(sol.k[i][:, None] - full.k[i][None, :]).argmin(axis=1)
+            assert np.array_equal(sol.k[i], full.k[i][perm])
             assert np.allclose(sol.er[i], full.er[i][perm], rtol=1e-9, atol=1e-12)
     amps = sol.point_excited_waves(0.01, 0.05, np.ones(N))
     assert amps.shape == (len(c['f']), mw, 1)
