@@ -22,8 +22,9 @@ What is restated (reference file:line):
   * eig + B-normalisation        solver.py:136-149   (scipy.linalg.eig == LAPACK zgeev,
                                  the same third-party routine the reference calls)
   * biorthogonal mode tracking   solver.py:151-182
-The only third-party arithmetic is ``scipy.linalg.eig`` (SciPy 1.18.1 / OpenBLAS
-0.3.30 in this image; the reference pins no version).
+  * subset (shift-invert) mode   solver.py:137-140   (scipy.sparse.linalg.eigs == ARPACK znaupd)
+The only third-party arithmetic is ``scipy.linalg.eig`` / ``scipy.sparse.linalg.eigs``
+(SciPy 1.18.1 / OpenBLAS 0.3.30 / ARPACK in this image; the reference pins no version).
 """
 import numpy as np
 import scipy.linalg as la
@@ -421,6 +422,29 @@ def solve(G, n, f):
     psi = np.zeros([len(w), 2 * op['N'], 2 * op['N']], complex)
     for i, wi in enumerate(w):
         val, vec = eig_normalised(op, wi)
+        if i == 0:
+            k[i], psi[i] = val, vec
+        else:
+            k[i], psi[i], _ = track(psi[i - 1], op['B'], val, vec)
+    return k, psi
+
+
+def solve_subset(G, n, f, no_of_waves, central_wavespeed):
+    """The reference's shift-invert mode (solver.py:137-140 inside the loop of :119-182):
+    ``scipy.sparse.linalg.eigs(S, k=m, sigma=w/c, which='LM')`` (ARPACK, the same third-party
+    routine, started from a fixed vector here), B-normalised and tracked among the m columns.
+    Returns k [nf, m], psi_hat [nf, 2N, m]."""
+    import scipy.sparse as sps
+    import scipy.sparse.linalg as spla
+    op = operators(G, n)
+    w = 2 * np.pi * np.asarray(f, float)
+    m = int(no_of_waves)
+    k = np.zeros([len(w), m], complex)
+    psi = np.zeros([len(w), 2 * op['N'], m], complex)
+    v0 = np.ones(2 * op['N'], complex)
+    for i, wi in enumerate(w):
+        val, vec = spla.eigs(sps.csc_matrix(S_matrix(op, wi)), k=m, sigma=wi / central_wavespeed, which='LM', v0=v0)
+        vec = vec / np.diag(vec.T @ op['B'] @ vec) ** 0.5
         if i == 0:
             k[i], psi[i] = val, vec
         else:

@@ -108,3 +108,37 @@ def test_oracle_energy_velocity_vs_reference(name, n, kw):
     assert e_k.shape == g['e_k'].shape
     for mine, ref in ((e_k, g['e_k']), (e_p, g['e_p']), (p, g['p'])):
         assert envel_by_eigenvalue(g['k'], ref, k, mine) < 1e-5
+
+
+SUBSET = [('free_steel_pipe', 0, {'nf': 24}), ('pipe_soil_pml', 0, {'nf': 16}), ('gravenkamp', 1, {'nf': 16})]
+
+
+@pytest.mark.parametrize('name,n,kw', SUBSET, ids=['%s-n%d' % (c[0], c[1]) for c in SUBSET])
+def test_oracle_subset_mode_vs_reference(name, n, kw):
+    """no_of_waves = m (solver.py:137-140): the oracle's ARPACK run returns the same set of
+    wavenumbers per frequency as the reference's (tests/golden/subset_*.npz) wherever the tracked
+    row is duplicate-free, and never a wavenumber outside the m nearest to sigma."""
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, 'subset_%s_n%d.npz' % (name, n)))
+    c = make_case(name, n, kw)
+    m, c0 = int(g['m']), float(g['c0'])
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), n)
+    k, psi = so.solve_subset(G, n, c['f'], m, c0)
+    assert k.shape == g['k'].shape and psi.shape[2] == m
+    op = so.operators(G, n)
+    checked = 0
+    for i, f in enumerate(c['f']):
+        w = 2 * np.pi * f
+        sigma = w / c0
+        full = np.linalg.eigvals(so.S_matrix(op, w))
+        near = full[np.argsort(abs(full - sigma))[:m]]
+        tol = 1e-8 * np.maximum(abs(near), abs(sigma)).max()
+        for row in (k[i], g['k'][i]):
+            assert np.all(abs(row[:, None] - near[None, :]).min(axis=1) <= tol), (i, name)
+        distinct = lambda v: len(np.unique(np.round(v / abs(sigma), 9))) == m
+        if distinct(k[i]) and distinct(g['k'][i]):
+            perm, _ = so.match_eigenvalues(g['k'][i], k[i])
+            assert np.all(abs(g['k'][i] - k[i][perm]) <= tol)
+            checked += 1
+    assert checked >= 1
