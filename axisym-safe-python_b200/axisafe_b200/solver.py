@@ -642,28 +642,39 @@ def _host_group(dist):
     """CPU (gloo) process group for the small per-chunk object exchange of the sharded pipeline:
     it must not queue behind (or wait for) the compute streams like an NCCL collective would."""
     if 'g' not in _GLOO:
-        _GLOO['g'] = dist.new_group(backend='gloo')
+        try:
+            _GLOO['g'] = dist.new_group(backend='gloo')
+        except Exception:                                # no usable CPU transport on this host (the same
+            _GLOO['g'] = None                            # on every rank of the node): default NCCL group
     return _GLOO['g']
 
 
-def _shard_plan(nf, world, unit, K=None):
+def _shard_plan(nf, world, unit, K=None, first=None):
     """Interleaved sharding of the frequency axis: the axis is cut into K global chunks and every
     chunk into ``world`` contiguous pieces, so that all ranks finish chunk c together and its tracked
     column order can be fixed (and its mode shapes downloaded) while chunk c+1 computes.
-    Returns pieces[c][r] = (lo, hi).  Chunk sizes follow the single-GPU pipeline (44/44/7/5 % in
-    whole waves of ``unit`` matrices per rank when the sweep is long enough)."""
+    Returns pieces[c][r] = (lo, hi).
+
+    K = 4: chunks run pairwise on two streams; ``first`` = share of the first pair.  The download of
+    the first pair has to fit behind the compute of the second one: x * r <= 1 - x with r = D2H time /
+    compute time per point.  Measured: 254 KB per point at ~50 GB/s against 27 us of compute on one or
+    two B200s (r = 0.19, x = 0.89: the 44/44/7/5 % split of the single-GPU pipeline), but only
+    ~19 GB/s per GPU when eight ranks download through one host at the same time (r = 0.5, x = 0.67).
+    The second pair is split 2:1 so that the last download is the small one.  Pieces are whole waves
+    of ``unit`` matrices (one halo frequency included) when the sweep is long enough."""
     per = nf // world
     if K is None:
         K = 4 if per >= 512 else 2
+    if first is None:
+        first = float(os.environ.get('AXS_SHARD_FIRST', 0.888 if world <= 2 else (0.77 if world <= 4 else 0.67)))
     if K == 4:
-        b1 = max(unit, int(round(0.444 * per / unit)) * unit)
-        b3 = 2 * b1 + max(unit, int(round(0.074 * per / unit)) * unit)
-        if per >= 8 * unit and b3 * world < nf:
-            # every piece carries one halo frequency: b1 - 1 kept points + halo = whole waves
-            p01, p2 = b1 - 1, b3 - 2 * b1 - 1
-            gb = [0, p01 * world, 2 * p01 * world, (2 * p01 + p2) * world, nf]
+        b1 = max(unit, int(first / 2 * per / unit + 0.05) * unit)      # rounded down: the download must fit
+        b2 = max(unit, int(round((1 - first) * 2 / 3 * per / unit)) * unit)
+        if per >= 8 * unit and (2 * b1 + b2) * world < nf:
+            # every piece carries one halo frequency: b - 1 kept points + halo = whole waves
+            gb = [0, (b1 - 1) * world, 2 * (b1 - 1) * world, (2 * b1 + b2 - 3) * world, nf]
         else:
-            gb = [0, int(nf * 0.4), int(nf * 0.8), int(nf * 0.9), nf]
+            gb = [0, int(nf * first / 2), int(nf * first), int(nf * (first + (1 - first) * 2 / 3)), nf]
     else:
         gb = [nf * c // K for c in range(K + 1)]
     pieces = []
