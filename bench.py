@@ -48,10 +48,12 @@ class ClockSampler(object):
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, enabled=True):
+        self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
 
     def __enter__(self):
+        if not self.enabled:                 # N > 1: rank 0 samples its GPU; the other ranks keep their host quiet
+            return self
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '100'],
@@ -212,7 +214,7 @@ def gpu_arm(args):
         product_step()
         device_step(False)
     barrier()
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, enabled=(rank == 0)) as clocks:
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(args.steps):
