@@ -104,7 +104,7 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_baseline(points_per_core=100):
+def cpu_baseline(points_per_core=100, as_shipped=False):
     """Oracle (port of the reference algorithm: S build + zgeev + normalisation + tracking) on
     all host cores: P single-threaded worker processes, contiguous frequency chunks
     ('tuned' variant - zgeev does not scale with BLAS threads at 2N=126)."""
@@ -121,9 +121,37 @@ def cpu_baseline(points_per_core=100):
         pool.map(_cpu_worker, chunks)
         wall = time.perf_counter() - t0
     npts = cores * points_per_core
-    return {'value': npts / wall, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+    shipped = as_shipped_baseline() if as_shipped else None
+    return {'as_shipped': shipped, 'value': npts / wall, 'unit': UNIT, 'cores': cores, 'kind': 'port',
             'sample': '%d of the 2000 sweep frequencies (%d per core, contiguous chunks, tracked within '
                       'a chunk), %d single-threaded processes, %.1f s wall' % (npts, points_per_core, cores, wall)}
+
+
+_AS_SHIPPED = """
+import sys, time
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from oracle import safe_oracle as so
+from axisafe_b200 import cases
+c = cases.pipe_soil_pml(nf=%d)
+G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), c['n'])
+so.solve(G, c['n'], c['f'][:2])
+t0 = time.perf_counter(); so.solve(G, c['n'], c['f'][:%d]); print(time.perf_counter() - t0)
+"""
+
+
+def as_shipped_baseline(points=40):
+    """the reference loop the way its examples run it - ONE process, the BLAS
+    library's default thread count (which at 2N = 126 is slower than one thread: oversubscription)."""
+    env = {k: v for k, v in os.environ.items() if k not in ('OPENBLAS_NUM_THREADS', 'OMP_NUM_THREADS', 'MKL_NUM_THREADS')}
+    try:
+        out = subprocess.run([sys.executable, '-c', _AS_SHIPPED % (ROOT, os.path.join(ROOT, 'axisym-safe-python_b200'),
+                                                                   POINTS_PER_GPU, points)],
+                             env=env, capture_output=True, text=True, timeout=300)
+        wall = float(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:                                            # pragma: no cover
+        return {'value': None, 'note': 'as-shipped run failed: %s' % exc}
+    return {'value': points / wall, 'unit': UNIT, 'processes': 1, 'blas_threads': 'library default',
+            'sample': 'first %d sweep frequencies, %.1f s wall' % (points, wall)}
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -298,7 +326,7 @@ def gpu_arm(args):
         'clocks': clocks.summary(),
         'hbm_peak_gbs': peaks.get('hbm_gbs'),
     }
-    out['cpu_baseline'] = cpu_baseline() if world == 1 and not args.no_cpu else None
+    out['cpu_baseline'] = cpu_baseline(as_shipped=True) if world == 1 and not args.no_cpu else None
     if saved_stdout is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
