@@ -107,7 +107,7 @@ def test_segmented_scan_random(built_lib):
         assert np.array_equal(got, ref), trial
 
 
-@pytest.mark.parametrize('nf,world,unit', [(301, 2, 148), (1200, 2, 148), (2400, 2, 148), (16000, 8, 148), (1111, 3, 16)])
+@pytest.mark.parametrize('nf,world,unit', [(301, 2, 148), (1200, 2, 148), (4000, 2, 148), (8000, 4, 148), (16000, 8, 148), (1111, 3, 16), (2051, 4, 132)])
 def test_interleaved_plan_and_chunk_chain(built_lib, nf, world, unit):
     """Host logic of the sharded pipeline (solver._solve_sharded_pipelined): the interleaved plan
     covers every frequency exactly once, and the per-chunk chain with the carried order reproduces
