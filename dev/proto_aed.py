@@ -9,7 +9,7 @@ trailing nw x nw window is Schur-decomposed before a batch, the spike is tested 
 converged eigenvalues are deflated (undeflatable ones are moved up, ztrexc), the rest is returned to
 Hessenberg form, and the undeflated window eigenvalues are the next shifts.
 
-Counts per matrix: batches, macro steps (split by the window size = kernel stage), AED calls.
+Counts per matrix: batches, macro steps (split by the top index u = kernel stage), AED calls.
 Not imported by the product or the tests.   usage: python dev/proto_aed.py [nw ...]
 """
 import os
@@ -76,11 +76,14 @@ def sweep(H, l, u, sig):
 
 
 def shifts_2x2(H, l, u, nb):
-    """Eigenvalues of the trailing 2 x 2 diagonal blocks (what k_hqr_mb takes)."""
+    """Eigenvalues of the trailing 2 x 2 diagonal blocks, per block the one nearer to its lower
+    diagonal entry first (what k_hqr_mb takes, eig_small.cu 'shifts')."""
     out = []
     k = u
     while len(out) < nb and k - 1 >= l:
-        out.extend(np.linalg.eigvals(H[k - 1:k + 1, k - 1:k + 1]))
+        e = list(np.linalg.eigvals(H[k - 1:k + 1, k - 1:k + 1]))
+        e.sort(key=lambda z: cabs1(z - H[k, k]))
+        out.extend(e)
         k -= 2
     if len(out) < nb and k >= l:
         out.append(H[k, k])
@@ -187,11 +190,6 @@ def run(H, nw=0, nb=NB, stages=(117, 95, 82)):
             u -= 1
             stall = 0
             continue
-        if l == u - 1:
-            eig.extend(np.linalg.eigvals(H[l:u + 1, l:u + 1]))
-            u -= 2
-            stall = 0
-            continue
         shifts = None
         if nw:
             st['aed'] += 1
@@ -201,13 +199,14 @@ def run(H, nw=0, nb=NB, stages=(117, 95, 82)):
             if u2 < u:
                 u = u2
                 stall = 0
-                if u < l + 2 or len(defl) * 100 >= 14 * min(nw, u - l + 1 + len(defl)):   # nibble: AED again
+                if u < l + 1 or len(defl) * 100 >= 14 * min(nw, u - l + 1 + len(defl)):   # nibble: AED again
                     continue
         w = u - l + 1
-        if not shifts or len(shifts) < 2:
-            shifts = shifts_2x2(H, l, u, nb)
+        nbw = min(nb, (w - 2) // 3 + 1)                  # the kernel's bulge count for this window
+        if not shifts:
+            shifts = shifts_2x2(H, l, u, nbw)
         else:
-            shifts = sorted(shifts, key=lambda z: abs(z - H[u, u]))[:nb]
+            shifts = sorted(shifts, key=lambda z: abs(z - H[u, u]))[:nbw]
         stall += 1
         if stall % 10 == 0:
             shifts = [0.75 * abs(H[u, u - 1].real) + H[u, u]] * len(shifts)
@@ -219,7 +218,7 @@ def run(H, nw=0, nb=NB, stages=(117, 95, 82)):
         steps = (w - 1) + 3 * (len(shifts) - 1)
         st['batches'] += 1
         st['macro'] += steps
-        st['by_stage'][sum(w <= s for s in stages)] += steps
+        st['by_stage'][sum(u < s for s in stages)] += steps      # the kernel's stages end at u < m_stop
     return np.array(eig), st
 
 
@@ -236,7 +235,7 @@ def main():
         S = so.S_matrix(op, 2 * np.pi * c['f'][i])
         Sb, d, _ = balance(S)
         mats.append((hessenberg(Sb), np.linalg.eigvals(S)))
-    print('cfg1, 2N = %d, %d matrices; stages by window: >117 | 96-117 | 83-95 | <=82' % (mats[0][0].shape[0], len(mats)))
+    print('cfg1, 2N = %d, %d matrices; stages by top index u: >=117 | 95-116 | 82-94 | <82' % (mats[0][0].shape[0], len(mats)))
     for nw in nws:
         tot = dict(batches=0, macro=0, aed=0, aed_defl=0, by_stage=[0, 0, 0, 0], fail=0)
         worst = 0.0
