@@ -794,13 +794,20 @@ def _solve_sharded_pipelined(sol, torch, _native, ops, nf, n2, rank, world, host
                 _native._ptr(psi_sorted[q * nn:r_ * nn]), _native._stream(torch)), 'axs_apply_order')
             psi_h[q:r_].copy_(psi_sorted[q * nn:r_ * nn].view(r_ - q, n2, n2), non_blocking=True)
 
+    import time
+    trace = os.environ.get('AXS_PIPE_TRACE')
+    tl = [('start', time.perf_counter())]
     for c in range(K):
         compute(c)
+        tl.append(('enq%d' % c, time.perf_counter()))
         if c == min(1, K - 1) and host_work is not None:
             host_work()                                  # sparse host by-products, hidden behind the kernels
+            tl.append(('host', time.perf_counter()))
         if c >= 1:
             finish(c - 1)
+            tl.append(('fin%d' % (c - 1), time.perf_counter()))
     finish(K - 1)
+    tl.append(('fin%d' % (K - 1), time.perf_counter()))
     # full [nf, 2N] tables on every rank: all-gather of the kept rows (NCCL), rows back into global order
     main.wait_stream(xs)
     for s_ in cs:
@@ -828,7 +835,12 @@ def _solve_sharded_pipelined(sol, torch, _native, ops, nf, n2, rank, world, host
     o_h = pin(nf, n2, dtype=torch.int32)
     k_h.copy_(tables[0], non_blocking=True)
     o_h.copy_(tables[1], non_blocking=True)
+    tl.append(('gather', time.perf_counter()))
     torch.cuda.synchronize()
+    tl.append(('sync', time.perf_counter()))
+    if trace:                                            # host timeline of this rank (ms since entry)
+        print('AXS_PIPE rank %d host ms: %s' % (rank, ' '.join('%s=%.1f' % (n_, (t_ - tl[0][1]) * 1e3) for n_, t_ in tl)),
+              file=__import__('sys').stderr)
     sol.k, sol.order = k_h.numpy(), o_h.numpy()
     sol.k_native = tables[2]                             # stays on the device until it is read
     sol.info = np.zeros(nf, dtype=np.int32)
