@@ -119,12 +119,17 @@ class WaveElementAxisym(object):
         subset is a selection (axs_select_modes), not an Arnoldi iteration.
         ``distributed``: 'auto' shards the frequency axis over the ranks of an initialised
         ``torch.distributed`` process group; False forces a single-GPU sweep.
+        Non-finite frequencies raise ``ValueError`` (SciPy's ``check_finite``), QR non-convergence raises
+        ``numpy.linalg.LinAlgError`` - the two errors the reference's ``la.eig`` call can raise.
         ``pipeline``: single-GPU sweeps of >= 128 points run as a 4-chunk pipeline that copies the
         tracked ``psi_hat`` to (pinned) host memory while the next chunk computes; False keeps the
         mode shapes on the device until ``psi_hat`` is read.
         """
         from . import _native
         print('Calculating dispersion curves...')
+        if not np.isfinite(np.asarray(f, dtype=float)).all():
+            # what scipy.linalg.eig(check_finite=True) raises on the reference's S(w), solver.py:136
+            raise ValueError('array must not contain infs or NaNs')
         subset = None
         if not (isinstance(no_of_waves, str) and no_of_waves == 'full'):
             # the reference's shift-invert mode (solver.py:137-140): the no_of_waves eigenvalues nearest

@@ -203,3 +203,15 @@ def test_subset_scan_matches_reference_semantics(built_lib):
         cols[i] = sel[i][new_order]
     assert fixups > 3
     assert np.array_equal(got, cols)
+
+
+def test_solve_rejects_non_finite_frequencies():
+    """Reference error behaviour: scipy.linalg.eig(check_finite=True) -> ValueError."""
+    import contextlib
+    import io
+    import axisafe_b200 as ax
+    sol = ax.solver.WaveElementAxisym(ax.mesh.Mesh())
+    with contextlib.redirect_stdout(io.StringIO()):
+        for bad in ([1e3, np.nan], [np.inf]):
+            with pytest.raises(ValueError, match='infs or NaNs'):
+                sol.solve(np.array(bad))
