@@ -141,3 +141,22 @@ def test_interleaved_plan_and_chunk_chain(built_lib, nf, world, unit):
             rows = np.concatenate([rel[p:e][:, sigma[r][s]] for s, (p, e) in enumerate(zip(starts, ends))])
             got[lo:hi] = rows[halo:]
     assert np.array_equal(got, ref)
+
+
+def test_shard_plan_properties():
+    """Every plan solve() can ask for (>= 128 points per rank) tiles the axis with non-empty pieces."""
+    from hypothesis import given, settings, strategies as st
+    from axisafe_b200 import solver
+
+    @settings(max_examples=300, deadline=None)
+    @given(world=st.integers(2, 8), per=st.integers(128, 5000), extra=st.integers(0, 7),
+           unit=st.sampled_from([108, 132, 148]), first=st.sampled_from([None, 0.5, 0.67, 0.77, 0.888, 0.95]))
+    def check(world, per, extra, unit, first):
+        nf = per * world + extra % world
+        pieces = solver._shard_plan(nf, world, unit, first=first)
+        flat = [p for chunk in pieces for p in chunk]
+        assert len(pieces) in (2, 4) and all(len(chunk) == world for chunk in pieces)
+        assert flat[0][0] == 0 and flat[-1][1] == nf
+        assert all(a[1] == b[0] for a, b in zip(flat, flat[1:]))
+        assert all(hi > lo for lo, hi in flat)
+    check()
