@@ -174,7 +174,7 @@ def aed(H, l, u, nw):
     return kw + ns - 1, shifts, deflated
 
 
-def run(H, nw=0, nb=NB, stages=(117, 95, 82)):
+def run(H, nw=0, nb=NB, stages=(117, 95, 82), aed_above=0):
     H = H.copy()
     n = H.shape[0]
     eig = []
@@ -191,7 +191,7 @@ def run(H, nw=0, nb=NB, stages=(117, 95, 82)):
             stall = 0
             continue
         shifts = None
-        if nw:
+        if nw and u >= aed_above:                        # aed_above = 117: AED in the one-CTA-per-SM stage only
             st['aed'] += 1
             u2, shifts, defl = aed(H, l, u, nw)
             eig.extend(defl)
