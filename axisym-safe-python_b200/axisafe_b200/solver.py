@@ -744,7 +744,9 @@ def _solve_sharded_pipelined(sol, torch, _native, ops, nf, n2, rank, world, host
     order_h = pin(kept, n2, dtype=torch.int32)
     psi_h = pin(kept, n2, n2, dtype=torch.complex128)
     ev_track = [torch.cuda.Event() for _ in range(K)]
-    ev_small = [torch.cuda.Event() for _ in range(K)]
+    # AXS_EVENT_BLOCKING=1 (A/B): the host sleeps on the small-table events instead of spinning, which
+    # frees a core per rank for the NCCL / gloo service threads when eight ranks share 16 cores
+    ev_small = [torch.cuda.Event(blocking=os.environ.get('AXS_EVENT_BLOCKING', '0') == '1') for _ in range(K)]
     for s_ in cs + [xs, ss]:
         s_.wait_stream(main)
 
