@@ -34,6 +34,9 @@ _SIGNATURES = {
     'axs_modes': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 2 + [ctypes.c_int] +
                   [ctypes.c_void_p] * 3 + [ctypes.c_longlong, ctypes.c_void_p]),
     'axs_get_reduction': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 4),
+    'axs_hqr_stats': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 3),
+    'axs_set_tuning': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
+    'axs_get_tuning': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_void_p]),
     'axs_track_worksize': (ctypes.c_longlong, [ctypes.c_int, ctypes.c_int]),
     'axs_track_pairs': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 3 + [ctypes.c_int] +
                         [ctypes.c_void_p] * 3 + [ctypes.c_longlong, ctypes.c_void_p]),
@@ -321,6 +324,22 @@ def modes(ops, nf, k, work):
     check(lib().axs_modes(ops.N, ops.hb, _ptr(ops.Cb), _ptr(ops.K6d), nf, _ptr(k), _ptr(psi),
                           _ptr(work.buf), work.bytes, _stream(torch)), 'axs_modes')
     return psi
+
+
+def set_tuning(name, value):
+    """axs_set_tuning: kernel-selection switch (see include/axisafe_b200.h); returns the old value."""
+    old = ctypes.c_int(0)
+    check(lib().axs_get_tuning(name.encode(), ctypes.addressof(old)), 'axs_get_tuning(%s)' % name)
+    check(lib().axs_set_tuning(name.encode(), int(value)), 'axs_set_tuning(%s)' % name)
+    return old.value
+
+
+def hqr_stats(N, nf, work):
+    """axs_hqr_stats: host array [nf, 4] = macro steps, batches, AED calls, AED deflations per matrix."""
+    torch = torch_cuda()
+    st = torch.zeros(nf * 4, dtype=torch.int32, device='cuda')
+    check(lib().axs_hqr_stats(N, nf, _ptr(work.buf), _ptr(st), _stream(torch)), 'axs_hqr_stats')
+    return st.cpu().numpy().reshape(nf, 4)
 
 
 def get_reduction(N, nf, work):

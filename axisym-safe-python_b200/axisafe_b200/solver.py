@@ -22,6 +22,7 @@ eigenvalue / arg-max tables are all-gathered (NCCL).  No CPU fallback.
 from __future__ import print_function
 
 import os
+import warnings
 
 import numpy as np
 import scipy.sparse as sps
@@ -69,6 +70,7 @@ class WaveElementAxisym(object):
         self.local_range = None          # (first, last+1) frequencies solved by this rank (contiguous block)
         self.local_index = None          # global indices of the frequencies whose mode shapes this rank holds
         self._ncols = None               # subset mode: number of kept waves (device arrays stay 2N wide)
+        self._sharded = False            # the last solve() was sharded over torch.distributed ranks
         self.timings = {}
 
     # psi_hat lives on the GPU until somebody reads it ------------------------------------
@@ -166,6 +168,12 @@ class WaveElementAxisym(object):
             import torch.distributed as dist
             if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
                 rank, world = dist.get_rank(), dist.get_world_size()
+            if nf < 2 * world:
+                # too few points to shard (a rank with an empty block would leave the others waiting in
+                # a collective): decided from nf and the world size alone, so identically on every rank -
+                # every rank solves the whole sweep
+                rank, world = 0, 1
+        self._sharded = world > 1
         bounds = [(nf * r) // world for r in range(world + 1)]
         lo, hi = bounds[rank], bounds[rank + 1]
         halo = 1 if lo > 0 else 0
@@ -232,6 +240,9 @@ class WaveElementAxisym(object):
         if psi_nat is None:
             # the mode shapes of the whole block do not fit in HBM (the reference's psi_hat would be
             # nf x 2N x 2N x 16 B of host memory): eigenvalues and tracking are complete, shapes are not kept
+            warnings.warn('solve(): the mode shapes of %d frequencies x 2N = %d (%.1f GB) do not fit into the free '
+                          'device memory; k is complete, psi_hat is None - solve fewer frequencies per call '
+                          'to keep the shapes' % (hi - lo, n2, (hi - lo) * n2 * n2 * 16 / 1e9), RuntimeWarning)
             self._psi = None
         elif not small:
             self._psi = _LazyModes(_reorder_in_place(torch, _native, n2, order_loc, psi_nat, halo),
@@ -283,11 +294,9 @@ class WaveElementAxisym(object):
                                       triplets(M_tot), triplets(M_pml))
         if self._ncols is not None:
             er_loc = er_loc[:, :self._ncols]                  # the padding columns are not modes
-        if len(loc) == len(self.w):
-            self.er = er_loc
-        else:
-            self.er = np.full([len(self.w), er_loc.shape[1]], np.nan)   # other ranks' frequencies
-            self.er[loc] = er_loc
+        # sharded sweep: the [nf, 2N] table is completed from the other ranks (it is as small as k), so
+        # that k_propagating() / energy_velocity() see the same er on every rank as a single-GPU sweep
+        self.er = _complete_rows(self, er_loc)
 
     def k_propagating(self, imag_threshold=10, ER_threshold=0.9):
         """Positive-going propagating solutions (ref solver.py:271-299); host, O(nf * 2N)."""
@@ -349,6 +358,9 @@ class WaveElementAxisym(object):
         if only_propagating:
             if self.propagating_indices is None or len(self.propagating_indices) == 0:
                 self.k_propagating()
+            if self.propagating_indices is None:
+                raise RuntimeError('energy_velocity(only_propagating=True) needs energy_ratio() and '
+                                   'k_propagating() first')
             sel = np.asarray(self.propagating_indices, dtype=np.int32)
         else:
             sel = None if self._ncols is None else np.arange(self._ncols, dtype=np.int32)
@@ -366,13 +378,8 @@ class WaveElementAxisym(object):
                       k * n * fKFtT + k.conj() * n * fKFt + k * k.conj() * fK6)
         p = -w / 2 * np.imag(fKF - 1j * n * fKFt - 1j * k * fK6)
 
-        def full(a):
-            if len(loc) == len(self.w):
-                return a
-            out = np.full([len(self.w), a.shape[1]], np.nan, dtype=a.dtype)   # other ranks' frequencies
-            out[loc] = a
-            return out
-        self.e_k, self.e_p, self.p = full(e_k), full(e_p), full(p)
+        # sharded sweep: completed from the other ranks, like er
+        self.e_k, self.e_p, self.p = (_complete_rows(self, a) for a in (e_k, e_p, p))
         with np.errstate(divide='ignore', invalid='ignore'):
             self.en_vel = self.p / (self.e_k + self.e_p)
 
@@ -395,21 +402,74 @@ class WaveElementAxisym(object):
             proj = _native.modal_projection(N, len(loc), self.psi_hat_device.reshape(-1), force_vector)
             if self._ncols is not None:
                 proj = proj[:, :self._ncols]
-            if len(loc) != len(self.w):
-                full = np.full([len(self.w), proj.shape[1]], np.nan + 0j)      # other ranks' frequencies
-                full[loc] = proj
-                proj = full
+            proj = _complete_rows(self, proj)                # sharded sweep: the other ranks' frequencies
             return (1j * np.sinc(self.Mesh.n * theta_0 / np.pi) / (2 * np.pi * r_f) * proj)[:, :, np.newaxis]
 
     def calculate_frf(self, theta_0, r_f, f_ext, distance=0):
         """Modal contributions to the point-force FRF at ``distance`` (ref solver.py:437-474)."""
         idx = self.propagating_indices
-        amps = self.point_excited_waves(theta_0, r_f, f_ext)[:, idx, 0] * np.exp(-1j * self.k[:, idx] * distance)
+        with np.errstate(over='ignore', invalid='ignore'):       # growing (non-propagating) columns overflow
+            amps = self.point_excited_waves(theta_0, r_f, f_ext)[:, idx, 0] * np.exp(-1j * self.k[:, idx] * distance)
+        # a sharded sweep holds the mode shapes of local_index only: the product is formed for those
+        # frequencies and the [nf, N, modes] result completed from the other ranks
+        loc = self.local_index if self.local_index is not None else np.arange(len(self.w))
         shapes = self.psi_hat[:, self.Mesh.no_of_dofs:, idx]
-        return shapes * amps[:, np.newaxis, :]
+        return _complete_rows(self, shapes * amps[loc][:, np.newaxis, :])
+
+
+def _complete_rows(sol, rows):
+    """[len(local_index), ...] rows of this rank -> the full [nf, ...] host array on every rank.
+
+    Single-GPU sweeps return ``rows`` unchanged.  After a sharded sweep every rank holds the mode
+    shapes of ``local_index`` only, so per-mode results derived from them (energy ratio, energy
+    velocity, modal amplitudes) are exchanged: one all-gather of the padded blocks + their global
+    frequency indices over the default process group (device tensors for NCCL, host tensors for
+    gloo).  Collective: every rank of the sweep must make the same call.
+    """
+    nf = len(sol.w)
+    loc = sol.local_index
+    if not sol._sharded or loc is None or len(loc) == nf:
+        return rows
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    dev = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+    rows = np.ascontiguousarray(rows)
+    tail, dtype = rows.shape[1:], rows.dtype
+    flat = rows.reshape(len(loc), -1)
+    as_real = np.ascontiguousarray(flat).view(np.float64) if np.iscomplexobj(flat) else flat.astype(np.float64, copy=False)
+    width = as_real.shape[1]
+    cnt = torch.tensor([len(loc)], dtype=torch.int64, device=dev)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    cnts = [int(c.item()) for c in cnts]
+    size = max(cnts)
+    pad = torch.zeros(size, width + 1, dtype=torch.float64, device=dev)
+    if len(loc):
+        pad[:len(loc), :width] = torch.from_numpy(as_real).to(dev)
+        pad[:len(loc), width] = torch.from_numpy(np.asarray(loc, dtype=np.float64)).to(dev)   # exact below 2^53
+    full = torch.empty(world * size, width + 1, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(full, pad)
+    full = full.cpu().numpy()
+    out = np.full([nf, width], np.nan)
+    for r in range(world):
+        blk = full[r * size:r * size + cnts[r]]
+        out[blk[:, width].astype(np.int64)] = blk[:, :width]
+    if np.issubdtype(dtype, np.complexfloating):
+        out = out.view(np.complex128)
+    return out.reshape((nf,) + tail).astype(dtype, copy=False)
 
 
 _PIPE = {}
+
+
+def _pipe_streams(torch):
+    """Side streams of the chunk pipelines, one set per device (a process may drive several GPUs)."""
+    dev = torch.cuda.current_device()
+    if dev not in _PIPE:
+        _PIPE[dev] = dict(cs=[torch.cuda.Stream(), torch.cuda.Stream()], xs=torch.cuda.Stream(), ss=torch.cuda.Stream())
+    d = _PIPE[dev]
+    return d['cs'], d['xs'], d['ss']
 
 
 def _solve_pipelined(sol, torch, _native, ops, nf, n2, host_work=None):
@@ -447,11 +507,7 @@ def _solve_pipelined(sol, torch, _native, ops, nf, n2, host_work=None):
     else:
         bounds = [nf * c // K for c in range(K + 1)]
     nn = n2 * n2
-    if not _PIPE:
-        _PIPE['cs'] = [torch.cuda.Stream(), torch.cuda.Stream()]
-        _PIPE['xs'] = torch.cuda.Stream()
-        _PIPE['ss'] = torch.cuda.Stream()
-    cs, xs, ss = _PIPE['cs'], _PIPE['xs'], _PIPE['ss']
+    cs, xs, ss = _pipe_streams(torch)
     main = torch.cuda.current_stream()
     cmax = max(bounds[c + 1] - bounds[c] for c in range(K))
     dev = 'cuda'
@@ -648,9 +704,21 @@ def _host_group(dist):
     it must not queue behind (or wait for) the compute streams like an NCCL collective would."""
     if 'g' not in _GLOO:
         try:
-            _GLOO['g'] = dist.new_group(backend='gloo')
-        except Exception:                                # no usable CPU transport on this host (the same
-            _GLOO['g'] = None                            # on every rank of the node): default NCCL group
+            group = dist.new_group(backend='gloo')
+        except Exception:                                # no usable CPU transport on this host
+            group = None
+        # the ranks must agree: if gloo failed anywhere, everybody takes the default (NCCL) group
+        import torch
+        dev = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+        flag = torch.tensor([1 if group is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if group is not None:
+                warnings.warn('axisafe_b200: no gloo group on some rank; the per-chunk exchange of the sharded '
+                              'pipeline uses the NCCL group (it then queues behind the compute streams)',
+                              RuntimeWarning)
+            group = None
+        _GLOO['g'] = group
     return _GLOO['g']
 
 
@@ -716,11 +784,7 @@ def _solve_sharded_pipelined(sol, torch, _native, ops, nf, n2, rank, world, host
     ko = [0] + list(np.cumsum(cnt))                                 # offsets of the kept rows
     slots, kept = int(so[-1]), int(ko[-1])
     nn = n2 * n2
-    if not _PIPE:
-        _PIPE['cs'] = [torch.cuda.Stream(), torch.cuda.Stream()]
-        _PIPE['xs'] = torch.cuda.Stream()
-        _PIPE['ss'] = torch.cuda.Stream()
-    cs, xs, ss = _PIPE['cs'], _PIPE['xs'], _PIPE['ss']
+    cs, xs, ss = _pipe_streams(torch)
     main = torch.cuda.current_stream()
     dev = 'cuda'
     w_loc = np.concatenate([sol.w[lo - h:hi] for h, (lo, hi) in zip(halo, mine)])
@@ -744,9 +808,15 @@ def _solve_sharded_pipelined(sol, torch, _native, ops, nf, n2, rank, world, host
     order_h = pin(kept, n2, dtype=torch.int32)
     psi_h = pin(kept, n2, n2, dtype=torch.complex128)
     ev_track = [torch.cuda.Event() for _ in range(K)]
-    # AXS_EVENT_BLOCKING=1 (A/B): the host sleeps on the small-table events instead of spinning, which
-    # frees a core per rank for the NCCL / gloo service threads when eight ranks share 16 cores
-    ev_small = [torch.cuda.Event(blocking=os.environ.get('AXS_EVENT_BLOCKING', '0') == '1') for _ in range(K)]
+    # the host SLEEPS on the small-table events instead of spinning (cudaEventBlockingSync): with one
+    # process per GPU the spinning threads of 8 ranks compete with the NCCL / gloo service threads for the
+    # host cores (AXS_EVENT_BLOCKING=0 restores the spin wait for A/B)
+    ev_small = [torch.cuda.Event(blocking=os.environ.get('AXS_EVENT_BLOCKING', '1') == '1') for _ in range(K)]
+    SMAX = 6                                             # segments per piece carried by the fixed-size exchange
+    xcap = 2 + n2 * (4 * SMAX - 3)
+    xdev = 'cpu' if group is not None else dev
+    xsend = torch.zeros(xcap, dtype=torch.int32, device=xdev)
+    xrecv = torch.zeros(world * xcap, dtype=torch.int32, device=xdev)
     for s_ in cs + [xs, ss]:
         s_.wait_stream(main)
 
@@ -779,8 +849,7 @@ def _solve_sharded_pipelined(sol, torch, _native, ops, nf, n2, rank, world, host
         comps = np.stack([rel[e - 1] for e in ends])
         fix = np.asarray(starts[1:], dtype=np.int64) - 1
         payload = (comps, arg_n[fix].copy(), amax_n[fix].copy(), int(np.count_nonzero(info_h[a:b].numpy())))
-        gathered = [None] * world
-        dist.all_gather_object(gathered, payload, group=group)
+        gathered = _exchange_segments(torch, dist, group, payload, n2, SMAX, xsend, xrecv, world)
         bad = sum(g[3] for g in gathered)
         if bad:
             torch.cuda.synchronize()
@@ -828,18 +897,20 @@ def _solve_sharded_pipelined(sol, torch, _native, ops, nf, n2, rank, world, host
     back = np.empty(nf, dtype=np.int64)
     back[index] = src                                    # global frequency -> row of the gathered table
     back_d = torch.from_numpy(back).to(dev)
+    # (the per-frequency counts of unconverged eigenvalues travel as an extra column of the order table)
+    order_info = torch.cat([order_d.view(kept, n2), info.index_select(0, keep_slots).view(kept, 1)], dim=1)
     tables = []
-    for t in (k_sorted.view(kept, n2), order_d.view(kept, n2), k_nat_kept):
-        pad = torch.zeros(size, n2, dtype=t.dtype, device=dev)
+    for t in (k_sorted.view(kept, n2), order_info, k_nat_kept):
+        pad = torch.zeros(size, t.shape[1], dtype=t.dtype, device=dev)
         pad[:kept] = t
-        full = torch.empty(world * size, n2, dtype=t.dtype, device=dev)
+        full = torch.empty(world * size, t.shape[1], dtype=t.dtype, device=dev)
         if t.dtype.is_complex:
             dist.all_gather_into_tensor(torch.view_as_real(full), torch.view_as_real(pad))
         else:
             dist.all_gather_into_tensor(full, pad)
         tables.append(full.index_select(0, back_d))
     k_h = pin(nf, n2, dtype=torch.complex128)
-    o_h = pin(nf, n2, dtype=torch.int32)
+    o_h = pin(nf, n2 + 1, dtype=torch.int32)
     k_h.copy_(tables[0], non_blocking=True)
     o_h.copy_(tables[1], non_blocking=True)
     tl.append(('gather', time.perf_counter()))
@@ -848,14 +919,52 @@ def _solve_sharded_pipelined(sol, torch, _native, ops, nf, n2, rank, world, host
     if trace:                                            # host timeline of this rank (ms since entry)
         print('AXS_PIPE rank %d host ms: %s' % (rank, ' '.join('%s=%.1f' % (n_, (t_ - tl[0][1]) * 1e3) for n_, t_ in tl)),
               file=__import__('sys').stderr)
-    sol.k, sol.order = k_h.numpy(), o_h.numpy()
+    sol.k = k_h.numpy()
+    sol.order = np.ascontiguousarray(o_h.numpy()[:, :n2])
     sol.k_native = tables[2]                             # stays on the device until it is read
-    sol.info = np.zeros(nf, dtype=np.int32)
+    sol.info = o_h.numpy()[:, n2].copy()                 # gathered per-frequency counts (all zero here: a
+                                                         # non-converged chunk has raised LinAlgError above)
     sol.local_index = np.concatenate([np.arange(lo, hi) for lo, hi in mine])
     sol.local_range = None                               # not one contiguous block
     modes = _LazyModes(psi_sorted, (kept, n2, n2), None, nf)
     modes.host = psi_h.numpy()
     sol._psi = modes
+
+
+def _exchange_segments(torch, dist, group, payload, n2, smax, send, recv, world):
+    """All-gather of the per-piece tracking composites of one chunk (see _solve_sharded_pipelined).
+
+    ``payload`` = (comps [S, n2] int32, d_arg [S-1, n2] int32, d_amax [S-1, n2] float64, bad count).
+    One fixed-size int32 tensor per rank ([S, bad | comps | d_arg | d_amax bits], room for ``smax``
+    segments) instead of pickled objects: a single collective without serialisation.  A piece with
+    more than ``smax`` fix-up segments is rare (a segment ends where a tracked mode falls below the 0.9
+    threshold); every rank sees every header, so all of them then repeat the exchange with
+    all_gather_object.  Returns the list of payload tuples of all ranks.
+    """
+    comps, d_arg, d_amax, bad = payload
+    S = comps.shape[0]
+    buf = np.zeros(send.numel(), dtype=np.int32)
+    buf[0], buf[1] = S, bad
+    if S <= smax:
+        o = 2
+        buf[o:o + S * n2] = comps.reshape(-1); o += smax * n2
+        buf[o:o + (S - 1) * n2] = d_arg.reshape(-1); o += (smax - 1) * n2
+        buf[o:o + 2 * (S - 1) * n2] = np.ascontiguousarray(d_amax, dtype=np.float64).reshape(-1).view(np.int32)
+    send.copy_(torch.from_numpy(buf))
+    dist.all_gather_into_tensor(recv, send, group=group)
+    got = recv.cpu().numpy().reshape(world, -1)
+    if (got[:, 0] > smax).any():
+        gathered = [None] * world
+        dist.all_gather_object(gathered, payload, group=group)
+        return gathered
+    out = []
+    for r in range(world):
+        Sr, o = int(got[r, 0]), 2
+        c = got[r, o:o + Sr * n2].reshape(Sr, n2).copy(); o += smax * n2
+        a = got[r, o:o + (Sr - 1) * n2].reshape(Sr - 1, n2).copy(); o += (smax - 1) * n2
+        m = got[r, o:o + 2 * (Sr - 1) * n2].copy().view(np.float64).reshape(Sr - 1, n2)
+        out.append((c, a, m, int(got[r, 1])))
+    return out
 
 
 def _sweep_large(torch, _native, ops, omega, halo, select=None):

@@ -3,6 +3,7 @@
 #include "../../include/axisafe_b200.h"
 #include <string.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 extern "C" {
 int axs_launch_element_matrices(int, const int*, const double*, const double*, const double*, cplx*, cudaStream_t);
@@ -31,6 +32,83 @@ int axs_launch_energy_ratio(int, int, const cplx*, const int*, int, const int*, 
 }
 
 #define AXS_ERR_TOO_LARGE 100001
+#define AXS_GRID_Y 32768                /* frequencies per launch of the kernels that put nf in gridDim.y */
+
+// ---- kernel-selection switches: environment read once, then axs_set_tuning ----------------------
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+static AxsTuning* tuning_mut(void)
+{
+    static AxsTuning t;
+    static bool init = false;
+    if (!init) {
+        t.reduce_oc = env_int("AXS_REDUCE_OC", 12);
+        t.reduce_prebal = env_int("AXS_REDUCE_PREBAL", 1);
+        t.hqr_stages = env_int("AXS_HQR_STAGES", 4);
+        t.hqr_bulges = env_int("AXS_HQR_BULGES", 8);
+        t.hqr_small_direct = env_int("AXS_HQR_SMALL_DIRECT", 1);
+        t.hqr_aed = env_int("AXS_HQR_AED", 8);
+        t.backnorm_wy = env_int("AXS_BACKNORM_WY", 1);
+        t.backnorm_wy_modes = env_int("AXS_BACKNORM_WY_MODES", 64);
+        t.bpsi_tiled = env_int("AXS_BPSI_TILED", 1);
+        t.track_fma = env_int("AXS_TRACK_FMA", 0);
+        t.big_blocked = env_int("AXS_BIG_BLOCKED", 1);
+        t.big_panel = env_int("AXS_BIG_PANEL", 32);
+        init = true;
+    }
+    return &t;
+}
+extern "C" const AxsTuning* axs_tuning(void) { return tuning_mut(); }
+
+static int* tuning_field(const char* name)
+{
+    AxsTuning* t = tuning_mut();
+    if (!name) return nullptr;
+    if (!strcmp(name, "reduce_oc")) return &t->reduce_oc;
+    if (!strcmp(name, "reduce_prebal")) return &t->reduce_prebal;
+    if (!strcmp(name, "hqr_stages")) return &t->hqr_stages;
+    if (!strcmp(name, "hqr_bulges")) return &t->hqr_bulges;
+    if (!strcmp(name, "hqr_small_direct")) return &t->hqr_small_direct;
+    if (!strcmp(name, "hqr_aed")) return &t->hqr_aed;
+    if (!strcmp(name, "backnorm_wy")) return &t->backnorm_wy;
+    if (!strcmp(name, "backnorm_wy_modes")) return &t->backnorm_wy_modes;
+    if (!strcmp(name, "bpsi_tiled")) return &t->bpsi_tiled;
+    if (!strcmp(name, "track_fma")) return &t->track_fma;
+    if (!strcmp(name, "big_blocked")) return &t->big_blocked;
+    if (!strcmp(name, "big_panel")) return &t->big_panel;
+    return nullptr;
+}
+extern "C" int axs_set_tuning(const char* name, int value)
+{
+    int* p = tuning_field(name);
+    if (!p) return -1;
+    *p = value;
+    return 0;
+}
+extern "C" int axs_get_tuning(const char* name, int* value)
+{
+    int* p = tuning_field(name);
+    if (!p) return -1;
+    if (!value) return -2;
+    *value = *p;
+    return 0;
+}
+
+// workspace views advanced by f0 frequencies (launch chunking)
+static AxsWork work_at(AxsWork w, int n2, long long f0)
+{
+    w.A += f0 * n2 * n2; w.Hc += f0 * hcol_size(n2); w.Hr += f0 * hrow_size(n2); w.tau += f0 * n2;
+    w.scale += f0 * n2; w.ucur += f0; w.Hp += f0 * hcol_size(n2); w.stats += 4 * f0;
+    return w;
+}
+static AxsWorkBig workbig_at(AxsWorkBig w, int n2, long long f0)
+{
+    w.A += f0 * n2 * n2; w.Hc += f0 * hcol_size(n2); w.Hm += f0 * hcol_size(n2); w.tau += f0 * n2;
+    w.scale += f0 * n2; w.ucur += f0; w.yw += f0 * AXS_BIG_YW * n2;
+    return w;
+}
 
 extern "C" int axs_version(void) { return 100; }
 
@@ -100,8 +178,14 @@ extern "C" int axs_build_S(int N, int hb, const axs_cplx* K0s, const axs_cplx* C
     if (!omega) return -8;
     if (nf <= 0) return -9;
     if (!S) return -10;
-    return axs_launch_build_S(N, hb, (const cplx*)K0s, (const cplx*)Cb, (const cplx*)Mb, (const cplx*)K1c,
-                              (const cplx*)K6d, omega, nf, (cplx*)S, (cudaStream_t)stream);
+    const long long n2 = 2 * N;
+    for (int f0 = 0; f0 < nf; f0 += AXS_GRID_Y) {
+        const int cnt = (nf - f0 < AXS_GRID_Y) ? nf - f0 : AXS_GRID_Y;
+        rc = axs_launch_build_S(N, hb, (const cplx*)K0s, (const cplx*)Cb, (const cplx*)Mb, (const cplx*)K1c,
+                                (const cplx*)K6d, omega + f0, cnt, (cplx*)S + f0 * n2 * n2, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 extern "C" long long axs_eig_worksize(int N, int nf)
@@ -169,16 +253,25 @@ extern "C" int axs_modes(int N, int hb, const axs_cplx* Cb, const axs_cplx* K6d,
     if (!psi) return -7;
     if (!work) return -8;
     if (work_bytes < axs_eig_worksize(N, nf)) return -9;
-    if (is_big(N)) {
-        AxsWorkBig wb;
-        axs_work_layout_big(2 * N, nf, work, &wb);
-        return axs_launch_modes_big(N, hb, (const cplx*)Cb, (const cplx*)K6d, nf, (const cplx*)k, (cplx*)psi, wb,
-                                    (cudaStream_t)stream);
+    const int n2 = 2 * N;
+    const axs_cplx* kk = k;
+    for (int f0 = 0; f0 < nf; f0 += AXS_GRID_Y) {        // kernels with nf in gridDim.y: <= 65535 per launch
+        const int cnt = (nf - f0 < AXS_GRID_Y) ? nf - f0 : AXS_GRID_Y;
+        int rc;
+        if (is_big(N)) {
+            AxsWorkBig wb;
+            axs_work_layout_big(n2, nf, work, &wb);
+            rc = axs_launch_modes_big(N, hb, (const cplx*)Cb, (const cplx*)K6d, cnt, (const cplx*)kk + (long long)f0 * n2,
+                                      (cplx*)psi + (long long)f0 * n2 * n2, workbig_at(wb, n2, f0), (cudaStream_t)stream);
+        } else {
+            AxsWork wk;
+            axs_work_layout(n2, nf, work, &wk);
+            rc = axs_launch_modes(N, hb, (const cplx*)Cb, (const cplx*)K6d, cnt, (const cplx*)kk + (long long)f0 * n2,
+                                  (cplx*)psi + (long long)f0 * n2 * n2, work_at(wk, n2, f0), (cudaStream_t)stream);
+        }
+        if (rc) return rc;
     }
-    AxsWork wk;
-    axs_work_layout(2 * N, nf, work, &wk);
-    return axs_launch_modes(N, hb, (const cplx*)Cb, (const cplx*)K6d, nf, (const cplx*)k, (cplx*)psi, wk,
-                            (cudaStream_t)stream);
+    return 0;
 }
 
 extern "C" int axs_eig_sweep(int N, int hb, const axs_cplx* K0s, const axs_cplx* Cb, const axs_cplx* Mb,
@@ -219,6 +312,20 @@ extern "C" int axs_get_reduction(int N, int nf, const void* work, double* scale,
     return 0;
 }
 
+extern "C" int axs_hqr_stats(int N, int nf, const void* work, int* stats, void* stream)
+{
+    if (N <= 0) return -1;
+    if (nf <= 0) return -2;
+    if (!work) return -3;
+    if (!stats) return -4;
+    if (is_big(N)) return -1;                              /* counters exist for the shared-memory path only */
+    AxsWork wk;
+    axs_work_layout(2 * N, nf, (void*)work, &wk);
+    AXS_CUDA_OK(cudaMemcpyAsync(stats, wk.stats, (size_t)nf * 4 * sizeof(int), cudaMemcpyDeviceToDevice,
+                                (cudaStream_t)stream));
+    return 0;
+}
+
 extern "C" long long axs_track_worksize(int N, int npairs)
 {
     if (N <= 0 || npairs <= 0) return 0;
@@ -240,8 +347,14 @@ extern "C" int axs_track_pairs(int N, int hb, const axs_cplx* Cb, const axs_cplx
     if (!amax) return -8;
     if (!work) return -9;
     if (work_bytes < axs_track_worksize(N, npairs)) return -10;
-    return axs_launch_track(N, hb, (const cplx*)Cb, (const cplx*)K6d, (const cplx*)psi, npairs, (cplx*)work,
-                            arg, amax, (cudaStream_t)stream);
+    const long long n2 = 2 * N;
+    for (int p0 = 0; p0 < npairs; p0 += AXS_GRID_Y) {
+        const int cnt = (npairs - p0 < AXS_GRID_Y) ? npairs - p0 : AXS_GRID_Y;
+        const int rc = axs_launch_track(N, hb, (const cplx*)Cb, (const cplx*)K6d, (const cplx*)psi + p0 * n2 * n2, cnt,
+                                        (cplx*)work, arg + p0 * n2, amax + p0 * n2, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 extern "C" int axs_track_scan(const int* h_arg, const double* h_amax, int nf, int n2, int start, int* h_order)
@@ -276,8 +389,15 @@ extern "C" int axs_apply_order(int n2, int nf, const int* order, const axs_cplx*
     if (!order) return -3;
     if (!k) return -4;
     if (!k_out) return -6;
-    return axs_launch_apply_order(n2, nf, order, (const cplx*)k, (const cplx*)psi, (cplx*)k_out,
-                                  (cplx*)psi_out, (cudaStream_t)stream);
+    for (int f0 = 0; f0 < nf; f0 += AXS_GRID_Y) {
+        const int cnt = (nf - f0 < AXS_GRID_Y) ? nf - f0 : AXS_GRID_Y;
+        const long long o1 = (long long)f0 * n2, o2 = o1 * n2;
+        const int rc = axs_launch_apply_order(n2, cnt, order + o1, (const cplx*)k + o1,
+                                              psi ? (const cplx*)psi + o2 : nullptr, (cplx*)k_out + o1,
+                                              psi_out ? (cplx*)psi_out + o2 : nullptr, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 extern "C" int axs_select_modes(int n2, int nf, const axs_cplx* k, const double* sigma, int m, int* rank,
@@ -289,7 +409,14 @@ extern "C" int axs_select_modes(int n2, int nf, const axs_cplx* k, const double*
     if (!sigma) return -4;
     if (m <= 0 || m > n2) return -5;
     if (!rank) return -6;
-    return axs_launch_select_modes(n2, nf, (const cplx*)k, sigma, m, rank, (cplx*)psi, (cudaStream_t)stream);
+    for (int f0 = 0; f0 < nf; f0 += AXS_GRID_Y) {
+        const int cnt = (nf - f0 < AXS_GRID_Y) ? nf - f0 : AXS_GRID_Y;
+        const long long o1 = (long long)f0 * n2;
+        const int rc = axs_launch_select_modes(n2, cnt, (const cplx*)k + o1, sigma + f0, m, rank + o1,
+                                               psi ? (cplx*)psi + o1 * n2 : nullptr, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 extern "C" int axs_energy_ratio(int N, int nf, const axs_cplx* psi, const int* tclass,
@@ -304,9 +431,15 @@ extern "C" int axs_energy_ratio(int N, int nf, const axs_cplx* psi, const int* t
     if (nnz_total <= 0 || !rows_total || !cols_total || !vals_total) return -5;
     if (nnz_pml < 0 || (nnz_pml > 0 && (!rows_pml || !cols_pml || !vals_pml))) return -9;
     if (!er) return -13;
-    return axs_launch_energy_ratio(N, nf, (const cplx*)psi, tclass, nnz_total, rows_total, cols_total,
-                                   (const cplx*)vals_total, nnz_pml, rows_pml, cols_pml, (const cplx*)vals_pml,
-                                   er, (cudaStream_t)stream);
+    const long long n2 = 2 * N;
+    for (int f0 = 0; f0 < nf; f0 += AXS_GRID_Y) {
+        const int cnt = (nf - f0 < AXS_GRID_Y) ? nf - f0 : AXS_GRID_Y;
+        const int rc = axs_launch_energy_ratio(N, cnt, (const cplx*)psi + f0 * n2 * n2, tclass, nnz_total, rows_total,
+                                               cols_total, (const cplx*)vals_total, nnz_pml, rows_pml, cols_pml,
+                                               (const cplx*)vals_pml, er + f0 * n2, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 extern "C" int axs_quadratic_forms(int N, int nf, const axs_cplx* psi, const int* tclass, int n_sel, const int* sel,
@@ -317,15 +450,23 @@ extern "C" int axs_quadratic_forms(int N, int nf, const axs_cplx* psi, const int
     if (nf <= 0) return -2;
     if (!psi) return -3;
     if (!tclass) return -4;
-    if (n_sel <= 0 || n_sel > 2 * N) return -5;
+    if (n_sel < 0 || n_sel > 2 * N) return -5;
+    if (n_sel == 0) return 0;                              /* no mode selected: nothing to do (empty result) */
     if (n_mat <= 0) return -7;
     if (!mat_off) return -8;
     if (!rows) return -9;
     if (!cols) return -10;
     if (!vals) return -11;
     if (!out) return -12;
-    return axs_launch_quad_forms(N, nf, (const cplx*)psi, tclass, n_sel, sel, n_mat, mat_off, rows, cols,
-                                 (const cplx*)vals, (cplx*)out, (cudaStream_t)stream);
+    const long long n2 = 2 * N;
+    for (int f0 = 0; f0 < nf; f0 += AXS_GRID_Y) {
+        const int cnt = (nf - f0 < AXS_GRID_Y) ? nf - f0 : AXS_GRID_Y;
+        const int rc = axs_launch_quad_forms(N, cnt, (const cplx*)psi + f0 * n2 * n2, tclass, n_sel, sel, n_mat, mat_off,
+                                             rows, cols, (const cplx*)vals, (cplx*)out + (long long)f0 * n_sel * n_mat,
+                                             (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 extern "C" int axs_modal_projection(int N, int nf, const axs_cplx* psi, const axs_cplx* fvec, axs_cplx* out,
@@ -336,6 +477,12 @@ extern "C" int axs_modal_projection(int N, int nf, const axs_cplx* psi, const ax
     if (!psi) return -3;
     if (!fvec) return -4;
     if (!out) return -5;
-    return axs_launch_modal_projection(2 * N, nf, (const cplx*)psi, (const cplx*)fvec, (cplx*)out,
-                                       (cudaStream_t)stream);
+    const long long n2 = 2 * N;
+    for (int f0 = 0; f0 < nf; f0 += AXS_GRID_Y) {
+        const int cnt = (nf - f0 < AXS_GRID_Y) ? nf - f0 : AXS_GRID_Y;
+        const int rc = axs_launch_modal_projection(2 * N, cnt, (const cplx*)psi + f0 * n2 * n2, (const cplx*)fvec,
+                                                   (cplx*)out + f0 * n2, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
 }

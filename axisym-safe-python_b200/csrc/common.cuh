@@ -166,6 +166,37 @@ __device__ __forceinline__ void gen_rot(cplx x, cplx y, cplx& a, cplx& b, cplx& 
 
 #define AXS_CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
+// Opt-in to more than 48 KB of dynamic shared memory ONCE per (kernel instance, device) instead of
+// on every launch: the macro keeps the largest size it has set per device in a static of the call site.
+#define AXS_SMEM_ONCE(bytes, ...) do {                                                              \
+        static size_t axs_done_[32];                                                                 \
+        int axs_dev_ = 0;                                                                            \
+        AXS_CUDA_OK(cudaGetDevice(&axs_dev_));                                                       \
+        const size_t axs_b_ = (size_t)(bytes);                                                       \
+        if (axs_dev_ < 0 || axs_dev_ >= 32 || axs_done_[axs_dev_] < axs_b_) {                        \
+            AXS_CUDA_OK(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)axs_b_)); \
+            if (axs_dev_ >= 0 && axs_dev_ < 32) axs_done_[axs_dev_] = axs_b_;                       \
+        }                                                                                            \
+    } while (0)
+
+// Kernel-selection switches.  Read ONCE from the environment when the library is first used
+// (api.cu) and adjustable afterwards through axs_set_tuning() - the launchers never call getenv.
+struct AxsTuning {
+    int reduce_oc;          // AXS_REDUCE_OC: warps per CTA of the on-chip Hessenberg reduction (12 | 8); 0 = L2-resident k_reduce
+    int reduce_prebal;      // AXS_REDUCE_PREBAL: 1 = k_balance in front of k_reduce (2N < 96)
+    int hqr_stages;         // AXS_HQR_STAGES: length of the shrinking-window cascade (4)
+    int hqr_bulges;         // AXS_HQR_BULGES: bulges in flight per batch (8)
+    int hqr_small_direct;   // AXS_HQR_SMALL_DIRECT: problems that fit an SM twice skip the one-CTA-per-SM stage (1)
+    int hqr_aed;            // AXS_HQR_AED: aggressive-early-deflation window (8; 0 = off)
+    int backnorm_wy;        // AXS_BACKNORM_WY: blocked compact-WY back-transformation on DMMA tiles (1)
+    int backnorm_wy_modes;  // AXS_BACKNORM_WY_MODES: modes per CTA (64 | 32)
+    int bpsi_tiled;         // AXS_BPSI_TILED: tiled B psi kernel (1)
+    int track_fma;          // AXS_TRACK_FMA: scalar-DFMA tracking GEMM instead of DMMA (0)
+    int big_blocked;        // AXS_BIG_BLOCKED: large path, blocked multi-CTA Hessenberg reduction (1); 0 = one CTA per frequency
+    int big_panel;          // AXS_BIG_PANEL: panel width of the blocked reduction (32)
+};
+extern "C" const AxsTuning* axs_tuning(void);
+
 // limits of the shared-memory ("small") eigen path
 #define AXS_MAX_SMALL_N2 166
 
@@ -178,6 +209,7 @@ struct AxsWork {
     double* scale;  // [nf][n2]  balancing factors D
     int*    ucur;   // [nf]      active-window top between QR stages
     cplx*   Hp;     // [nf][hcol_size] leading block parked between QR stages (Hc stays intact)
+    int*    stats;  // [nf][4]   QR counters per matrix: macro steps, batches, AED calls, AED deflations
 };
 
 static inline long long axs_align(long long x) { return (x + 255) & ~255LL; }
@@ -206,6 +238,8 @@ static inline long long axs_work_layout(int n2, int nf, void* base, AxsWork* w) 
     off += axs_align((long long)nf * sizeof(int));
     if (w) w->Hp = (cplx*)(b + off);
     off += szHc;
+    if (w) w->stats = (int*)(b + off);
+    off += axs_align((long long)nf * 4 * sizeof(int));
     return off;
 }
 

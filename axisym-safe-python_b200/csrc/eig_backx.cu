@@ -277,8 +277,7 @@ extern "C" int axs_launch_backnorm_wy(int N, int hb, const cplx* Cb, const cplx*
                                       const cplx* eig, cplx* psi, AxsWork wk, cudaStream_t st)
 {
     const int n = 2 * N;
-    const char* env = getenv("AXS_BACKNORM_WY");     // 0: per-reflector slab kernel (k_backnorm)
-    if ((env && !atoi(env)) || n > WY_MAX_N || n < 16) return -1;
+    if (!axs_tuning()->backnorm_wy || n > WY_MAX_N || n < 16) return -1;   // 0: per-reflector slab kernel (k_backnorm)
     const int nblk = (n - 2 + WY_NB - 1) / WY_NB;
     // T factors live in the QR parking buffer (dead once the eigenvalues are out)
     if ((long long)nblk * WY_NB * WY_NB > (long long)hcol_size(n)) return -1;
@@ -286,14 +285,14 @@ extern "C" int axs_launch_backnorm_wy(int N, int hb, const cplx* Cb, const cplx*
     k_wy_tfactor<<<dim3(nblk, nf), 32, 0, st>>>(n, wk, Tg, nblk);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    const char* menv = getenv("AXS_BACKNORM_WY_MODES");   // modes per CTA: 64 (default, 12.2 ms per 2000 points with k_modes) or 32 (2 CTAs per SM, 14.3 ms: V staging twice as often)
-    if (!(menv && atoi(menv) == 32)) {
+    // modes per CTA: 64 (default, 12.2 ms per 2000 points with k_modes) or 32 (2 CTAs per SM, 14.3 ms: V staging twice as often)
+    if (axs_tuning()->backnorm_wy_modes != 32) {
         const size_t smem = backnorm_wy_smem(n, 64);
-        AXS_CUDA_OK(cudaFuncSetAttribute(k_backnorm_wy<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AXS_SMEM_ONCE(smem, k_backnorm_wy<64>);
         k_backnorm_wy<64><<<dim3((n + 63) / 64, nf), 256, smem, st>>>(N, hb, Cb, K6d, eig, psi, wk, Tg, nblk);
     } else {
         const size_t smem = backnorm_wy_smem(n, 32);
-        AXS_CUDA_OK(cudaFuncSetAttribute(k_backnorm_wy<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AXS_SMEM_ONCE(smem, k_backnorm_wy<32>);
         k_backnorm_wy<32><<<dim3((n + 31) / 32, nf), 128, smem, st>>>(N, hb, Cb, K6d, eig, psi, wk, Tg, nblk);
     }
     return (int)cudaGetLastError();

@@ -1017,7 +1017,7 @@ __global__ void k_unpack_big(int n, AxsWorkBig wk, cplx* __restrict__ Hd)
 
 // ------------------------------------------------------------------------------ launchers
 extern "C" int axs_launch_hqr_stages(int n, int nf, int m_first, cplx* Hp, cplx* eig, int* info, int* ucur,
-                                     cudaStream_t st);
+                                     int* stats, cudaStream_t st);
 extern "C" int axs_hqr_stage_capacity(int per_sm);
 
 extern "C" int axs_launch_reduce_big(int N, int hb, const cplx* K0s, const cplx* Cb, const cplx* Mb,
@@ -1026,19 +1026,8 @@ extern "C" int axs_launch_reduce_big(int N, int hb, const cplx* K0s, const cplx*
 {
     const int n = 2 * N;
     const size_t smem = (size_t)n * sizeof(cplx);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_reduce_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AXS_SMEM_ONCE(smem, k_reduce_big);
     k_reduce_big<<<nf, RB_NT, smem, st>>>(N, hb, K0s, Cb, Mb, K1c, K6d, omega, S_in, wk);
-    return (int)cudaGetLastError();
-}
-
-// windowed QR down to an active block of m_stop rows, in place on packed matrices H (also usable as
-// stage 0 of the shared-memory cascade: AXS_HQR_WINDOW_FIRST)
-extern "C" int axs_launch_hqr_window(int n, int nf, int m_stop, cplx* H, cplx* eig, int* info, int* ucur,
-                                     cudaStream_t st)
-{
-    const size_t smem = hqr_big_smem();
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_hqr_big<<<nf, HB_NT, smem, st>>>(n, m_stop, H, eig, info, ucur);
     return (int)cudaGetLastError();
 }
 
@@ -1046,11 +1035,11 @@ extern "C" int axs_launch_hqr_big(int n, int nf, cplx* eig, int* info, AxsWorkBi
 {
     const int m2 = axs_hqr_stage_capacity(2);            // what the 2-CTA/SM shared-memory stage can hold
     const size_t smem = hqr_big_smem();
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AXS_SMEM_ONCE(smem, k_hqr_big);
     k_hqr_big<<<nf, HB_NT, smem, st>>>(n, m2, wk.Hc, eig, info, wk.ucur);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    return axs_launch_hqr_stages(n, nf, m2, wk.Hc, eig, info, wk.ucur, st);
+    return axs_launch_hqr_stages(n, nf, m2, wk.Hc, eig, info, wk.ucur, nullptr, st);
 }
 
 template <int NT, int R, int M>
@@ -1060,10 +1049,7 @@ static int launch_modes_col(int n, int nf, const cplx* eig, cplx* psi, AxsWorkBi
     long long items = (long long)nf * groups;
     int grid = items < AXS_BIG_MODE_GRID ? (int)items : AXS_BIG_MODE_GRID;
     const size_t smem = (size_t)n * sizeof(cplx);
-    if (smem > 48 * 1024) {
-        cudaError_t ea = cudaFuncSetAttribute(k_modes_col<NT, R, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (ea != cudaSuccess) return (int)ea;
-    }
+    if (smem > 48 * 1024) AXS_SMEM_ONCE(smem, k_modes_col<NT, R, M>);
     k_modes_col<NT, R, M><<<grid, NT, smem, st>>>(n, nf, eig, psi, wk);
     return (int)cudaGetLastError();
 }
@@ -1088,7 +1074,7 @@ extern "C" int axs_launch_modes_big(int N, int hb, const cplx* Cb, const cplx* K
     while (Cs >= 1 && (size_t)(Cs + 4) * n * sizeof(cplx) > 224 * 1024) Cs >>= 1;
     if (Cs >= 1) {
         const size_t smem = (size_t)(Cs + 4) * n * sizeof(cplx);
-        AXS_CUDA_OK(cudaFuncSetAttribute(k_backx_slab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        AXS_SMEM_ONCE(smem, k_backx_slab);
         k_backx_slab<<<dim3((n + Cs - 1) / Cs, nf), 256, smem, st>>>(n, Cs, psi, wk);
         e = cudaGetLastError();
     } else {

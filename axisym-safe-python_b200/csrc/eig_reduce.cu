@@ -470,7 +470,7 @@ static int launch_oc(int n, int nf, AxsWork wk, cudaStream_t st)
     if (ncs > n - 1) ncs = n - 1;                    // column 0 never needs to be on chip
     const int jg = n - ncs;
     const size_t smem = fixed + (size_t)ncs * colb;
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_reduce_oc<NWARP, R, PAD, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AXS_SMEM_ONCE(smem, k_reduce_oc<NWARP, R, PAD, PIPE>);
     k_reduce_oc<NWARP, R, PAD, PIPE><<<nf, NWARP * 32, smem, st>>>(n, jg, wk);
     return (int)cudaGetLastError();
 }
@@ -481,7 +481,7 @@ extern "C" int axs_launch_balance(int N, int hb, const cplx* K0s, const cplx* Cb
 {
     const int n = 2 * N;
     size_t smem = balance_smem(n);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_balance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AXS_SMEM_ONCE(smem, k_balance);
     k_balance<<<nf, BAL_THREADS, smem, st>>>(N, hb, K0s, Cb, Mb, K1c, K6d, omega, S_in, wk);
     return (int)cudaGetLastError();
 }
@@ -492,11 +492,10 @@ extern "C" int axs_launch_reduce_oc(int N, int hb, const cplx* K0s, const cplx* 
                                     const cplx* S_in, AxsWork wk, cudaStream_t st)
 {
     const int n = 2 * N;
-    const char* env = getenv("AXS_REDUCE_OC");       // 0: L2-resident k_reduce; 8 / 12: warps per CTA
-    int nw = env ? atoi(env) : 12;
+    const int nw = axs_tuning()->reduce_oc;          // 0: L2-resident k_reduce; 8 / 12: warps per CTA
     if (nw == 0 || n < 96 || n > AXS_MAX_SMALL_N2) return -1;
     size_t smem = balance_smem(n);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_balance, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AXS_SMEM_ONCE(smem, k_balance);
     k_balance<<<nf, BAL_THREADS, smem, st>>>(N, hb, K0s, Cb, Mb, K1c, K6d, omega, S_in, wk);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;

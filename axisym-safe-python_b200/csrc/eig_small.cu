@@ -19,6 +19,7 @@
 //              un-balancing, B-normalisation psi = v / sqrt(2k u^T K6 u + u^T C u) and the
 //              store in the reference psi_hat layout.
 #include "common.cuh"
+#include "aed.cuh"
 #include <stdlib.h>
 #include <stdio.h>
 
@@ -303,167 +304,8 @@ static size_t reduce_smem(int n) {
 }
 
 // =========================================================================================
-// k_hqr
+// k_hqr_mb
 // =========================================================================================
-
-__device__ cplx wilkinson_shift(cplx* H, int i) {
-    // eigenvalue of the trailing 2x2 closer to H(i,i)  (zlahqr)
-    cplx t = HC(H, i, i);
-    cplx u2 = cmul(csqrt_(HC(H, i - 1, i)), csqrt_(HC(H, i, i - 1)));
-    double s = cabs1(u2);
-    if (s != 0.0) {
-        cplx x = cscale(csub(HC(H, i - 1, i - 1), t), 0.5);
-        double sx = cabs1(x);
-        s = fmax(s, sx);
-        cplx xs = cscale(x, 1.0 / s), us = cscale(u2, 1.0 / s);
-        cplx yv = cscale(csqrt_(cadd(cmul(xs, xs), cmul(us, us))), s);
-        if (sx > 0.0) {
-            cplx xn = cscale(x, 1.0 / sx);
-            if (xn.x * yv.x + xn.y * yv.y < 0.0) yv = cneg(yv);
-        }
-        t = csub(t, cmul(u2, cdiv(u2, cadd(x, yv))));
-    }
-    return t;
-}
-
-__global__ void __launch_bounds__(192, 1)
-k_hqr(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* __restrict__ info)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int f = blockIdx.x, tid = threadIdx.x;
-    const int hsz = hcol_size(n);
-    cplx* H = (cplx*)smem_raw;          // packed column-major Hessenberg
-    cplx* ra = H + hsz;                 // [n] rotation a_k
-    cplx* rb = ra + n;                  // [n] rotation b_k
-    __shared__ int s_l;
-    __shared__ cplx s_shift;
-
-    const cplx* Hg = Hc_all + (long long)f * hsz;
-    for (int i = tid; i < hsz; i += blockDim.x) H[i] = Hg[i];
-    cplx* eig = eig_all + (long long)f * n;
-    __syncthreads();
-
-    int u = n - 1, its = 0, failed = 0;
-    const int itmax = 60;
-    while (u >= 0) {
-        // ---- deflation scan (parallel over subdiagonal entries) -------------------------
-        if (tid == 0) s_l = 0;
-        __syncthreads();
-        if (tid >= 1 && tid <= u) {
-            const int k = tid;
-            const cplx hkk1 = HC(H, k, k - 1);
-            const double sub = cabs1(hkk1);
-            bool neg = false;
-            if (sub <= SMALL_D) neg = true;
-            else {
-                const cplx hkk = HC(H, k, k), hk1k1 = HC(H, k - 1, k - 1);
-                double tst = cabs1(hk1k1) + cabs1(hkk);
-                if (tst == 0.0) {
-                    if (k - 2 >= 0) tst += cabs1(HC(H, k - 1, k - 2));
-                    if (k + 1 <= n - 1) tst += cabs1(HC(H, k + 1, k));
-                }
-                if (sub <= EPS_D * tst) {
-                    const double up = cabs1(HC(H, k - 1, k));
-                    const double ab = fmax(sub, up), ba = fmin(sub, up);
-                    const double dd = cabs1(csub(hk1k1, hkk));
-                    const double aa = fmax(cabs1(hkk), dd), bb = fmin(cabs1(hkk), dd);
-                    const double s = aa + ab;
-                    if (ba * (ab / s) <= fmax(SMALL_D, EPS_D * (bb * (aa / s)))) neg = true;
-                }
-            }
-            if (neg) atomicMax(&s_l, k);
-        }
-        __syncthreads();
-        const int l = s_l;
-        if (l > 0 && tid == 0) HC(H, l, l - 1) = mk(0, 0);
-        if (l == u) {
-            if (tid == 0) eig[u] = HC(H, u, u);
-            --u; its = 0;
-            __syncthreads();
-            continue;
-        }
-        ++its;
-        if (its > itmax) {                 // give up on this eigenvalue: report and move on
-            if (tid == 0) eig[u] = HC(H, u, u);
-            ++failed; --u; its = 0;
-            __syncthreads();
-            continue;
-        }
-        // ---- shift ------------------------------------------------------------------------
-        if (tid == 0) {
-            cplx sg;
-            if (its % 20 == 10) sg = cadd(HC(H, l, l), mk(0.75 * fabs(HC(H, l + 1, l).x), 0));
-            else if (its % 20 == 0) sg = cadd(HC(H, u, u), mk(0.75 * fabs(HC(H, u, u - 1).x), 0));
-            else sg = wilkinson_shift(H, u);
-            s_shift = sg;
-        }
-        __syncthreads();
-        const cplx sg = s_shift;
-
-        // ---- left rotations: systolic wavefront, thread j owns column j --------------------
-        const bool mine = (tid >= l && tid <= u);
-        cplx carry = mk(0, 0);
-        if (mine) {
-            carry = HC(H, l, tid);
-            if (tid == l) carry = csub(carry, sg);
-        }
-        for (int k = l; k < u; ++k) {
-            if (tid == k) {
-                const cplx g = HC(H, k + 1, k);
-                const double r2 = cabs2(carry) + cabs2(g);
-                cplx a = mk(1, 0), b = mk(0, 0);
-                double r = 0.0;
-                if (r2 > 0.0) {
-                    const double ir = rsqrt(r2);
-                    a = mk(carry.x * ir, -carry.y * ir);
-                    b = mk(g.x * ir, -g.y * ir);
-                    r = r2 * ir;
-                }
-                ra[k] = a; rb[k] = b;
-                HC(H, k, k) = mk(r, 0.0);
-            }
-            __syncthreads();
-            if (tid > k && tid <= u) {
-                const cplx a = ra[k], b = rb[k];
-                cplx low = HC(H, k + 1, tid);
-                if (tid == k + 1) low = csub(low, sg);
-                // [top; bot] = [[a, b], [-conj(b), conj(a)]] [carry; low]
-                const cplx top = cfma(a, carry, cmul(b, low));
-                const cplx bot = csub(cmulc(low, a), cmulc(carry, b));
-                HC(H, k, tid) = top;
-                carry = bot;
-            }
-        }
-        if (tid == u) HC(H, u, u) = carry;
-        __syncthreads();
-
-        // ---- right rotations: thread i owns row i -----------------------------------------
-        if (mine) {
-            const int i = tid;
-            int kk = (i - 1 >= l) ? i - 1 : l;
-            cplx left = (i - 1 >= l) ? mk(0, 0) : HC(H, i, l);
-            for (int k = kk; k < u; ++k) {
-                const cplx right = HC(H, i, k + 1);
-                const cplx a = ra[k], b = rb[k];
-                // [newl, newr] = [left, right] * [[conj(a), -b], [conj(b), a]]
-                cplx newl = cfmac(left, a, cmulc(right, b));
-                const cplx newr = csub(cmul(right, a), cmul(left, b));
-                if (k == i) newl = cadd(newl, sg);
-                HC(H, i, k) = newl;
-                left = newr;
-            }
-            if (i == u) left = cadd(left, sg);
-            HC(H, i, u) = left;
-        }
-        __syncthreads();
-    }
-    if (tid == 0) info[f] = failed;
-}
-
-
-static size_t hqr_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(cplx); }
-
-// -----------------------------------------------------------------------------------------
 // k_hqr_mb: implicit single-shift QR with several bulges chased concurrently ("small-bulge
 // multishift").  A batch takes nb shifts (eigenvalues of the trailing 2x2 diagonal blocks of
 // the active window, closed form), starts bulge b at macro step b*MB_D and advances every
@@ -478,33 +320,33 @@ static size_t hqr_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(c
 #define MB_THREADS 512
 #define MB_WORKERS (MB_THREADS - 32)
 #define MB_ITEMS 3                      // ceil(MB_MAX * (AXS_MAX_SMALL_N2 + 1) / MB_THREADS)
+#define AED_ITEMS 3                     // ceil(window rows above x AED_MAX / threads) for every stage instance
 
 // Staging: the active window only shrinks, so the sweep is cut into stages with a smaller
 // shared-memory footprint each; a stage stops once the window is <= m_stop, parks the leading
 // block and its size in global memory, and the next stage resumes with more CTAs per SM
 // (the kernel is latency bound, so co-resident matrices translate into throughput).
-// OPT (stage 1, one CTA per SM, where phase R is bound by shared-memory bandwidth and the leader
-// chain by contention on its sub-partition):
-//   * the lower output of a row rotation is the upper input of the same (bulge, column) item one
-//     macro step later: it is carried in a register instead of a store + load whenever no column
-//     rotation of the intervening phase C touches it (columns k+3d, k+3d+1 of the bulges ahead);
-//   * the warps that share the leader warp's SM sub-partition take no phase-C items.
-// LDG: the leader lane of a bulge owns the whole 2 x 2 diagonal block (rows / columns k, k+1) plus
-// H(k+2, k+1): it applies the row AND the column rotation there and generates the next rotation
-// already during phase R, so the chain overlaps both bulk phases instead of only phase C.
-template <int NT, int MINB, int NITEMS, bool OPT = false, bool CARRY = false, bool RC = false, bool LDG = false>
+// OPT (stage 1, one CTA per SM, where the leader chain suffers from contention on its
+// sub-partition): the warps that share the leader warp's SM sub-partition take no phase-C items.
+// Rotations have a real cosine (zlartg form, common.cuh).  Variants that were measured and
+// rejected in round 1 (explicit-shift wavefronts, register carry, leader-owned diagonal block,
+// complex-cosine rotations, the windowed warp-specialised stage 1) are in the git history
+// (commit 3cb38ed) and in DESIGN.md section 4.5; they are no longer compiled into the library.
+template <int NT, int MINB, int NITEMS, bool OPT = false>
 __global__ void __launch_bounds__(NT, MINB)
-k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ Hc_all, cplx* __restrict__ Hp_all,
-         cplx* __restrict__ eig_all, int* __restrict__ info, int* __restrict__ ucur)
+k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* __restrict__ Hc_all,
+         cplx* __restrict__ Hp_all, cplx* __restrict__ eig_all, int* __restrict__ info, int* __restrict__ ucur,
+         int* __restrict__ stats)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int f = blockIdx.x, tid = threadIdx.x;
     const int hsz = hcol_size(n);
     cplx* H = (cplx*)smem_raw;
     __shared__ int s_l;
-    __shared__ cplx s_shift[MB_MAX];
+    __shared__ cplx s_shift[AED_MAX > MB_MAX ? AED_MAX : MB_MAX];
     __shared__ cplx s_ra[2][MB_MAX], s_rb[2][MB_MAX];
     __shared__ cplx s_rr[2][MB_MAX];
+    __shared__ AedScratch s_aed;
 
     const cplx* Hg = (first_stage ? Hc_all : Hp_all) + (long long)f * hsz;
     cplx* Hpark = Hp_all + (long long)f * hsz;
@@ -515,14 +357,10 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
     __syncthreads();
 
     int its = 0, failed = 0;
-#ifdef OC_TIMING
-    long long tq[5] = {0, 0, 0, 0, 0}, tq0 = clock64(); int nmacro = 0, nbatch = 0;
-#define HQ_MARK(i) { const long long t1c = clock64(); tq[i] += t1c - tq0; tq0 = t1c; }
-#else
-#define HQ_MARK(i)
-#endif
+    int n_macro = 0, n_batch = 0, n_aed = 0, n_aed_defl = 0;
+    bool have_shifts = false;                             // s_shift[0..ns_aed) hold the AED window's eigenvalues
+    int ns_aed = 0;
     while (u >= m_stop) {
-        HQ_MARK(4)
         // ---- deflation scan ----------------------------------------------------------------
         if (tid == 0) s_l = 0;
         __syncthreads();
@@ -553,22 +391,99 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
         if (l > 0 && tid == 0) HC(H, l, l - 1) = mk(0, 0);
         if (l == u) {
             if (tid == 0) eig[u] = HC(H, u, u);
-            --u; its = 0;
+            --u; its = 0; have_shifts = false;
             __syncthreads();
             continue;
         }
         ++its;
         if (its > 120) {
             if (tid == 0) eig[u] = HC(H, u, u);
-            ++failed; --u; its = 0;
+            ++failed; --u; its = 0; have_shifts = false;
             __syncthreads();
             continue;
         }
+        // ---- aggressive early deflation on the trailing window (zlaqr2 semantics) ------------
+        have_shifts = false;
+        if (aed_nw >= 2 && u - l + 1 >= 3) {
+            __syncthreads();                              // H(l, l-1) = 0 is visible
+            const int nw = (aed_nw < u - l + 1) ? aed_nw : u - l + 1;
+            const int kw = u - nw + 1;
+            if (tid < 32) aed_window(H, l, u, nw, &s_aed, tid);
+            __syncthreads();
+            ++n_aed;
+            const int aed_ok = s_aed.ok;
+            const int ns = s_aed.ns, nd = nw - ns;        // undeflated / deflated window eigenvalues
+            if (aed_ok && nd > 0) {
+                // rows of the active block above the window: H[l:kw, kw:u+1] <- H[l:kw, kw:u+1] Z
+                // (one thread per output entry, results held back until every input has been read)
+                const int nra = kw - l;
+                cplx upd[AED_ITEMS];
+#pragma unroll
+                for (int q = 0; q < AED_ITEMS; ++q) {
+                    const int idx = tid + q * NT;
+                    upd[q] = mk(0, 0);
+                    if (idx < nra * nw) {
+                        const int j = idx / nra, i = l + (idx - j * nra);
+                        cplx acc = mk(0, 0);
+                        for (int qq = 0; qq < nw; ++qq) acc = cfma(HC(H, i, kw + qq), s_aed.Z[qq][j], acc);
+                        upd[q] = acc;
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < AED_ITEMS; ++q) {
+                    const int idx = tid + q * NT;
+                    if (idx < nra * nw) {
+                        const int j = idx / nra, i = l + (idx - j * nra);
+                        HC(H, i, kw + j) = upd[q];
+                    }
+                }
+                // the window itself: T (Hessenberg in its leading ns x ns part, triangular below) and the spike
+                for (int idx = tid; idx < nw * nw; idx += NT) {
+                    const int j = idx / nw, i = idx - j * nw;
+                    if (i <= j + 1) HC(H, kw + i, kw + j) = s_aed.T[i][j];
+                }
+                if (tid == 0 && kw > l) HC(H, kw, kw - 1) = s_aed.spike_new;
+                for (int j = ns + tid; j < nw; j += NT) eig[kw + j] = s_aed.T[j][j];
+                n_aed_defl += nd;
+                u = kw + ns - 1;
+                its = 0;
+            }
+            if (aed_ok) {
+                for (int j = tid; j < ns; j += NT) s_shift[j] = s_aed.shift[j];
+                have_shifts = ns > 0;
+                ns_aed = ns;
+            }
+            __syncthreads();
+            if (aed_ok && nd > 0) {
+                // LAPACK's "nibble": a productive window is followed by another one, not by a sweep
+                if (u < l + 1 || nd * 100 >= 14 * nw) continue;
+            }
+        }
         const int m = u - l + 1;
+        if (m < 2) continue;
         int nb = (m - 2) / MB_D + 1;
         if (nb > bmax) nb = bmax;
-        // ---- shifts: eigenvalues of the trailing 2x2 diagonal blocks -------------------------
-        if (tid < (nb + 1) / 2) {
+        // ---- shifts ---------------------------------------------------------------------------
+        if (have_shifts && its % 10 != 0) {
+            // the undeflated eigenvalues of the AED window, the ones nearest to H(u, u) first
+            if (nb > ns_aed) nb = ns_aed;
+            __shared__ cplx s_tmp[AED_MAX];
+            const cplx huu = HC(H, u, u);
+            if (tid < ns_aed) {
+                const cplx me = s_shift[tid];
+                const double dme = cabs1(csub(me, huu));
+                int rank = 0;
+                for (int q = 0; q < ns_aed; ++q) {
+                    const double dq = cabs1(csub(s_shift[q], huu));
+                    rank += (dq < dme || (dq == dme && q < tid)) ? 1 : 0;
+                }
+                s_tmp[rank] = me;
+            }
+            __syncthreads();
+            if (tid < ns_aed) s_shift[tid] = s_tmp[tid];
+        } else if (tid < (nb + 1) / 2) {
+            // eigenvalues of the trailing 2x2 diagonal blocks
             const int i = u - 2 * tid;
             const cplx a11 = HC(H, i - 1, i - 1), a12 = HC(H, i - 1, i), a21 = HC(H, i, i - 1), a22 = HC(H, i, i);
             const cplx hd = cscale(csub(a11, a22), 0.5);
@@ -586,7 +501,7 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
         __syncthreads();
         if (tid == 0) {                                  // rotation that introduces bulge 0
             cplx a, b, r;
-            gen_rot<RC>(csub(HC(H, l, l), s_shift[0]), HC(H, l + 1, l), a, b, r);
+            make_rot_rc(csub(HC(H, l, l), s_shift[0]), HC(H, l + 1, l), a, b, r);
             s_ra[0][0] = a; s_rb[0][0] = b; s_rr[0][0] = r;
         }
         __syncthreads();
@@ -595,8 +510,6 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
         // per-thread work items are fixed for the whole batch: (bulge, column) for the row
         // rotations, (bulge, row) for the column rotations; only k = k0 + t moves.
         int r_k0[NITEMS], r_col[NITEMS], r_off[NITEMS], c_k0[NITEMS], c_row[NITEMS];
-        cplx r_carry[NITEMS];
-        bool r_has[NITEMS];
         // phase-C workers: all worker warps, or (OPT) only those on other sub-partitions than the leader's
         const int wq = tid >> 5;
         const int NCW = OPT ? (NT / 32 - NT / 128) * 32 : (NT - 32);
@@ -607,7 +520,6 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
             const int item = (tid < (NT - 32)) ? tid + q * (NT - 32) : (1 << 30);   // last warp: leaders only
             r_k0[q] = c_k0[q] = 1 << 28;                 // "never active"
             r_col[q] = 0; r_off[q] = 0; c_row[q] = 0;
-            r_has[q] = false; r_carry[q] = mk(0, 0);
             if (item < nb * CW) {
                 const int b = item / CW, col = l - 1 + (item - b * CW);
                 if (col >= l) { r_k0[q] = l - b * MB_D; r_col[q] = col; r_off[q] = hcol_off(col); }
@@ -619,81 +531,31 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
                 c_k0[q] = l - b * MB_D; c_row[q] = l + (citem - b * m);
             }
         }
-        HQ_MARK(0)
-#ifdef OC_TIMING
-        nmacro += nsteps; ++nbatch;
-#endif
+        n_macro += nsteps; ++n_batch;
         for (int t = 0; t < nsteps; ++t) {
             const int cur = t & 1, nxt = cur ^ 1;
-            if (LDG && tid >= (NT - 32)) {
-                const int b = tid - ((NT - 32));
-                const int k = l + t - b * MB_D;
-                if (b < nb && k >= l && k <= u - 1) {
-                    const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
-                    cplx* p0 = H + hcol_off(k) + k;          // (k, k), (k+1, k)
-                    cplx* p1 = H + hcol_off(k + 1) + k;      // (k, k+1), (k+1, k+1), (k+2, k+1)
-                    const cplx a00 = p0[0], a10 = p0[1], a01 = p1[0], a11 = p1[1];
-                    const cplx h = (k + 2 <= u) ? p1[2] : mk(0, 0);
-                    cplx t00, t10, t01, t11, n00, n01, n10, n11;
-                    rot_rows<RC>(ga, gb, a00, a10, t00, t10);
-                    rot_rows<RC>(ga, gb, a01, a11, t01, t11);
-                    rot_cols<RC>(ga, gb, t10, t11, n10, n11);   // row k+1 first: it feeds the next rotation
-                    if (k + 2 <= u) {
-                        const cplx y = cmulc(h, gb);
-                        cplx a2, b2, r2;
-                        gen_rot<RC>(n10, y, a2, b2, r2);
-                        s_ra[nxt][b] = a2; s_rb[nxt][b] = b2; s_rr[nxt][b] = r2;
-                        p1[2] = RC ? cscale(h, ga.x) : cmul(h, ga);
-                    }
-                    rot_cols<RC>(ga, gb, t00, t01, n00, n01);
-                    p0[0] = n00; p0[1] = n10; p1[0] = n01; p1[1] = n11;
-                }
-                if (b == nb && (t + 1) % MB_D == 0 && (t + 1) / MB_D < nb) {   // bulge (t+1)/D starts next step
-                    const int bn = (t + 1) / MB_D;
-                    cplx a2, b2, r2;
-                    gen_rot<RC>(csub(HC(H, l, l), s_shift[bn]), HC(H, l + 1, l), a2, b2, r2);
-                    s_ra[nxt][bn] = a2; s_rb[nxt][bn] = b2; s_rr[nxt][bn] = r2;
-                }
-            }
-                // ---- phase R: row rotations ---------------------------------------------------------
+            // ---- phase R: row rotations ---------------------------------------------------------
 #pragma unroll
             for (int q = 0; q < NITEMS; ++q) {
                 const int k = r_k0[q] + t, col = r_col[q];
-                if (k >= l && k <= u - 1 && col >= k - 1 && k < (1 << 27) && !(LDG && (col == k || col == k + 1))) {
+                if (k >= l && k <= u - 1 && col >= k - 1 && k < (1 << 27)) {
                     const int b = (l - r_k0[q]) / MB_D;
                     cplx* pk = H + r_off[q] + k;
                     if (col == k - 1) { *pk = s_rr[cur][b]; }
-                    else if (!CARRY) {
+                    else {
                         const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
                         const cplx p = pk[0], qv = pk[1];
                         cplx top, bot;
-                        rot_rows<RC>(ga, gb, p, qv, top, bot);
+                        rot_rows<true>(ga, gb, p, qv, top, bot);
                         pk[0] = top; pk[1] = bot;
-                    } else {
-                        const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
-                        const cplx p = r_has[q] ? r_carry[q] : pk[0];
-                        const cplx qv = pk[1];
-                        cplx top, bot;
-                        rot_rows<RC>(ga, gb, p, qv, top, bot);
-                        pk[0] = top;
-                        // row k+1 of this column stays in a register if the item runs again next step
-                        // and no column rotation of this step's phase C touches it: the bulges ahead
-                        // (d = 1..b) rotate the columns k+3d, k+3d+1, this bulge the columns k, k+1
-                        const int dl = col - k;
-                        const int d3 = dl / 3;
-                        const bool keep = (k + 1 <= u - 1) && (dl >= 2) && ((dl - 3 * d3 == 2) || (d3 > b));
-                        if (keep) r_carry[q] = bot; else pk[1] = bot;
-                        r_has[q] = keep;
                     }
                 }
             }
-            HQ_MARK(1)
             __syncthreads();
-            HQ_MARK(2)
             // ---- phase C: column rotations, next rotation ---------------------------------------
             // The last warp owns the critical chain of every bulge (rows k+1, k+2 -> next rotation)
             // so that it overlaps with the bulk updates done by the other warps.
-            if (!LDG && tid >= (NT - 32)) {
+            if (tid >= (NT - 32)) {
                 const int b = tid - ((NT - 32));
                 const int k = l + t - b * MB_D;
                 if (b < nb && k >= l && k <= u - 1) {
@@ -703,248 +565,55 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, const cplx* __restrict__ 
                     const cplx c0 = *p0, c1 = *p1;
                     const cplx h = (k + 2 <= u) ? p1[1] : mk(0, 0);         // H(k+2, k+1), before the stores
                     cplx n0, n1;
-                    rot_cols<RC>(ga, gb, c0, c1, n0, n1);
+                    rot_cols<true>(ga, gb, c0, c1, n0, n1);
                     *p0 = n0;
                     *p1 = n1;
                     if (k + 2 <= u) {
                         const cplx y = cmulc(h, gb);                        // new bulge H(k+2, k) = h conj(b)
-                        p1[1] = RC ? cscale(h, ga.x) : cmul(h, ga);
+                        p1[1] = cscale(h, ga.x);
                         cplx a2, b2, r2;
-                        gen_rot<RC>(n0, y, a2, b2, r2);
+                        make_rot_rc(n0, y, a2, b2, r2);
                         s_ra[nxt][b] = a2; s_rb[nxt][b] = b2; s_rr[nxt][b] = r2;
                     }
                 }
                 if (b == nb && (t + 1) % MB_D == 0 && (t + 1) / MB_D < nb) {   // bulge (t+1)/D starts next step
                     const int bn = (t + 1) / MB_D;
                     cplx a2, b2, r2;
-                    gen_rot<RC>(csub(HC(H, l, l), s_shift[bn]), HC(H, l + 1, l), a2, b2, r2);
+                    make_rot_rc(csub(HC(H, l, l), s_shift[bn]), HC(H, l + 1, l), a2, b2, r2);
                     s_ra[nxt][bn] = a2; s_rb[nxt][bn] = b2; s_rr[nxt][bn] = r2;
                 }
             }
 #pragma unroll
             for (int q = 0; q < NITEMS; ++q) {
                 const int k = c_k0[q] + t, r = c_row[q];
-                if (k >= l && k <= u - 1 && r <= k - (LDG ? 1 : 0)) {
+                if (k >= l && k <= u - 1 && r <= k) {
                     const int b = (l - c_k0[q]) / MB_D;
                     const cplx ga = s_ra[cur][b], gb = s_rb[cur][b];
                     cplx* p0 = H + hcol_off(k) + r;
                     cplx* p1 = H + hcol_off(k + 1) + r;
                     const cplx c0 = *p0, c1 = *p1;
                     cplx n0, n1;
-                    rot_cols<RC>(ga, gb, c0, c1, n0, n1);
+                    rot_cols<true>(ga, gb, c0, c1, n0, n1);
                     *p0 = n0; *p1 = n1;
                 }
             }
-            HQ_MARK(3)
             __syncthreads();
-            HQ_MARK(2)
         }
     }
-#ifdef OC_TIMING
-    if (f == 0 && first_stage && (tid == 0 || tid == NT - 32 || tid == 256))
-        printf("hqr stage1 tid %d: setup %lld phaseR %lld barrier %lld phaseC %lld other %lld cycles, %d macro steps, %d batches\n",
-               tid, tq[0], tq[1], tq[2], tq[3], tq[4], nmacro, nbatch);
-#endif
-    if (tid == 0) { info[f] = first_stage ? failed : info[f] + failed; ucur[f] = u; }
+    if (tid == 0) {
+        info[f] = first_stage ? failed : info[f] + failed;
+        ucur[f] = u;
+        if (stats) {                                      // per-matrix counters (axs_hqr_stats): macro steps,
+            int* sp = stats + 4 * (long long)f;           // batches, AED calls, eigenvalues deflated by AED
+            if (first_stage) { sp[0] = n_macro; sp[1] = n_batch; sp[2] = n_aed; sp[3] = n_aed_defl; }
+            else { sp[0] += n_macro; sp[1] += n_batch; sp[2] += n_aed; sp[3] += n_aed_defl; }
+        }
+    }
     if (u >= 0)                                           // park the remaining leading block
         for (int i = tid; i < hcol_size(u + 1); i += NT) Hpark[i] = H[i];
 }
 
 static size_t hqr_mb_smem(int n) { return (size_t)hcol_size(n) * sizeof(cplx); }
-
-// -----------------------------------------------------------------------------------------
-// k_hqr_ws: explicit single-shift QR, warp-shuffle systolic wavefront without per-rotation
-// block barriers.
-//   threads [0, W)   own one COLUMN each (left rotations).  The warp that contains the
-//                    diagonal column k is the "front": lane k generates G_k, broadcasts it to its
-//                    warp with shuffles and publishes it in shared memory (rot[k], then
-//                    `ready = k+1` after a block-scope fence).  Warps that own later columns poll
-//                    `ready` and apply the rotations at their own pace until the front reaches them.
-//   threads [W, 2W)  own one ROW each (right rotations R G_k^H) and trail the front: step k of
-//                    row i runs as soon as ready >= k+2 (column k+1 is final by then).
-// One __syncthreads per sweep; the per-rotation critical path is apply -> rotg -> shuffle.
-__device__ __forceinline__ cplx shfl_c(cplx v, int src) {
-    v.x = __shfl_sync(0xffffffffu, v.x, src);
-    v.y = __shfl_sync(0xffffffffu, v.y, src);
-    return v;
-}
-
-__global__ void __launch_bounds__(384, 1)
-k_hqr_ws(int n, const cplx* __restrict__ Hc_all, cplx* __restrict__ eig_all, int* __restrict__ info)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int f = blockIdx.x, tid = threadIdx.x;
-    const int W = blockDim.x >> 1;
-    const int hsz = hcol_size(n);
-    cplx* H = (cplx*)smem_raw;
-    cplx* ra = H + hsz;
-    cplx* rb = ra + n;
-    __shared__ int s_l;
-    __shared__ cplx s_shift;
-    __shared__ volatile int s_ready;
-
-    const cplx* Hg = Hc_all + (long long)f * hsz;
-    for (int i = tid; i < hsz; i += blockDim.x) H[i] = Hg[i];
-    cplx* eig = eig_all + (long long)f * n;
-    __syncthreads();
-
-    int u = n - 1, its = 0, failed = 0;
-    while (u >= 0) {
-        if (tid == 0) s_l = 0;
-        __syncthreads();
-        if (tid >= 1 && tid <= u) {
-            const int k = tid;
-            const double sub = cabs1(HC(H, k, k - 1));
-            bool neg = false;
-            if (sub <= SMALL_D) neg = true;
-            else {
-                const cplx hkk = HC(H, k, k), hk1k1 = HC(H, k - 1, k - 1);
-                double tst = cabs1(hk1k1) + cabs1(hkk);
-                if (tst == 0.0) {
-                    if (k - 2 >= 0) tst += cabs1(HC(H, k - 1, k - 2));
-                    if (k + 1 <= n - 1) tst += cabs1(HC(H, k + 1, k));
-                }
-                if (sub <= EPS_D * tst) {
-                    const double up = cabs1(HC(H, k - 1, k));
-                    const double ab = fmax(sub, up), ba = fmin(sub, up);
-                    const double dd = cabs1(csub(hk1k1, hkk));
-                    const double aa = fmax(cabs1(hkk), dd), bb = fmin(cabs1(hkk), dd);
-                    const double sm = aa + ab;
-                    if (ba * (ab / sm) <= fmax(SMALL_D, EPS_D * (bb * (aa / sm)))) neg = true;
-                }
-            }
-            if (neg) atomicMax(&s_l, k);
-        }
-        __syncthreads();
-        const int l = s_l;
-        if (l > 0 && tid == 0) HC(H, l, l - 1) = mk(0, 0);
-        if (l == u) {
-            if (tid == 0) eig[u] = HC(H, u, u);
-            --u; its = 0;
-            __syncthreads();
-            continue;
-        }
-        ++its;
-        if (its > 60) {
-            if (tid == 0) eig[u] = HC(H, u, u);
-            ++failed; --u; its = 0;
-            __syncthreads();
-            continue;
-        }
-        if (tid == 0) {
-            cplx sg;
-            if (its % 20 == 10) sg = cadd(HC(H, l, l), mk(0.75 * fabs(HC(H, l + 1, l).x), 0));
-            else if (its % 20 == 0) sg = cadd(HC(H, u, u), mk(0.75 * fabs(HC(H, u, u - 1).x), 0));
-            else sg = wilkinson_shift(H, u);
-            s_shift = sg;
-            s_ready = l;
-        }
-        __syncthreads();
-        const cplx sg = s_shift;
-
-        if (tid < W) {
-            // ================= left rotations: one column per thread =========================
-            // Shared-memory stores of one thread become visible in program order (in-order LSU),
-            // so "rotation record, then ready counter" needs no fence; volatile keeps the compiler
-            // from reordering them.
-            volatile cplx* vra = ra;
-            volatile cplx* vrb = rb;
-            const int j = tid, wbase = tid & ~31;
-            if (wbase <= u && wbase + 31 >= l) {
-                const bool act = (j >= l && j <= u);
-                cplx carry = mk(0, 0);
-                if (act) { carry = HC(H, l, j); if (j == l) carry = csub(carry, sg); }
-                const int front0 = wbase > l ? wbase : l;
-                // phase 1: rotations generated by earlier warps, consumed in batches
-                int k = l;
-                while (k < front0) {
-                    int avail = s_ready;
-                    while (avail <= k) { __nanosleep(64); avail = s_ready; }
-                    asm volatile("" ::: "memory");      // compiler-only barrier (acquire)
-                    if (avail > front0) avail = front0;
-                    if (act) {
-                        cplx low = HC(H, k + 1, j);
-                        for (; k < avail; ++k) {
-                            const cplx a = mk(vra[k].x, vra[k].y), b = mk(vrb[k].x, vrb[k].y);
-                            cplx lw = low;
-                            if (k + 1 < avail || k + 2 <= u) low = HC(H, (k + 2 <= u) ? k + 2 : u, j);   // prefetch
-                            if (j == k + 1) lw = csub(lw, sg);
-                            HC(H, k, j) = cfma(a, carry, cmul(b, lw));
-                            carry = csub(cmulc(lw, a), cmulc(carry, b));
-                        }
-                    }
-                    k = avail;
-                }
-                // phase 2: this warp is the front
-                const int last = (wbase + 31 < u - 1) ? wbase + 31 : u - 1;
-                cplx low = mk(0, 0);
-                if (front0 <= last && j <= u && j > front0) low = HC(H, front0 + 1, j);
-                cplx g = mk(0, 0);
-                if (j >= front0 && j <= last) g = HC(H, j + 1, j);          // own subdiagonal entry
-                for (k = front0; k <= last; ++k) {
-                    cplx a = mk(1, 0), b = mk(0, 0);
-                    double r = 0.0;
-                    if (j == k) make_rot(carry, g, a, b, r);
-                    a = shfl_c(a, k - wbase);
-                    b = shfl_c(b, k - wbase);
-                    if (j > k && j <= u) {
-                        cplx lw = low;
-                        if (k + 2 <= u) low = HC(H, k + 2, j);              // prefetch next row
-                        if (j == k + 1) lw = csub(lw, sg);
-                        HC(H, k, j) = cfma(a, carry, cmul(b, lw));
-                        carry = csub(cmulc(lw, a), cmulc(carry, b));
-                    } else if (j == k) {                                    // publish off the critical path
-                        HC(H, k, k) = mk(r, 0.0);
-                        asm volatile("" ::: "memory");  // keep the stores in program order
-                        vra[k].x = a.x; vra[k].y = a.y; vrb[k].x = b.x; vrb[k].y = b.y;
-                        asm volatile("" ::: "memory");
-                        s_ready = k + 1;
-                    }
-                }
-                if (j == u) {
-                    HC(H, u, u) = carry;
-                    __threadfence_block();
-                    s_ready = u + 1;
-                }
-            }
-        } else {
-            // ================= right rotations: one row per thread ===========================
-            volatile cplx* vra = ra;
-            volatile cplx* vrb = rb;
-            const int i = tid - W;
-            if (i >= l && i <= u) {
-                const int kk = (i - 1 >= l) ? i - 1 : l;
-                cplx left = mk(0, 0);
-                bool have_left = (i - 1 >= l);
-                int k = kk;
-                while (k < u) {                          // lanes advance independently of each other
-                    const int avail = s_ready;
-                    asm volatile("" ::: "memory");
-                    if (avail < k + 2) { __nanosleep(32); continue; }
-                    if (!have_left) { left = HC(H, i, l); have_left = true; }     // R[l,l]
-                    const cplx rt = HC(H, i, k + 1);
-                    const cplx a = mk(vra[k].x, vra[k].y), b = mk(vrb[k].x, vrb[k].y);
-                    cplx newl = cfmac(left, a, cmulc(rt, b));
-                    const cplx newr = csub(cmul(rt, a), cmul(left, b));
-                    if (k == i) newl = cadd(newl, sg);
-                    HC(H, i, k) = newl;
-                    left = newr;
-                    ++k;
-                }
-                if (i == u) left = cadd(left, sg);
-                HC(H, i, u) = left;
-            }
-        }
-        __syncthreads();
-    }
-    if (tid == 0) info[f] = failed;
-}
-
-static size_t hqr_ws_smem(int n) { return (size_t)(hcol_size(n) + 2 * n) * sizeof(cplx); }
-
-
-
-
 
 // =========================================================================================
 // k_modes
@@ -1179,137 +848,6 @@ static size_t backnorm_smem(int n) {
 }
 
 
-// -----------------------------------------------------------------------------------------
-// k_backnorm_reg: same operation as k_backnorm with the mode vectors in REGISTERS.
-// CTA = one frequency x 16 modes, 256 threads = 16 modes x 16 row groups (rows i = grp mod 16,
-// at most 11 per thread); a reflector costs one shared-memory read of v per row, a 2-step
-// reduction (shuffle across the two row groups of a warp, 8 partials through shared memory) and
-// one block barrier.  k_backnorm keeps the 64-mode slab in shared memory and is bound by its
-// bandwidth (three passes over the slab per reflector); this one is bound by instruction issue.
-#define BR_COLS 16
-#define BR_ROWS 11                      // ceil(AXS_MAX_SMALL_N2 / 16); the slot switches below list 0..10
-static_assert(AXS_MAX_SMALL_N2 <= 16 * 11, "k_backnorm_reg: register slots");
-#define BR_AHEAD 4
-#define BR_RING (BR_AHEAD + 2)
-__global__ void __launch_bounds__(256, 3)
-k_backnorm_reg(int N, int hb, const cplx* __restrict__ Cb, const cplx* __restrict__ K6d,
-               const cplx* __restrict__ eig_all, cplx* __restrict__ psi_all, AxsWork wk)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = 2 * N;
-    cplx* vbuf = (cplx*)smem_raw;                     // [BR_RING][n]   (slot kk+1 of a buffer holds tau[kk])
-    cplx* red = vbuf + BR_RING * n;                         // [2][8][16], reused [16][16] by the epilogue
-    cplx* Xs = red + 256;                             // [n][16]  (epilogue only)
-    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int col = tid & 15, grp = tid >> 4;
-    const int mode = blockIdx.x * BR_COLS + col;
-    const bool live = mode < n;
-    const cplx* A = wk.A + (long long)f * n * n;
-    const cplx* tau = wk.tau + (long long)f * n;
-    const double* dsc = wk.scale + (long long)f * n;
-    cplx* psi = psi_all + (long long)f * n * n;
-
-    cplx x[BR_ROWS];
-#pragma unroll
-    for (int q = 0; q < BR_ROWS; ++q) {
-        const int i = grp + 16 * q;
-        x[q] = (live && i < n) ? psi[(long long)i * n + mode] : mk(0, 0);
-    }
-    // reflectors travel through a ring of BR_RING shared-memory buffers, fetched BR_AHEAD steps
-    // ahead with cp.async (L2 latency ~ 4 steps of this kernel)
-    auto stage = [&](int kk) {
-        if (kk >= 0) {
-            cplx* dst = vbuf + (size_t)(kk % BR_RING) * n;
-            const int i = kk + 1 + tid;
-            if (i < n) __pipeline_memcpy_async(dst + i, (i == kk + 1) ? tau + kk : A + (long long)kk * n + i, sizeof(cplx));
-        }
-        __pipeline_commit();
-    };
-#pragma unroll
-    for (int a = 0; a < BR_AHEAD; ++a) stage(n - 3 - a);
-    __pipeline_wait_prior(BR_AHEAD - 1);
-    __syncthreads();
-    for (int kk = n - 3; kk >= 0; --kk) {
-        const cplx* vv = vbuf + (size_t)(kk % BR_RING) * n;
-        stage(kk - BR_AHEAD);
-        const cplx t = vv[kk + 1];
-        const bool skip = (t.x == 0.0 && t.y == 0.0);
-        if (!skip) {
-            cplx part = mk(0, 0);
-            // rows <= kk are untouched: jump over the register slots that hold none of the active rows
-            // (uniform switch with fall-through keeps the register indexing static)
-#define BR_DOT(q) { const int i = grp + 16 * (q); \
-                    if (i > kk && i < n) part = (i == kk + 1) ? cadd(part, x[q]) : cfmac(x[q], vv[i], part); }
-            switch ((kk + 1) >> 4) {
-                case 0: BR_DOT(0) case 1: BR_DOT(1) case 2: BR_DOT(2) case 3: BR_DOT(3) case 4: BR_DOT(4)
-                case 5: BR_DOT(5) case 6: BR_DOT(6) case 7: BR_DOT(7) case 8: BR_DOT(8) case 9: BR_DOT(9)
-                default: BR_DOT(10)
-            }
-#undef BR_DOT
-            part.x += __shfl_xor_sync(0xffffffffu, part.x, 16);
-            part.y += __shfl_xor_sync(0xffffffffu, part.y, 16);
-            if (lane < 16) red[(kk & 1) * 128 + warp * 16 + lane] = part;
-        }
-        __pipeline_wait_prior(BR_AHEAD - 1);               // reflector kk-1 has landed
-        __syncthreads();
-        if (!skip) {
-            const cplx* rd = red + (kk & 1) * 128 + col;
-            cplx dot = rd[0];
-#pragma unroll
-            for (int w = 1; w < 8; ++w) dot = cadd(dot, rd[w * 16]);
-            const cplx td = cmul(t, dot);
-#define BR_UPD(q) { const int i = grp + 16 * (q); \
-                    if (i > kk && i < n) x[q] = (i == kk + 1) ? csub(x[q], td) : cfms(td, vv[i], x[q]); }
-            switch ((kk + 1) >> 4) {
-                case 0: BR_UPD(0) case 1: BR_UPD(1) case 2: BR_UPD(2) case 3: BR_UPD(3) case 4: BR_UPD(4)
-                case 5: BR_UPD(5) case 6: BR_UPD(6) case 7: BR_UPD(7) case 8: BR_UPD(8) case 9: BR_UPD(9)
-                default: BR_UPD(10)
-            }
-#undef BR_UPD
-        }
-    }
-    // v = D y into shared memory, then B-normalise with u = v[N:]:  s = 2 k u^T K6 u + u^T C u
-#pragma unroll
-    for (int q = 0; q < BR_ROWS; ++q) {
-        const int i = grp + 16 * q;
-        if (i < n) Xs[i * BR_COLS + col] = cscale(x[q], dsc[i]);
-    }
-    __syncthreads();
-    const cplx lam = eig_all[(long long)f * n + (live ? mode : n - 1)];
-    const int W = 2 * hb + 1;
-    cplx s6 = mk(0, 0), sc = mk(0, 0);
-    for (int r = grp; r < N; r += 16) {
-        const cplx ur = Xs[(N + r) * BR_COLS + col];
-        s6 = cfma(cmul(ur, ur), K6d[r], s6);
-        cplx cu0 = mk(0, 0), cu1 = mk(0, 0);
-        const int c0 = max(0, r - hb), c1 = min(N - 1, r + hb);
-        const cplx* crow = Cb + (long long)r * W - r + hb;
-        int c = c0;
-        for (; c + 1 <= c1; c += 2) {
-            cu0 = cfma(crow[c], Xs[(N + c) * BR_COLS + col], cu0);
-            cu1 = cfma(crow[c + 1], Xs[(N + c + 1) * BR_COLS + col], cu1);
-        }
-        if (c <= c1) cu0 = cfma(crow[c], Xs[(N + c) * BR_COLS + col], cu0);
-        sc = cfma(ur, cadd(cu0, cu1), sc);
-    }
-    red[grp * 16 + col] = cadd(cscale(cmul(lam, s6), 2.0), sc);
-    __syncthreads();
-    cplx nrm = red[col];
-#pragma unroll
-    for (int g = 1; g < 16; ++g) nrm = cadd(nrm, red[g * 16 + col]);
-    const cplx inv = cdiv(mk(1.0, 0.0), csqrt_(nrm));
-    if (live) {
-        for (int r = grp; r < N; r += 16) {
-            const cplx u = cmul(Xs[(N + r) * BR_COLS + col], inv);
-            psi[(long long)(N + r) * n + mode] = u;
-            psi[(long long)r * n + mode] = cmul(lam, u);
-        }
-    }
-}
-
-static size_t backnorm_reg_smem(int n) { return ((size_t)BR_RING * n + 256 + (size_t)n * BR_COLS) * sizeof(cplx); }
-
-
 // =========================================================================================
 // debug accessor: dense H and scale factors out of the workspace
 // =========================================================================================
@@ -1341,60 +879,50 @@ extern "C" int axs_launch_reduce(int N, int hb, const cplx* K0s, const cplx* Cb,
     // 2N >= 96: trailing block on chip (eig_reduce.cu); smaller matrices stay L2-resident, 2 CTAs per SM
     const int rc = axs_launch_reduce_oc(N, hb, K0s, Cb, Mb, K1c, K6d, omega, nf, S_in, wk, st);
     if (rc != -1) return rc;
-    // small matrices: the short-chain balancing kernel first (AXS_REDUCE_PREBAL=0: the fused one-warp loop)
+    // small matrices: the short-chain balancing kernel first (tuning reduce_prebal = 0: the fused one-warp loop)
     int prebal = 0;
-    const char* pb = getenv("AXS_REDUCE_PREBAL");
-    if (!(pb && !atoi(pb))) {
+    if (axs_tuning()->reduce_prebal) {
         const int rb = axs_launch_balance(N, hb, K0s, Cb, Mb, K1c, K6d, omega, nf, S_in, wk, st);
         if (rb) return rb;
         prebal = 1;
     }
     size_t smem = reduce_smem(n);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AXS_SMEM_ONCE(smem, k_reduce);
     k_reduce<<<nf, RED_THREADS, smem, st>>>(N, hb, K0s, Cb, Mb, K1c, K6d, omega, S_in, wk, prebal);
     return (int)cudaGetLastError();
 }
 
-// launch one k_hqr_mb stage; AXS_HQR_RC=0 selects the complex-cosine rotation form (A/B)
+// launch one k_hqr_mb stage
 template <int NT, int MINB, int NITEMS, bool OPT>
 static int launch_mb(int nf, size_t smem, cudaStream_t st, int n, int bmax, int first, int m_stop,
-                     const cplx* Hc, cplx* Hp, cplx* eig, int* info, int* ucur)
+                     const cplx* Hc, cplx* Hp, cplx* eig, int* info, int* ucur, int* stats)
 {
-    const char* rc = getenv("AXS_HQR_RC");            // default: real-cosine rotations (35.9 -> 34.5 ms / 2000 points)
-    const char* ldg = getenv("AXS_HQR_LDG");
-    if (ldg && atoi(ldg)) {
-        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<NT, MINB, NITEMS, OPT, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hqr_mb<NT, MINB, NITEMS, OPT, false, true, true><<<nf, NT, smem, st>>>(n, bmax, first, m_stop, Hc, Hp, eig, info, ucur);
-    } else if (!(rc && !atoi(rc))) {
-        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<NT, MINB, NITEMS, OPT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hqr_mb<NT, MINB, NITEMS, OPT, false, true><<<nf, NT, smem, st>>>(n, bmax, first, m_stop, Hc, Hp, eig, info, ucur);
-    } else {
-        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<NT, MINB, NITEMS, OPT, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hqr_mb<NT, MINB, NITEMS, OPT, false, false><<<nf, NT, smem, st>>>(n, bmax, first, m_stop, Hc, Hp, eig, info, ucur);
-    }
+    int aed = axs_tuning()->hqr_aed;
+    if (aed > AED_MAX) aed = AED_MAX;
+    AXS_SMEM_ONCE(smem, k_hqr_mb<NT, MINB, NITEMS, OPT>);
+    k_hqr_mb<NT, MINB, NITEMS, OPT><<<nf, NT, smem, st>>>(n, bmax, first, m_stop, aed, Hc, Hp, eig, info, ucur, stats);
     return (int)cudaGetLastError();
 }
 
-// Largest active window whose packed storage fits `per_sm` times into the shared memory of an SM.
+// Largest active window whose packed storage fits `per_sm` times into the shared memory of an SM
+// (5 KB per CTA: static shared memory of k_hqr_mb incl. the AED scratch + the 1 KB the system reserves).
 extern "C" int axs_hqr_stage_capacity(int per_sm)
 {
     int m = 0;
-    while (hqr_mb_smem(m + 1) + 2048 <= (size_t)(227 * 1024 / per_sm)) ++m;
+    while (hqr_mb_smem(m + 1) + 5120 <= (size_t)(227 * 1024 / per_sm)) ++m;
     return m;
 }
 
 // The cascade below stage 1: starts with the instance whose occupancy fits the current window
-// (512 threads x 2 CTAs/SM above 95, 384 x 3 above 82, 256 x 4 above 73, 256 x 5, and 128 x 8 for
-// windows <= 35) and hands the shrinking window down.  Hc_first != nullptr: the matrices are the
-// un-parked packed Hessenberg matrices of size n (small problems that skip stage 1); otherwise the
-// leading blocks parked in Hp (window <= m_cur, top index in ucur).  Also the tail of the large path.
+// (512 threads x 2 CTAs/SM, 384 x 3, 256 x 4, 256 x 5, and 128 x 8 for windows <= 35) and hands the
+// shrinking window down.  Hc_first != nullptr: the matrices are the un-parked packed Hessenberg
+// matrices of size n (small problems that skip stage 1); otherwise the leading blocks parked in Hp
+// (window <= m_cur, top index in ucur).  Also the tail of the large path.
 static int hqr_cascade(int n, int nf, int m_cur, const cplx* Hc_first, cplx* Hp, cplx* eig, int* info, int* ucur,
-                       cudaStream_t st)
+                       int* stats, cudaStream_t st)
 {
-    const char* st_env = getenv("AXS_HQR_STAGES");
-    const int stages = st_env ? atoi(st_env) : 4;      // 4 stages measured fastest on B200 (36.3 vs 37.7 ms)
-    const char* mode = getenv("AXS_HQR_BULGES");
-    int bulges = mode ? atoi(mode) : MB_MAX;
+    const int stages = axs_tuning()->hqr_stages;       // 4 stages measured fastest on B200 (36.3 vs 37.7 ms)
+    int bulges = axs_tuning()->hqr_bulges;
     if (bulges < 1 || bulges > MB_MAX) bulges = MB_MAX;
     const int m3 = (stages >= 3) ? axs_hqr_stage_capacity(3) : 0;
     const int m4 = (stages >= 4) ? axs_hqr_stage_capacity(4) : 0;
@@ -1402,123 +930,58 @@ static int hqr_cascade(int n, int nf, int m_cur, const cplx* Hc_first, cplx* Hp,
     int first = Hc_first ? 1 : 0;
     const cplx* src = Hc_first ? Hc_first : Hp;
     if (m_cur <= 35 && bulges * (m_cur + 1) <= 3 * (128 - 32) && stages >= 4)
-        return launch_mb<128, 8, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, 0, src, Hp, eig, info, ucur);
+        return launch_mb<128, 8, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, 0, src, Hp, eig, info, ucur, stats);
     if (m3 == 0 || m_cur > m3) {
         const int stop = (m3 >= 8 && m3 < m_cur) ? m3 : 0;
-        const int rc = launch_mb<512, 2, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, stop, src, Hp, eig, info, ucur);
+        const int rc = launch_mb<512, 2, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, stop, src, Hp, eig, info, ucur, stats);
         if (rc || !stop) return rc;
         first = 0; src = Hp; m_cur = stop;
     }
     if (m4 == 0 || m_cur > m4) {
         const int stop = (m4 >= 8 && m4 < m_cur) ? m4 : 0;
-        const int rc = launch_mb<384, 3, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, stop, src, Hp, eig, info, ucur);
+        const int rc = launch_mb<384, 3, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, stop, src, Hp, eig, info, ucur, stats);
         if (rc || !stop) return rc;
         first = 0; src = Hp; m_cur = stop;
     }
     if (!(m5 >= 8 && m_cur <= m5)) {
         const int stop = (m5 >= 8 && m5 < m_cur) ? m5 : 0;
-        const int rc = launch_mb<256, 4, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, stop, src, Hp, eig, info, ucur);
+        const int rc = launch_mb<256, 4, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, stop, src, Hp, eig, info, ucur, stats);
         if (rc || !stop) return rc;
         first = 0; src = Hp; m_cur = stop;
     }
-    return launch_mb<256, 5, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, 0, src, Hp, eig, info, ucur);
+    return launch_mb<256, 5, 3, false>(nf, hqr_mb_smem(m_cur), st, n, bulges, first, 0, src, Hp, eig, info, ucur, stats);
 }
 
 extern "C" int axs_launch_hqr_stages(int n, int nf, int m_first, cplx* Hp, cplx* eig, int* info, int* ucur,
-                                     cudaStream_t st)
+                                     int* stats, cudaStream_t st)
 {
-    return hqr_cascade(n, nf, m_first, nullptr, Hp, eig, info, ucur, st);
+    return hqr_cascade(n, nf, m_first, nullptr, Hp, eig, info, ucur, stats, st);
 }
-
-extern "C" int axs_launch_hqr_window(int n, int nf, int m_stop, cplx* H, cplx* eig, int* info, int* ucur,
-                                     cudaStream_t st);
-
-extern "C" int axs_launch_hqr_win(int n, int nf, int bulges, int m_stop, const cplx* Hc, cplx* Hp, cplx* eig,
-                                  int* info, int* ucur, cudaStream_t st);
 
 extern "C" int axs_launch_hqr(int n, int nf, cplx* eig, int* info, AxsWork wk, cudaStream_t st)
 {
-    const char* mode = getenv("AXS_HQR_BULGES");
-    int bulges = mode ? atoi(mode) : MB_MAX; // default: 8 concurrent bulges (fastest measured on B200)
-    if (bulges < 0) {                        // -1: warp-shuffle systolic wavefront (kept for A/B)
-        size_t smem = hqr_ws_smem(n);
-        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int W = ((n + 31) / 32) * 32;
-        k_hqr_ws<<<nf, 2 * W, smem, st>>>(n, wk.Hc, eig, info);
-        return (int)cudaGetLastError();
-    }
-    if (bulges == 0) {                       // barrier-per-rotation variant (kept for A/B)
-        size_t smem = hqr_smem(n);
-        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int threads = ((n + 31) / 32) * 32;
-        if (threads < 64) threads = 64;
-        k_hqr<<<nf, threads, smem, st>>>(n, wk.Hc, eig, info);
-        return (int)cudaGetLastError();
-    }
-    if (bulges > MB_MAX) bulges = MB_MAX;
+    int bulges = axs_tuning()->hqr_bulges;             // 8 concurrent bulges: fastest measured on B200
+    if (bulges < 1 || bulges > MB_MAX) bulges = MB_MAX;
     // stage 1: whole matrix, 512 threads, one CTA per SM; stage 2: window fits twice into shared
     // memory (512 threads, 64 registers, 2 CTAs per SM); stage 3: fits three times (384 threads,
-    // 56 registers, 3 CTAs per SM).  AXS_HQR_STAGES=1|2|3 limits the cascade (A/B testing).
-    const char* st_env = getenv("AXS_HQR_STAGES");
-    const int stages = st_env ? atoi(st_env) : 4;
+    // 56 registers, 3 CTAs per SM); ...  tuning hqr_stages = 1|2|3 limits the cascade (A/B testing).
+    const int stages = axs_tuning()->hqr_stages;
     int m2 = (stages >= 2) ? axs_hqr_stage_capacity(2) : 0;
     if (m2 >= n || m2 < 8) m2 = 0;
-    const char* wf = getenv("AXS_HQR_WINDOW_FIRST");       // A/B: windowed global-memory QR as stage 1
-    if (wf && atoi(wf) && m2) {
-        int ms = atoi(wf) > 1 ? atoi(wf) : m2;
-        if (ms > m2) ms = m2;
-        AXS_CUDA_OK(cudaMemcpyAsync(wk.Hp, wk.Hc, (size_t)nf * hcol_size(n) * sizeof(cplx),
-                                    cudaMemcpyDeviceToDevice, st));       // Hc stays intact
-        int rc = axs_launch_hqr_window(n, nf, ms, wk.Hp, eig, info, wk.ucur, st);
-        if (rc) return rc;
-        return axs_launch_hqr_stages(n, nf, m2, wk.Hp, eig, info, wk.ucur, st);
-    }
     size_t smem = hqr_mb_smem(n);
-    // problems that fit into the shared memory of an SM at least twice (2N <= 117) skip stage 1 and
-    // enter the cascade at the instance that fits (AXS_HQR_SMALL_DIRECT=0: one 512-thread CTA per SM)
-    if (m2 == 0 && !(getenv("AXS_HQR_SMALL_DIRECT") && !atoi(getenv("AXS_HQR_SMALL_DIRECT"))))
-        return hqr_cascade(n, nf, n, wk.Hc, wk.Hp, eig, info, wk.ucur, st);
-    const char* win = getenv("AXS_HQR_WIN");               // warp-specialised windowed stage 1 (eig_hqrwin.cu)
-    if (win && atoi(win) && m2) {
-        const int rcw = axs_launch_hqr_win(n, nf, bulges, m2, wk.Hc, wk.Hp, eig, info, wk.ucur, st);
-        if (rcw > 0) return rcw;
-        if (rcw == 0) return axs_launch_hqr_stages(n, nf, m2, wk.Hp, eig, info, wk.ucur, st);
-    }
-    const char* lean = getenv("AXS_HQR_S1_LEAN");          // A/B: stage 1 capped at 64 registers (room for a co-resident CTA)
-    const char* wide = getenv("AXS_HQR_S1_WIDE");          // A/B: stage 1 with 1024 threads; value = bulges in flight
-    if (wide && atoi(wide)) {
-        int b1 = atoi(wide);
-        if (b1 > MB_MAX) b1 = MB_MAX;
-        if (b1 * (n + 1) <= 1024 - 32) {
-            AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<1024, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_hqr_mb<1024, 1, 1><<<nf, 1024, smem, st>>>(n, b1, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
-        } else {
-            AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<1024, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_hqr_mb<1024, 1, 2><<<nf, 1024, smem, st>>>(n, b1, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
-        }
-    } else if (getenv("AXS_HQR_S1_OPT") && atoi(getenv("AXS_HQR_S1_OPT")) == 2 && bulges * n <= 3 * 384) {
-        // A/B: register carry in phase R + leader sub-partition kept free in phase C
-        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 1, 3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hqr_mb<512, 1, 3, true, true><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
-    } else if (!(getenv("AXS_HQR_S1_OPT") && atoi(getenv("AXS_HQR_S1_OPT")) == 0) && bulges * n <= 3 * 384) {
-        // (the 12 phase-C warps x 3 item slots must hold bulges x n column-rotation items: 2N <= 144)
-        // default: leader sub-partition kept free in phase C (36.5 -> 35.8 ms / 2000 points);
-        // AXS_HQR_S1_OPT=0 restores the plain mapping, =2 adds the phase-R register carry (39.3 ms)
-        const char* nt1 = getenv("AXS_HQR_S1_THREADS");
-        const int rc1 = (nt1 && atoi(nt1) == 640)
-            ? launch_mb<640, 1, 3, true>(nf, smem, st, n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur)
-            : launch_mb<512, 1, 3, true>(nf, smem, st, n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
-        if (rc1) return rc1;
-    } else if (lean && atoi(lean)) {
-        AXS_CUDA_OK(cudaFuncSetAttribute(k_hqr_mb<512, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_hqr_mb<512, 2, 3><<<nf, 512, smem, st>>>(n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
-    } else {
-        const int rc1 = launch_mb<512, 1, 3, false>(nf, smem, st, n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur);
-        if (rc1) return rc1;
-    }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess || m2 == 0) return (int)e;
-    return axs_launch_hqr_stages(n, nf, m2, wk.Hp, eig, info, wk.ucur, st);
+    // problems that fit into the shared memory of an SM at least twice skip stage 1 and enter the
+    // cascade at the instance that fits
+    if (m2 == 0 && axs_tuning()->hqr_small_direct)
+        return hqr_cascade(n, nf, n, wk.Hc, wk.Hp, eig, info, wk.ucur, wk.stats, st);
+    int rc1;
+    if (bulges * n <= 3 * 384)
+        // leader sub-partition kept free in phase C (the 12 phase-C warps x 3 item slots must hold
+        // bulges x n column-rotation items: 2N <= 144)
+        rc1 = launch_mb<512, 1, 3, true>(nf, smem, st, n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur, wk.stats);
+    else
+        rc1 = launch_mb<512, 1, 3, false>(nf, smem, st, n, bulges, 1, m2, wk.Hc, wk.Hp, eig, info, wk.ucur, wk.stats);
+    if (rc1 || m2 == 0) return rc1;
+    return axs_launch_hqr_stages(n, nf, m2, wk.Hp, eig, info, wk.ucur, wk.stats, st);
 }
 
 extern "C" int axs_launch_backnorm_wy(int N, int hb, const cplx* Cb, const cplx* K6d, int nf,
@@ -1531,27 +994,19 @@ extern "C" int axs_launch_modes(int N, int hb, const cplx* Cb, const cplx* K6d, 
     int nw = 4;
     while (nw > 1 && modes_smem(n, nw) > 227 * 1024) --nw;
     size_t smem = modes_smem(n, nw);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_modes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AXS_SMEM_ONCE(smem, k_modes);
     k_modes<<<dim3((n + 8 * nw - 1) / (8 * nw), nf), 32 * nw, smem, st>>>(N, hb, Cb, K6d, eig, psi, wk);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    // default: 64-mode slab in shared memory (7.0 ms / 2000 points); AXS_BACKNORM_REG=1 selects the
-    // register-resident variant (measured 7.7 ms: 4x more CTAs each streaming the reflectors)
-    // 2N <= 128: blocked compact-WY back-transformation on DMMA tiles (eig_backx.cu)
+    // 2N <= 128: blocked compact-WY back-transformation on DMMA tiles (eig_backx.cu); above that the
+    // per-reflector kernel with a 64-mode slab in shared memory
     {
         const int rc = axs_launch_backnorm_wy(N, hb, Cb, K6d, nf, eig, psi, wk, st);
         if (rc != -1) return rc;
     }
-    const char* regv = getenv("AXS_BACKNORM_REG");
-    if (!(regv && atoi(regv))) {
-        size_t smem2 = backnorm_smem(n);
-        AXS_CUDA_OK(cudaFuncSetAttribute(k_backnorm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-        k_backnorm<<<dim3((n + BN_COLS - 1) / BN_COLS, nf), 256, smem2, st>>>(N, hb, Cb, K6d, eig, psi, wk);
-        return (int)cudaGetLastError();
-    }
-    size_t smem2 = backnorm_reg_smem(n);
-    AXS_CUDA_OK(cudaFuncSetAttribute(k_backnorm_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    k_backnorm_reg<<<dim3((n + BR_COLS - 1) / BR_COLS, nf), 256, smem2, st>>>(N, hb, Cb, K6d, eig, psi, wk);
+    size_t smem2 = backnorm_smem(n);
+    AXS_SMEM_ONCE(smem2, k_backnorm);
+    k_backnorm<<<dim3((n + BN_COLS - 1) / BN_COLS, nf), 256, smem2, st>>>(N, hb, Cb, K6d, eig, psi, wk);
     return (int)cudaGetLastError();
 }
 

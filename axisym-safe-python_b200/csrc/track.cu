@@ -395,11 +395,9 @@ extern "C" int axs_launch_track(int N, int hb, const cplx* Cb, const cplx* K6d, 
         const size_t budget = (size_t)110 * 1024;
         int crows = ubytes < budget ? (int)((budget - ubytes) / ((size_t)W * sizeof(cplx))) : 0;
         if (crows > N) crows = N;
-        const char* tl = getenv("AXS_BPSI_TILED");
-        if (crows >= 8 && !(tl && !atoi(tl))) {
+        if (crows >= 8 && axs_tuning()->bpsi_tiled) {
             const size_t smemb = ubytes + (size_t)crows * W * sizeof(cplx);
-            e = cudaFuncSetAttribute(k_bpsi_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemb);
-            if (e != cudaSuccess) return (int)e;
+            AXS_SMEM_ONCE(smemb, k_bpsi_tiled);
             k_bpsi_tiled<<<dim3((n + BP_COLS - 1) / BP_COLS, npairs + 1), 256, smemb, st>>>(N, hb, crows, Cb, K6d, psi, Y);
         } else {
             int bx = (n * n + 255) / 256; if (bx > 64) bx = 64;
@@ -408,14 +406,12 @@ extern "C" int axs_launch_track(int N, int hb, const cplx* Cb, const cplx* K6d, 
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    const char* env = getenv("AXS_TRACK_FMA");
-    if (env && atoi(env) && n <= TR_BMAX) {                // scalar-FMA tiles (kept for A/B)
+    if (axs_tuning()->track_fma && n <= TR_BMAX) {                // scalar-FMA tiles (kept for A/B)
         k_track_gemm<<<dim3((n + TR_TA - 1) / TR_TA, npairs), 256, 0, st>>>(n, psi, Y, arg, amax);
         return (int)cudaGetLastError();
     }
     size_t smem = (size_t)(TM_KC * TM_SA + TM_KC * TM_SB) * sizeof(cplx) + 8 * 32 * (sizeof(double) + sizeof(int));
-    e = cudaFuncSetAttribute(k_track_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    AXS_SMEM_ONCE(smem, k_track_mma);
     k_track_mma<<<dim3((n + 31) / 32, npairs), 256, smem, st>>>(n, psi, Y, arg, amax);
     return (int)cudaGetLastError();
 }

@@ -87,7 +87,8 @@ int axs_build_S(int N, int hb, const axs_cplx* K0s, const axs_cplx* Cb, const ax
  * Replaces val, vec = scipy.linalg.eig(S) (LAPACK zgeev, solver.py:136) and the
  * B-normalisation solver.py:142:
  *   stage A  build S(w), zgebal-style scaling, Householder Hessenberg   (axs_reduce)
- *   stage B  explicit single-shift QR on the Hessenberg matrix          (axs_hqr)
+ *   stage B  multi-bulge implicit single-shift QR with aggressive early
+ *            deflation on the Hessenberg matrix                         (axs_hqr)
  *   stage C  inverse iteration, back-transformation, psi = v/sqrt(v^T B v) (axs_modes)
  * axs_eig_sweep runs A, B, C for nf frequencies.  Workspace: axs_eig_worksize() bytes.
  *   k    [nf][n2]          eigenvalues in the solver's native order
@@ -114,6 +115,19 @@ int axs_modes(int N, int hb, const axs_cplx* Cb, const axs_cplx* K6d, int nf,
 /* Debug/parity accessors into the workspace: copy scale factors D [nf][n2] (double) and the
  * Hessenberg matrix H [nf][n2][n2] (dense column-major, zeros below the subdiagonal). */
 int axs_get_reduction(int N, int nf, const void* work, double* scale, axs_cplx* H, void* stream);
+/* Counters of the QR stage left in the workspace by axs_hqr (shared-memory path, 2N <= axs_max_small_n2()):
+ * stats [nf][4] (device, int32) = macro steps, shift batches, aggressive-early-deflation calls,
+ * eigenvalues deflated inside those calls - the iteration counts LAPACK's zhseqr (zlaqr0/zlaqr3
+ * behind solver.py:136) would report through its own counters. */
+int axs_hqr_stats(int N, int nf, const void* work, int* stats, void* stream);
+
+/* Kernel-selection switches (A/B measurements and the variant parity tests).  Every switch is read
+ * ONCE from the environment variable AXS_<NAME> when the library is first used; afterwards it can be
+ * changed with axs_set_tuning.  Names: reduce_oc, reduce_prebal, hqr_stages, hqr_bulges,
+ * hqr_small_direct, hqr_aed, backnorm_wy, backnorm_wy_modes, bpsi_tiled, track_fma, big_blocked,
+ * big_panel.  Return 0, or -1 for an unknown name.  Not thread safe against concurrent launches. */
+int axs_set_tuning(const char* name, int value);
+int axs_get_tuning(const char* name, int* value);
 
 /* ---- mode tracking ------------------------------------------------------------------
  * Replaces the two dense products of solver.py:157 and the row arg-max of :159-161:

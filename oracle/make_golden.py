@@ -186,8 +186,73 @@ def subset_fixtures():
             os.path.basename(path), len(c['f']), 2 * N, m, min(margin), os.path.getsize(path) / 1024))
 
 
+BIG_CASES = [('coated_pipe', 1, {}, [20e3, 35e3], 'cfg4'), ('ten_layer', 1, {}, [20e3], 'cfg5')]
+
+
+def big_fixtures(which=None):
+    """tests/golden/big_cfg4.npz / big_cfg5.npz: the full-size synthetic meshes of BASELINE.md
+    (cfg4 2N = 3966, cfg5 2N = 7806), the reference's own S(w) (solver.py:115-134) pushed through the
+    reference's own call ``scipy.linalg.eig`` (solver.py:136) at 2 / 1 frequencies.  Stored: the
+    untracked eigenvalues, their condition numbers on the balanced matrix and ||S_bal||_2 (the inputs of
+    oracle.eig_tolerance), tr S, tr S^2 and the B-normalised lower halves of 16 eigenvectors (every
+    (2N / 16)-th column).  zgeev needs ~1-2 min (cfg4) / ~10 min (cfg5) per frequency on
+    the build container's 8 threads; S itself (252 MB / 975 MB) is not stored - the GPU test
+    rebuilds it from its own operators, which are pinned to the reference's by the small cases.
+    """
+    import time
+    ref = refshim.load()
+    from axisafe_b200 import cases
+    outdir = os.path.join(ROOT, 'tests', 'golden')
+    for name, n, kw, freqs, tag in BIG_CASES:
+        if which and tag not in which:
+            continue
+        c = cases.ALL[name](n=n, nf=2, **kw)
+        with refshim.quiet():
+            mesh = ref.mesh.Mesh()
+            mesh.create(c['sets'], c['fmax'], PML=c['PML'], PML_props=c['PML_props'])
+            mesh.assemble_matrices(n)
+            sol = ref.solver.WaveElementAxisym(mesh)
+            sol.t_transform()
+        N = mesh.no_of_dofs
+        B = sps.bmat([[None, mesh.K6.tocsr()], [mesh.K6.tocsr(), n * mesh.K4.tocsr() + sol.K3_hat.tocsr()]]).tocsr()
+        cols = np.arange(0, 2 * N, (2 * N) // 16)[:16]
+        ev, tr1, tr2, psi_low, secs, kappa, nrm2 = [], [], [], [], [], [], []
+        for f in freqs:
+            S = reference_S(sol, mesh, n, 2 * np.pi * f)
+            t0 = time.time()
+            with refshim.quiet():
+                val, vec = la.eig(S)
+            secs.append(time.time() - t0)
+            v = vec[:, cols]
+            v = v / np.sqrt(np.einsum('ij,ij->j', v, B @ v))
+            ev.append(val); tr1.append(np.trace(S)); tr2.append(np.sum(S * S.T)); psi_low.append(v[N:])
+            print('%s f=%g: zgeev %.0f s' % (tag, f, secs[-1]), flush=True)
+            # conditioning of every eigenvalue on the balanced matrix (what oracle.eig_tolerance uses):
+            # kappa_k = ||y_k|| ||x_k|| / |y_k^H x_k| with the left vectors taken from inv(V)
+            _, D = la.matrix_balance(S, permute=False, separate=True)
+            d = D[0]
+            vinv = la.inv(vec)
+            kap = np.linalg.norm(vinv * d[None, :], axis=1) * np.linalg.norm(vec / d[:, None], axis=0)
+            Sb = S * (d[None, :] / d[:, None])
+            x = np.ones(2 * N, complex)
+            for _ in range(60):                                   # ||S_bal||_2 by power iteration on S^H S
+                x = Sb.conj().T @ (Sb @ x)
+                x /= np.linalg.norm(x)
+            kappa.append(kap); nrm2.append(np.linalg.norm(Sb @ x))
+            print('%s f=%g: kappa max %.2e median %.2e, ||S_bal||_2 %.3e' % (tag, f, kap.max(), np.median(kap), nrm2[-1]), flush=True)
+            del S, vec, vinv, Sb
+        path = os.path.join(outdir, 'big_%s.npz' % tag)
+        np.savez_compressed(path, f=np.array(freqs), n=n, N=N, eig_untracked=np.array(ev), trS=np.array(tr1),
+                            trS2=np.array(tr2), cols=cols, psi_low=np.array(psi_low), zgeev_seconds=np.array(secs),
+                            kappa=np.array(kappa), norm2_balanced=np.array(nrm2),
+                            threads=len(os.sched_getaffinity(0)))
+        print('%-20s 2N=%d %6.0f KB' % (os.path.basename(path), 2 * N, os.path.getsize(path) / 1024), flush=True)
+
+
 if __name__ == '__main__':
-    if 'subset' in sys.argv[1:]:
+    if 'big' in sys.argv[1:]:
+        big_fixtures([a for a in sys.argv[1:] if a.startswith('cfg')])
+    elif 'subset' in sys.argv[1:]:
         subset_fixtures()
     elif 'envel' in sys.argv[1:]:
         energy_velocity_fixtures()

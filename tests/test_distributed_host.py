@@ -160,3 +160,49 @@ def test_shard_plan_properties():
         assert all(a[1] == b[0] for a, b in zip(flat, flat[1:]))
         assert all(hi > lo for lo, hi in flat)
     check()
+
+
+def _worker_exchange(rank, world, port, out_dir):
+    """Fixed-size segment exchange + completion of per-rank rows (solver._exchange_segments / _complete_rows)."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(os.path.dirname(here), 'axisym-safe-python_b200'))
+    from axisafe_b200 import solver
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    n2, smax = 10, 3
+    for round_, big in enumerate((False, True)):
+        rng = np.random.default_rng(100 * round_ + rank)
+        S = 1 + rank % smax if not (big and rank == 1) else smax + 2          # one rank overflows the fixed buffer
+        comps = rng.integers(0, n2, size=[S, n2]).astype(np.int32)
+        d_arg = rng.integers(0, n2, size=[S - 1, n2]).astype(np.int32)
+        d_amax = rng.random([S - 1, n2])
+        cap = 2 + n2 * (4 * smax - 3)
+        send = torch.zeros(cap, dtype=torch.int32)
+        recv = torch.zeros(world * cap, dtype=torch.int32)
+        got = solver._exchange_segments(torch, dist, None, (comps, d_arg, d_amax, rank), n2, smax, send, recv, world)
+        assert len(got) == world
+        for r, g in enumerate(got):
+            rr = np.random.default_rng(100 * round_ + r)
+            Sr = 1 + r % smax if not (big and r == 1) else smax + 2
+            assert np.array_equal(g[0], rr.integers(0, n2, size=[Sr, n2]).astype(np.int32))
+            assert np.array_equal(g[1], rr.integers(0, n2, size=[Sr - 1, n2]).astype(np.int32))
+            assert np.array_equal(g[2], rr.random([Sr - 1, n2]))
+            assert g[3] == r
+    # rows of an interleaved layout completed on every rank, real and complex, 2-D and 3-D
+    nf = 23
+    sol = solver.WaveElementAxisym(None)
+    sol.w = np.zeros(nf)
+    sol._sharded = True
+    sol.local_index = np.arange(rank, nf, world)
+    full_r = np.arange(nf * 4, dtype=float).reshape(nf, 4)
+    full_c = (np.arange(nf * 6).reshape(nf, 2, 3) * (1 + 0.5j)).astype(complex)
+    assert np.array_equal(solver._complete_rows(sol, full_r[sol.local_index]), full_r)
+    out = solver._complete_rows(sol, full_c[sol.local_index])
+    assert out.dtype == complex and np.array_equal(out, full_c)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_segment_exchange_and_row_completion(tmp_path, world):
+    mp.spawn(_worker_exchange, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)

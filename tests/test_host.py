@@ -215,3 +215,120 @@ def test_solve_rejects_non_finite_frequencies():
         for bad in ([1e3, np.nan], [np.inf]):
             with pytest.raises(ValueError, match='infs or NaNs'):
                 sol.solve(np.array(bad))
+
+
+# ------------------------------------------------------------- aggressive early deflation (host build)
+def _aed_host_exe():
+    """tests/host/aed_host: csrc/aed.cuh compiled as sequential host code (the same source the kernel
+    k_hqr_mb runs per warp) + a model of the kernel's batch loop."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not available')
+    src = os.path.join(ROOT, 'tests', 'host', 'aed_host.cu')
+    exe = os.path.join(ROOT, 'tests', 'host', 'aed_host')
+    hdr = os.path.join(ROOT, 'axisym-safe-python_b200', 'csrc', 'aed.cuh')
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.run([nvcc, '-x', 'cu', '-DAED_HOST', '-O2', '-Wno-deprecated-gpu-targets', '-o', exe, src], check=True)
+    return exe
+
+
+def _aed_run(exe, mode, H, l, u, nw, nb=8):
+    import struct
+    import subprocess
+    import tempfile
+    n = H.shape[0]
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, 'in'), os.path.join(d, 'out')
+        with open(fi, 'wb') as f:
+            f.write(struct.pack('5i', n, l, u, nw, nb))
+            f.write(np.asarray(H, dtype=complex).tobytes(order='F'))
+        subprocess.run([exe, mode, fi, fo], check=True)
+        raw = open(fo, 'rb').read()
+    if mode == 'solve':
+        return struct.unpack('5i', raw[:20]), np.frombuffer(raw[20:], dtype=complex)
+    ns, ok, iters = struct.unpack('3i', raw[:12])
+    a = np.frombuffer(raw[12:], dtype=complex)
+    return ns, ok, iters, a[:64].reshape(8, 8), a[64:128].reshape(8, 8), a[128:136], a[136]
+
+
+def _safe_hessenberg(i, nf=2000):
+    import scipy.linalg as la
+    from oracle import safe_oracle as so
+    from axisafe_b200 import cases
+    c = cases.pipe_soil_pml(nf=nf)
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), c['n'])
+    S = so.S_matrix(so.operators(G, c['n']), 2 * np.pi * c['f'][i])
+    Sb, _ = la.matrix_balance(S, permute=False)
+    return np.triu(la.hessenberg(Sb), -1), np.linalg.eigvals(S)
+
+
+def test_aed_window_is_a_similarity():
+    """One AED call (zlaqr2 semantics): Z unitary, Z^H W Z = T with T Hessenberg in its leading ns x ns
+    part and triangular below, the spike vector reduced to one entry, every deflated eigenvalue
+    meeting the spike criterion, spectrum of the window preserved."""
+    exe = _aed_host_exe()
+    eps = np.finfo(float).eps
+    rng = np.random.default_rng(5)
+    H, _ = _safe_hessenberg(700)
+    n = H.shape[0]
+    # a few QR-like iterations so that the trailing window carries converged eigenvalues
+    st, _ = _aed_run(exe, 'solve', H, 0, n - 1, 0)
+    cases_ = []
+    for nw in (8, 5, 3):
+        for u in (n - 1, 60):
+            cases_.append((H, 0, u, nw))
+    R = np.triu(rng.standard_normal([20, 20]) + 1j * rng.standard_normal([20, 20]), -1)
+    R[np.arange(13, 20), np.arange(12, 19)] *= 1e-9          # nearly decoupled tail: deflation must trigger
+    cases_ += [(R, 0, 19, 8), (R, 4, 19, 6), (R, 12, 19, 8)]
+    deflated_total = 0
+    for Hm, l, u, nw in cases_:
+        nw = min(nw, u - l + 1)
+        kw = u - nw + 1
+        ns, ok, iters, T, Z, shift, spike_new = _aed_run(exe, 'window', Hm, l, u, nw)
+        assert ok == 1 and 0 <= ns <= nw
+        T, Z = T[:nw, :nw], Z[:nw, :nw]
+        W = Hm[kw:u + 1, kw:u + 1]
+        scale = np.abs(W).max()
+        assert np.abs(Z.conj().T @ Z - np.eye(nw)).max() < 50 * eps
+        if ns == nw:
+            # nothing deflated: T / Z are the Schur form (the kernel discards them), shifts = its diagonal
+            assert np.abs(np.tril(T, -1)).max() == 0.0
+            assert np.abs(Z.conj().T @ W @ Z - T).max() < 200 * eps * scale
+            assert np.allclose(np.sort_complex(shift[:ns]), np.sort_complex(np.diag(T)))
+            continue
+        deflated_total += nw - ns
+        assert np.abs(Z.conj().T @ W @ Z - T).max() < 200 * eps * scale
+        assert np.abs(np.tril(T[:ns, :ns], -2)).max() == 0.0 if ns else True
+        assert np.abs(np.tril(T[ns:, ns:], -1)).max() == 0.0
+        assert np.abs(T[ns:, :ns]).max() == 0.0 if ns else True
+        spike = Hm[kw, kw - 1] if kw > l else 0.0
+        sv = np.conj(Z[0, :]) * spike                         # Z^H (spike e_1)
+        for j in range(ns, nw):                               # deflated: negligible spike entries
+            foo = abs(T[j, j].real) + abs(T[j, j].imag) or abs(spike)
+            assert abs(sv[j].real) + abs(sv[j].imag) <= 2.1 * max(np.finfo(float).tiny / eps, eps * foo)
+        if ns:
+            assert abs(sv[0] - spike_new) <= 200 * eps * abs(spike)
+            assert np.abs(sv[1:ns]).max() <= 200 * eps * abs(spike) if ns > 1 else True
+        ev = np.sort_complex(np.linalg.eigvals(W))
+        got = np.sort_complex(np.concatenate([np.linalg.eigvals(T[:ns, :ns]) if ns else [], np.diag(T)[ns:]]))
+        assert np.abs(ev - got).max() < 1e-9 * max(np.abs(ev).max(), 1e-300)
+    assert deflated_total > 0
+
+
+@pytest.mark.parametrize('i', [3, 1400])
+def test_aed_solve_matches_zgeev_and_cuts_the_sweeps(i):
+    """The kernel's batch loop with the AED window in front of every batch (host model): same
+    eigenvalues as LAPACK, no failures, less than 70 % of the macro steps of the plain cascade."""
+    from oracle import safe_oracle as so
+    exe = _aed_host_exe()
+    H, ref = _safe_hessenberg(i)
+    n = H.shape[0]
+    plain, ev0 = _aed_run(exe, 'solve', H, 0, n - 1, 0)
+    aed, ev8 = _aed_run(exe, 'solve', H, 0, n - 1, 8)
+    assert plain[4] == 0 and aed[4] == 0
+    assert so.match_eigenvalues(ref, ev0)[1] < 1e-9
+    assert so.match_eigenvalues(ref, ev8)[1] < 1e-9
+    assert aed[2] > 0 and aed[3] > 0.8 * n               # most eigenvalues deflate inside the window
+    assert aed[0] < 0.7 * plain[0], (aed, plain)
