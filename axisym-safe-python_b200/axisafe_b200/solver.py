@@ -990,6 +990,7 @@ def _sweep_large(torch, _native, ops, omega, halo, select=None):
     if C < 1:
         raise MemoryError('2N = %d: one frequency needs %.1f GB of HBM workspace' % (n2, (fixed + slope) / 1e9))
     C = min(C, nloc)
+    C = -(-nloc // -(-nloc // C))                   # equal chunks (148 points as 74 + 74, not 112 + 36)
     k = torch.empty(nloc * n2, dtype=torch.complex128, device='cuda')
     info = torch.zeros(nloc, dtype=torch.int32, device='cuda')
     arg = torch.empty(max(nloc - 1, 0) * n2, dtype=torch.int32, device='cuda')

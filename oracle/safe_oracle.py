@@ -510,6 +510,33 @@ def match_eigenvalues(a, b):
     return perm, rel.max()
 
 
+def match_eigenvalues_large(a, b):
+    """One-to-one nearest matching for thousands of eigenvalues (cfg4 / cfg5 fixtures): nearest
+    neighbours through a k-d tree; the (rare) eigenvalues whose nearest partner is claimed twice are
+    resolved by the greedy matcher on the left-over sets.  Returns (perm, max relative error)."""
+    from scipy.spatial import cKDTree
+    a, b = np.asarray(a), np.asarray(b)
+    tree = cKDTree(np.c_[b.real, b.imag])
+    _, nn = tree.query(np.c_[a.real, a.imag])
+    perm = -np.ones(len(a), int)
+    cnt = np.bincount(nn, minlength=len(b))
+    good = cnt[nn] == 1
+    perm[good] = nn[good]
+    rest_a = np.where(~good)[0]
+    if len(rest_a):
+        rest_b = np.setdiff1d(np.arange(len(b)), perm[good])
+        sub, _ = match_eigenvalues(a[rest_a], b[rest_b])
+        perm[rest_a] = rest_b[sub]
+    rel = abs(a - b[perm]) / np.maximum(abs(a), 1e-300)
+    return perm, rel.max()
+
+
+def eig_tolerance_from_kappa(val, kappa, norm2_balanced, rel=1e-8, backward=256.0):
+    """eig_tolerance with the conditioning data stored in a fixture (tests/golden/big_*.npz)."""
+    bound = backward * np.finfo(float).eps * np.asarray(kappa) * norm2_balanced
+    return np.maximum(rel * abs(np.asarray(val)), bound)
+
+
 def eig_tolerance(S, val, rel=1e-8, backward=256.0):
     """Per-eigenvalue parity tolerance: ``rel*|k|`` (the north-star bar) or, for eigenvalues
     whose own conditioning is worse than that, the first-order perturbation bound

@@ -180,25 +180,28 @@ def test_eigenvalues_vs_reference_zgeev(name, n, kw):
         assert plain == 0                     # flagship: plain 1e-8 bar, no allowance needed
 
 
-VARIANTS = [('AXS_REDUCE_OC', '0'), ('AXS_REDUCE_OC', '8'), ('AXS_REDUCE_OC', '9'), ('AXS_BACKNORM_WY', '0'),
-            ('AXS_BACKNORM_WY_MODES', '32'), ('AXS_HQR_RC', '0'), ('AXS_HQR_S1_OPT', '0'), ('AXS_HQR_S1_OPT', '2'),
-            ('AXS_HQR_WIN', '1'), ('AXS_HQR_STAGES', '2'), ('AXS_HQR_BULGES', '5')]
+VARIANTS = [('reduce_oc', 0), ('reduce_oc', 8), ('backnorm_wy', 0), ('backnorm_wy_modes', 32), ('hqr_stages', 2),
+            ('hqr_bulges', 5), ('hqr_aed', 0), ('hqr_aed', 4), ('hqr_aed', 6)]
 
 
 @pytest.mark.parametrize('var,val', VARIANTS, ids=['%s=%s' % v for v in VARIANTS])
-def test_kernel_variants_keep_parity(var, val, monkeypatch):
-    """Every A/B variant kept behind an environment switch meets the same bar
-    as the default kernels on the flagship case: eigenvalues vs zgeev, mode shapes vs the default."""
+def test_kernel_variants_keep_parity(var, val):
+    """Every kernel-selection switch that is still compiled in (include/axisafe_b200.h, axs_set_tuning)
+    meets the same bar as the default kernels on the flagship case: eigenvalues vs zgeev, mode shapes
+    vs the default."""
     g, c, m, ops, N, pick, omega, nat = _stages('pipe_soil_pml', 0, {})
     n2 = 2 * N
     k0, psi0, info0, _ = nat.eig_sweep(ops, omega)
     k0 = k0.cpu().numpy().reshape(len(pick), n2)
     psi0 = psi0.cpu().numpy().reshape(len(pick), n2, n2)
-    monkeypatch.setenv(var, val)
-    k1, psi1, info1, _ = nat.eig_sweep(ops, omega)
-    assert not info1.cpu().numpy().any()
-    k1 = k1.cpu().numpy().reshape(len(pick), n2)
-    psi1 = psi1.cpu().numpy().reshape(len(pick), n2, n2)
+    old = nat.set_tuning(var, val)
+    try:
+        k1, psi1, info1, _ = nat.eig_sweep(ops, omega)
+        assert not info1.cpu().numpy().any()
+        k1 = k1.cpu().numpy().reshape(len(pick), n2)
+        psi1 = psi1.cpu().numpy().reshape(len(pick), n2, n2)
+    finally:
+        nat.set_tuning(var, old)
     for j in range(len(pick)):
         ref = g['eig_untracked'][j]
         perm, _ = so.match_eigenvalues(ref, k1[j])
@@ -208,6 +211,37 @@ def test_kernel_variants_keep_parity(var, val, monkeypatch):
         a, b = psi0[j][N:], psi1[j][N:, p01]
         err = np.minimum(np.linalg.norm(a - b, axis=0), np.linalg.norm(a + b, axis=0)) / np.linalg.norm(a, axis=0)
         assert err.max() <= 1e-6, (j, err.max())
+
+
+def test_aed_cuts_the_qr_sweeps():
+    """Aggressive early deflation (csrc/aed.cuh, zlaqr2 semantics) in front of every shift batch: the
+    counters of axs_hqr_stats show most eigenvalues deflating inside the window and fewer than 70 % of
+    the macro steps of the plain cascade, with the same spectra (1e-9 against each other, 1e-8 against
+    zgeev elsewhere in this file)."""
+    import torch
+    from axisafe_b200 import cases
+    c = cases.pipe_soil_pml(nf=64)
+    m = _mesh(c)
+    ops, N = m._device_ops, m.no_of_dofs
+    from axisafe_b200 import _native as nat
+    omega = torch.from_numpy(2 * np.pi * c['f']).cuda()
+    res = {}
+    for aed in (0, 8):
+        old = nat.set_tuning('hqr_aed', aed)
+        try:
+            k, _, info, work = nat.eig_sweep(ops, omega, want_modes=False, chunks=1)
+            assert not info.cpu().numpy().any()
+            res[aed] = (k.cpu().numpy().reshape(64, 2 * N), nat.hqr_stats(N, 64, work))
+        finally:
+            nat.set_tuning('hqr_aed', old)
+    (k0, st0), (k8, st8) = res[0], res[8]
+    assert st0[:, 2].sum() == 0 and st0[:, 3].sum() == 0
+    assert (st8[:, 3] > 0.8 * 2 * N).all()
+    assert st8[:, 0].mean() < 0.7 * st0[:, 0].mean(), (st8[:, 0].mean(), st0[:, 0].mean())
+    for i in range(64):
+        assert so.match_eigenvalues(k0[i], k8[i])[1] < 1e-9
+    print('QR macro steps per matrix: %.0f plain, %.0f with AED (window 8): %.1f AED calls, %.1f of %d eigenvalues '
+          'deflated in the window' % (st0[:, 0].mean(), st8[:, 0].mean(), st8[:, 2].mean(), st8[:, 3].mean(), 2 * N))
 
 
 @pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
@@ -282,9 +316,17 @@ def test_solve_api_vs_reference(name, n, kw):
         assert sorted(sol.order[i]) == list(range(2 * N)) or name == 'nguyen'   # a permutation
     # tracked table: every reference entry is one of our eigenvalues at that frequency (our own
     # tracked rows may, like the reference's, duplicate/lose columns - use the native spectra)
+    # flagship cases (BASELINE.json configs 1-2): the north-star bar 1e-8 at EVERY frequency of the
+    # fixture sweep.  Other cases start at 1 Hz / 1 kHz where zgeev itself moves by 1e-5..1e-7 under
+    # 1e-15 perturbations of S (test_eigenvalue_allowance_report): 1e-7, and 1e-4 at the first point.
+    flagship = name in ('pipe_soil_pml', 'free_steel_pipe')
+    beyond = 0
     for i in range(len(c['f'])):
         d = np.abs(g['k'][i][:, None] - sol.k_native[i][None, :]).min(axis=1) / np.abs(g['k'][i])
-        assert d.max() < (1e-4 if i == 0 else 1e-7), (i, d.max())
+        assert d.max() < (1e-8 if flagship else (1e-4 if i == 0 else 1e-7)), (i, d.max())
+        beyond += int((d >= 1e-8).sum())
+    print('%s n=%d: %d of %d tracked reference eigenvalues further than 1e-8 from the GPU spectrum'
+          % (name, n, beyond, g['k'].size))
     _, frac = tracked_agreement(g['k'], sol.k)
     assert frac > 0.7, frac          # see tracked_agreement.__doc__ for why this is not 1.0
     psi = sol.psi_hat
@@ -296,6 +338,49 @@ def test_solve_api_vs_reference(name, n, kw):
     S = so.S_matrix(op, 2 * np.pi * c['f'][i])
     res = np.linalg.norm(S @ psi[i] - psi[i] * sol.k[i], axis=0) / (np.linalg.norm(psi[i], axis=0) * np.abs(sol.k[i]))
     assert np.median(res) < 1e-10
+
+
+def test_eigenvalue_allowance_report():
+    """How many eigenvalues need the conditioning allowance of oracle.eig_tolerance, per fixture, next
+    to LAPACK's own spread: zgeev(S) against zgeev(S (1 + 1e-15 randn)) on the same matrices.  The
+    report goes to gpurun_out/allowance_report.txt (copied to profiles/).  Asserted: the GPU needs the
+    allowance on no more eigenvalues than 2x LAPACK's own spread + 2 per fixture, and on none of the
+    flagship ones."""
+    import os
+    import torch
+    import scipy.linalg as la
+    from axisafe_b200 import _native as nat
+    rng = np.random.default_rng(0)
+    lines = ['fixture                 2N  eigenvalues  gpu>1e-8  zgeev-vs-perturbed-zgeev>1e-8  worst gpu  worst zgeev spread']
+    for name, n, kw in GOLDEN_CASES:
+        g = load_golden(name, n)
+        N = int(g['N'])
+        S = g['S']
+        Sd = torch.from_numpy(np.ascontiguousarray(S.transpose(0, 2, 1))).cuda().reshape(-1)
+        work = nat.reduce_dense(Sd, N, len(S))
+        k, info = nat.hqr(N, len(S), work)
+        assert not info.cpu().numpy().any()
+        k = k.cpu().numpy().reshape(len(S), 2 * N)
+        gpu_bad = lap_bad = 0
+        gpu_worst = lap_worst = 0.0
+        for j in range(len(S)):
+            ref = g['eig_untracked'][j]
+            perm, _ = so.match_eigenvalues(ref, k[j])
+            e = np.abs(ref - k[j][perm]) / np.abs(ref)
+            pert = la.eig(S[j] * (1 + 1e-15 * rng.standard_normal(S[j].shape)))[0]
+            pp, _ = so.match_eigenvalues(ref, pert)
+            ep = np.abs(ref - pert[pp]) / np.abs(ref)
+            gpu_bad += int((e > 1e-8).sum()); lap_bad += int((ep > 1e-8).sum())
+            gpu_worst, lap_worst = max(gpu_worst, e.max()), max(lap_worst, ep.max())
+        lines.append('%-22s %4d  %6d  %8d  %8d  %.2e  %.2e' % ('%s_n%d' % (name, n), 2 * N, k.size, gpu_bad, lap_bad,
+                                                             gpu_worst, lap_worst))
+        assert gpu_bad <= 2 * lap_bad + 2, lines[-1]
+        if name in ('pipe_soil_pml', 'free_steel_pipe'):
+            assert gpu_bad == 0, lines[-1]
+    os.makedirs('gpurun_out', exist_ok=True)
+    with open(os.path.join('gpurun_out', 'allowance_report.txt'), 'w') as fh:
+        fh.write('\n'.join(lines) + '\n')
+    print('\n'.join(lines))
 
 
 def test_full_size_sweep_properties():
