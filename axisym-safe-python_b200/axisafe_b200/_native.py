@@ -335,11 +335,13 @@ def set_tuning(name, value):
 
 
 def hqr_stats(N, nf, work):
-    """axs_hqr_stats: host array [nf, 4] = macro steps, batches, AED calls, AED deflations per matrix."""
+    """axs_hqr_stats: host array [nf, 16] per matrix = macro steps, batches, AED calls, AED deflations, then
+    for each of the four cascade stages the kilo-cycles thread 0 spent in the AED window, in its
+    application and in the sweeps."""
     torch = torch_cuda()
-    st = torch.zeros(nf * 4, dtype=torch.int32, device='cuda')
+    st = torch.zeros(nf * 16, dtype=torch.int32, device='cuda')
     check(lib().axs_hqr_stats(N, nf, _ptr(work.buf), _ptr(st), _stream(torch)), 'axs_hqr_stats')
-    return st.cpu().numpy().reshape(nf, 4)
+    return st.cpu().numpy().reshape(nf, 16)
 
 
 def get_reduction(N, nf, work):

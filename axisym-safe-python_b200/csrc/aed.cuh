@@ -33,47 +33,56 @@ struct AedScratch {
 
 #ifdef AED_HOST
 #define AED_FN inline
+#define AED_INL inline
 #define AED_LANES(v, lo, hi) for (int v = (lo); v < (hi); ++v)
 #define AED_SYNC()
 #define AED_EPS 2.220446049250313e-16
 #define AED_SMALL (2.2250738585072014e-308 / AED_EPS)
+#define AED_RSQRT(x) (1.0 / sqrt(x))
+static AedScratch g_aed;                 // host: one scratch object
 #else
 #define AED_FN __device__ __noinline__
+#define AED_INL __device__ __forceinline__
 #define AED_LANES(v, lo, hi) for (int v = (lo) + lane; v < (hi); v += 32)
 #define AED_SYNC() __syncwarp()
 #define AED_EPS EPS_D
 #define AED_SMALL SMALL_D
+#define AED_RSQRT(x) rsqrt(x)
+// one scratch object per CTA at file scope: the (non-inlined) window routine addresses it with LDS / STS
+// instead of generic loads through a pointer
+__shared__ AedScratch g_aed;
 #endif
 
 // rotation with a real cosine: [c s; -conj(s) c] [x; y] = [r; 0]   (zlartg; make_rot_rc of common.cuh)
-AXS_HD void aed_rot(cplx x, cplx y, double& c, cplx& s, cplx& r) {
+AED_INL void aed_rot(cplx x, cplx y, double& c, cplx& s, cplx& r) {
     const double nx = cabs2(x), ny = cabs2(y), n2 = nx + ny;
     if (ny == 0.0) { c = 1.0; s = mk(0, 0); r = x; }
     else if (nx > 0.0) {
-        const double w = 1.0 / (sqrt(nx) * sqrt(n2));
+        const cplx xy = cmulc(x, y);                      // off the rsqrt chain
+        const double w = AED_RSQRT(nx) * AED_RSQRT(n2);   // 1 / (|x| n)
         c = nx * w;
-        s = cscale(cmulc(x, y), w);
+        s = cscale(xy, w);
         r = cscale(x, n2 * w);
     } else {
-        const double iry = 1.0 / sqrt(ny);
+        const double iry = AED_RSQRT(ny);
         c = 0.0; s = mk(y.x * iry, -y.y * iry); r = mk(ny * iry, 0.0);
     }
 }
 // rows:  [p; q] <- [c s; -conj(s) c] [p; q]
-AXS_HD void aed_rows(double c, cplx s, cplx& p, cplx& q) {
+AED_INL void aed_rows(double c, cplx s, cplx& p, cplx& q) {
     const cplx top = cfma(s, q, cscale(p, c));
     const cplx bot = csub(cscale(q, c), cmulc(p, s));
     p = top; q = bot;
 }
 // columns:  [a b] <- [a b] [c s; -conj(s) c]^H  =  [c a + conj(s) b,  -s a + c b]
-AXS_HD void aed_cols(double c, cplx s, cplx& a, cplx& b) {
+AED_INL void aed_cols(double c, cplx s, cplx& a, cplx& b) {
     const cplx n0 = cfmac(b, s, cscale(a, c));
     const cplx n1 = cfms(s, a, cscale(b, c));
     a = n0; b = n1;
 }
 
 // eigenvalue of [[a11 a12] [a21 a22]] nearer to a22
-AXS_HD cplx aed_shift2(cplx a11, cplx a12, cplx a21, cplx a22) {
+AED_INL cplx aed_shift2(cplx a11, cplx a12, cplx a21, cplx a22) {
     const cplx hd = cscale(csub(a11, a22), 0.5);
     const cplx disc = csqrt_(cadd(cmul(hd, hd), cmul(a12, a21)));
     const cplx mid = cscale(cadd(a11, a22), 0.5);
@@ -81,9 +90,30 @@ AXS_HD cplx aed_shift2(cplx a11, cplx a12, cplx a21, cplx a22) {
     return (cabs1(csub(e2, a22)) < cabs1(csub(e1, a22))) ? e2 : e1;
 }
 
+// zlahqr's test for a negligible subdiagonal entry T(k, k-1) (standard + Ahues-Tisseur)
+AED_INL bool aed_negligible(const AedScratch* S, int nw, int k) {
+    const double sub = cabs1(S->T[k][k - 1]);
+    if (sub <= AED_SMALL) return true;
+    const cplx hkk = S->T[k][k], hk1 = S->T[k - 1][k - 1];
+    double tst = cabs1(hk1) + cabs1(hkk);
+    if (tst == 0.0) {
+        if (k - 2 >= 0) tst += cabs1(S->T[k - 1][k - 2]);
+        if (k + 1 <= nw - 1) tst += cabs1(S->T[k + 1][k]);
+    }
+    if (sub <= AED_EPS * tst) {
+        const double up = cabs1(S->T[k - 1][k]);
+        const double ab = fmax(sub, up), ba = fmin(sub, up);
+        const double dd = cabs1(csub(hk1, hkk));
+        const double aa = fmax(cabs1(hkk), dd), bb = fmin(cabs1(hkk), dd);
+        const double sm = aa + ab;
+        if (ba * (ab / sm) <= fmax(AED_SMALL, AED_EPS * (bb * (aa / sm)))) return true;
+    }
+    return false;
+}
+
 // One similarity rotation of the window in the plane (k, k+1): rows k, k+1 of the columns
 // jlo .. nw-1, then columns k, k+1 of the rows 0 .. ihi, and columns k, k+1 of Z.
-AED_FN void aed_apply(AedScratch* S, int nw, int k, int jlo, int ihi, double c, cplx s, int lane) {
+AED_INL void aed_apply(AedScratch* S, int nw, int k, int jlo, int ihi, double c, cplx s, int lane) {
     AED_LANES(j, jlo, nw) aed_rows(c, s, S->T[k][j], S->T[k + 1][j]);
     AED_SYNC();
     AED_LANES(i, 0, 2 * nw) {
@@ -94,8 +124,9 @@ AED_FN void aed_apply(AedScratch* S, int nw, int k, int jlo, int ihi, double c, 
 }
 
 // H: packed column-major Hessenberg matrix (hcol_off), active block [l, u], window kw = u-nw+1 .. u.
-AED_FN void aed_window(const cplx* H, int l, int u, int nw, AedScratch* S, int lane)
+AED_FN void aed_window(const cplx* H, int l, int u, int nw, int lane)
 {
+    AedScratch* const S = &g_aed;
     const int kw = u - nw + 1;
     AED_LANES(idx, 0, nw * nw) {
         const int j = idx / nw, i = idx - j * nw;
@@ -108,29 +139,17 @@ AED_FN void aed_window(const cplx* H, int l, int u, int nw, AedScratch* S, int l
     // ---- 1. Schur form of the window (implicit single-shift QR, zlahqr tests) -----------------
     int iu = nw - 1, its = 0, total = 0, ok = 1;
     while (iu >= 1) {
+        // largest k <= iu with a negligible subdiagonal entry (device: lane k tests entry k, one ballot)
         int il = 0;
-        for (int k = iu; k >= 1; --k) {
-            const double sub = cabs1(S->T[k][k - 1]);
-            bool neg = false;
-            if (sub <= AED_SMALL) neg = true;
-            else {
-                const cplx hkk = S->T[k][k], hk1 = S->T[k - 1][k - 1];
-                double tst = cabs1(hk1) + cabs1(hkk);
-                if (tst == 0.0) {
-                    if (k - 2 >= 0) tst += cabs1(S->T[k - 1][k - 2]);
-                    if (k + 1 <= nw - 1) tst += cabs1(S->T[k + 1][k]);
-                }
-                if (sub <= AED_EPS * tst) {
-                    const double up = cabs1(S->T[k - 1][k]);
-                    const double ab = fmax(sub, up), ba = fmin(sub, up);
-                    const double dd = cabs1(csub(hk1, hkk));
-                    const double aa = fmax(cabs1(hkk), dd), bb = fmin(cabs1(hkk), dd);
-                    const double sm = aa + ab;
-                    if (ba * (ab / sm) <= fmax(AED_SMALL, AED_EPS * (bb * (aa / sm)))) neg = true;
-                }
-            }
-            if (neg) { il = k; break; }
+#ifdef AED_HOST
+        for (int k = iu; k >= 1 && il == 0; --k) if (aed_negligible(S, nw, k)) il = k;
+#else
+        {
+            const bool neg = (lane >= 1 && lane <= iu) ? aed_negligible(S, nw, lane) : false;
+            const unsigned m = __ballot_sync(0xffffffffu, neg);
+            il = m ? 31 - __clz(m) : 0;
         }
+#endif
         AED_SYNC();                                       // every lane has read the subdiagonal
         if (il > 0) { AED_LANES(q, 0, 1) S->T[il][il - 1] = mk(0, 0); }
         if (il == iu) { --iu; its = 0; AED_SYNC(); continue; }

@@ -96,11 +96,32 @@ extern "C" int axs_get_tuning(const char* name, int* value)
     return 0;
 }
 
+// ---- dynamic shared-memory opt-in, once per (kernel, device) ---------------------------------------
+#include <mutex>
+extern "C" int axs_smem_once(const void* kernel, size_t bytes)
+{
+    struct Entry { const void* k; int dev; size_t bytes; };
+    static Entry table[256];
+    static int used = 0;
+    static std::mutex mu;
+    int dev = 0;
+    AXS_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    Entry* e = nullptr;
+    for (int i = 0; i < used; ++i)
+        if (table[i].k == kernel && table[i].dev == dev) { e = &table[i]; break; }
+    if (e && e->bytes >= bytes) return 0;
+    AXS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (!e && used < 256) { e = &table[used++]; e->k = kernel; e->dev = dev; }
+    if (e) e->bytes = bytes;
+    return 0;
+}
+
 // workspace views advanced by f0 frequencies (launch chunking)
 static AxsWork work_at(AxsWork w, int n2, long long f0)
 {
     w.A += f0 * n2 * n2; w.Hc += f0 * hcol_size(n2); w.Hr += f0 * hrow_size(n2); w.tau += f0 * n2;
-    w.scale += f0 * n2; w.ucur += f0; w.Hp += f0 * hcol_size(n2); w.stats += 4 * f0;
+    w.scale += f0 * n2; w.ucur += f0; w.Hp += f0 * hcol_size(n2); w.stats += AXS_QR_STATS * f0;
     return w;
 }
 static AxsWorkBig workbig_at(AxsWorkBig w, int n2, long long f0)
@@ -321,7 +342,7 @@ extern "C" int axs_hqr_stats(int N, int nf, const void* work, int* stats, void* 
     if (is_big(N)) return -1;                              /* counters exist for the shared-memory path only */
     AxsWork wk;
     axs_work_layout(2 * N, nf, (void*)work, &wk);
-    AXS_CUDA_OK(cudaMemcpyAsync(stats, wk.stats, (size_t)nf * 4 * sizeof(int), cudaMemcpyDeviceToDevice,
+    AXS_CUDA_OK(cudaMemcpyAsync(stats, wk.stats, (size_t)nf * AXS_QR_STATS * sizeof(int), cudaMemcpyDeviceToDevice,
                                 (cudaStream_t)stream));
     return 0;
 }

@@ -166,17 +166,13 @@ __device__ __forceinline__ void gen_rot(cplx x, cplx y, cplx& a, cplx& b, cplx& 
 
 #define AXS_CUDA_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
-// Opt-in to more than 48 KB of dynamic shared memory ONCE per (kernel instance, device) instead of
-// on every launch: the macro keeps the largest size it has set per device in a static of the call site.
+// Opt-in to more than 48 KB of dynamic shared memory ONCE per (kernel, device) instead of on every
+// launch: axs_smem_once (api.cu) remembers the largest size it has set for a kernel on a device and
+// only calls cudaFuncSetAttribute when a launch needs more (the attribute is never lowered).
+extern "C" int axs_smem_once(const void* kernel, size_t bytes);
 #define AXS_SMEM_ONCE(bytes, ...) do {                                                              \
-        static size_t axs_done_[32];                                                                 \
-        int axs_dev_ = 0;                                                                            \
-        AXS_CUDA_OK(cudaGetDevice(&axs_dev_));                                                       \
-        const size_t axs_b_ = (size_t)(bytes);                                                       \
-        if (axs_dev_ < 0 || axs_dev_ >= 32 || axs_done_[axs_dev_] < axs_b_) {                        \
-            AXS_CUDA_OK(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)axs_b_)); \
-            if (axs_dev_ >= 0 && axs_dev_ < 32) axs_done_[axs_dev_] = axs_b_;                       \
-        }                                                                                            \
+        const int axs_rc_ = axs_smem_once((const void*)(__VA_ARGS__), (size_t)(bytes));              \
+        if (axs_rc_) return axs_rc_;                                                                 \
     } while (0)
 
 // Kernel-selection switches.  Read ONCE from the environment when the library is first used
@@ -201,6 +197,7 @@ extern "C" const AxsTuning* axs_tuning(void);
 #define AXS_MAX_SMALL_N2 166
 
 // workspace layout for nf problems of size n2 (all offsets 256-B aligned)
+#define AXS_QR_STATS 16
 struct AxsWork {
     cplx*   A;      // [nf][n2*n2]  dense column-major work matrix (S -> reflectors below subdiag)
     cplx*   Hc;     // [nf][hcol_size] packed column-major Hessenberg (input of the QR kernel)
@@ -209,7 +206,8 @@ struct AxsWork {
     double* scale;  // [nf][n2]  balancing factors D
     int*    ucur;   // [nf]      active-window top between QR stages
     cplx*   Hp;     // [nf][hcol_size] leading block parked between QR stages (Hc stays intact)
-    int*    stats;  // [nf][4]   QR counters per matrix: macro steps, batches, AED calls, AED deflations
+    int*    stats;  // [nf][AXS_QR_STATS] QR counters per matrix: macro steps, batches, AED calls, AED deflations,
+                    //           then per stage (4 x 3) kilo-cycles of thread 0 in the AED window, its application, the sweeps
 };
 
 static inline long long axs_align(long long x) { return (x + 255) & ~255LL; }
@@ -239,7 +237,7 @@ static inline long long axs_work_layout(int n2, int nf, void* base, AxsWork* w) 
     if (w) w->Hp = (cplx*)(b + off);
     off += szHc;
     if (w) w->stats = (int*)(b + off);
-    off += axs_align((long long)nf * 4 * sizeof(int));
+    off += axs_align((long long)nf * AXS_QR_STATS * sizeof(int));
     return off;
 }
 

@@ -346,7 +346,7 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
     __shared__ cplx s_shift[AED_MAX > MB_MAX ? AED_MAX : MB_MAX];
     __shared__ cplx s_ra[2][MB_MAX], s_rb[2][MB_MAX];
     __shared__ cplx s_rr[2][MB_MAX];
-    __shared__ AedScratch s_aed;
+#define s_aed g_aed                                       /* file-scope shared scratch of csrc/aed.cuh */
 
     const cplx* Hg = (first_stage ? Hc_all : Hp_all) + (long long)f * hsz;
     cplx* Hpark = Hp_all + (long long)f * hsz;
@@ -358,6 +358,8 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
 
     int its = 0, failed = 0;
     int n_macro = 0, n_batch = 0, n_aed = 0, n_aed_defl = 0;
+    long long clk[4] = {0, 0, 0, 0}, clk0 = 0;            // thread 0: cycles in the AED window / its application / the sweeps
+#define AED_CLK(i) if (tid == 0) { const long long c_ = clock64(); if (i) clk[i] += c_ - clk0; clk0 = c_; }
     bool have_shifts = false;                             // s_shift[0..ns_aed) hold the AED window's eigenvalues
     int ns_aed = 0;
     while (u >= m_stop) {
@@ -408,8 +410,10 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
             __syncthreads();                              // H(l, l-1) = 0 is visible
             const int nw = (aed_nw < u - l + 1) ? aed_nw : u - l + 1;
             const int kw = u - nw + 1;
-            if (tid < 32) aed_window(H, l, u, nw, &s_aed, tid);
+            AED_CLK(0)
+            if (tid < 32) aed_window(H, l, u, nw, tid);
             __syncthreads();
+            AED_CLK(1)
             ++n_aed;
             const int aed_ok = s_aed.ok;
             const int ns = s_aed.ns, nd = nw - ns;        // undeflated / deflated window eigenvalues
@@ -455,6 +459,7 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
                 ns_aed = ns;
             }
             __syncthreads();
+            AED_CLK(2)
             if (aed_ok && nd > 0) {
                 // LAPACK's "nibble": a productive window is followed by another one, not by a sweep
                 if (u < l + 1 || nd * 100 >= 14 * nw) continue;
@@ -532,6 +537,7 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
             }
         }
         n_macro += nsteps; ++n_batch;
+        AED_CLK(0)
         for (int t = 0; t < nsteps; ++t) {
             const int cur = t & 1, nxt = cur ^ 1;
             // ---- phase R: row rotations ---------------------------------------------------------
@@ -599,14 +605,17 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
             }
             __syncthreads();
         }
+        AED_CLK(3)
     }
     if (tid == 0) {
         info[f] = first_stage ? failed : info[f] + failed;
         ucur[f] = u;
         if (stats) {                                      // per-matrix counters (axs_hqr_stats): macro steps,
-            int* sp = stats + 4 * (long long)f;           // batches, AED calls, eigenvalues deflated by AED
-            if (first_stage) { sp[0] = n_macro; sp[1] = n_batch; sp[2] = n_aed; sp[3] = n_aed_defl; }
-            else { sp[0] += n_macro; sp[1] += n_batch; sp[2] += n_aed; sp[3] += n_aed_defl; }
+            int* sp = stats + AXS_QR_STATS * (long long)f;   // batches, AED calls, eigenvalues deflated by AED,
+            const int stg = first_stage ? 0 : (NT == 512 ? 1 : NT == 384 ? 2 : 3);   // kilo-cycles: window / apply / sweeps per stage
+            if (first_stage) for (int q = 0; q < AXS_QR_STATS; ++q) sp[q] = 0;
+            sp[0] += n_macro; sp[1] += n_batch; sp[2] += n_aed; sp[3] += n_aed_defl;
+            sp[4 + 3 * stg] += (int)(clk[1] >> 10); sp[5 + 3 * stg] += (int)(clk[2] >> 10); sp[6 + 3 * stg] += (int)(clk[3] >> 10);
         }
     }
     if (u >= 0)                                           // park the remaining leading block

@@ -407,7 +407,9 @@ def qr_counters(nat, N, nloc, work):
     try:
         st = nat.hqr_stats(N, nloc, work)
         return {'macro_steps': float(st[:, 0].mean()), 'batches': float(st[:, 1].mean()),
-                'aed_calls': float(st[:, 2].mean()), 'aed_deflated': float(st[:, 3].mean())}
+                'aed_calls': float(st[:, 2].mean()), 'aed_deflated': float(st[:, 3].mean()),
+                'kcycles_per_stage_window_apply_sweeps': [[float(st[:, 4 + 3 * g + q].mean()) for q in range(3)]
+                                                          for g in range(4)]}
     except Exception as exc:                                            # pragma: no cover
         return {'error': str(exc)}
 

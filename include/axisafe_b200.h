@@ -116,9 +116,10 @@ int axs_modes(int N, int hb, const axs_cplx* Cb, const axs_cplx* K6d, int nf,
  * Hessenberg matrix H [nf][n2][n2] (dense column-major, zeros below the subdiagonal). */
 int axs_get_reduction(int N, int nf, const void* work, double* scale, axs_cplx* H, void* stream);
 /* Counters of the QR stage left in the workspace by axs_hqr (shared-memory path, 2N <= axs_max_small_n2()):
- * stats [nf][4] (device, int32) = macro steps, shift batches, aggressive-early-deflation calls,
+ * stats [nf][16] (device, int32) = macro steps, shift batches, aggressive-early-deflation calls,
  * eigenvalues deflated inside those calls - the iteration counts LAPACK's zhseqr (zlaqr0/zlaqr3
- * behind solver.py:136) would report through its own counters. */
+ * behind solver.py:136) would report through its own counters - followed, for each of the four
+ * cascade stages, by the kilo-cycles one thread spent in the AED window, applying it, and sweeping. */
 int axs_hqr_stats(int N, int nf, const void* work, int* stats, void* stream);
 
 /* Kernel-selection switches (A/B measurements and the variant parity tests).  Every switch is read

@@ -15,6 +15,8 @@
 #include <vector>
 
 #define MB_D 3
+static long g_iters = 0;
+static int g_stage[4] = {0, 0, 0, 0}, g_mstage[4] = {0, 0, 0, 0};
 #define MB_MAX 8
 typedef std::vector<cplx> Packed;
 static inline cplx& HP(Packed& H, int i, int j) { return H[hcol_off(j) + i]; }
@@ -77,11 +79,15 @@ static void solve(Packed& H, int n, int aed_nw, int bmax, std::vector<cplx>& eig
         ++its;
         if (its > 120) { eig[u] = HP(H, u, u); ++failed; --u; its = 0; have_shifts = false; continue; }
         have_shifts = false;
-        if (aed_nw >= 2 && u - l + 1 >= 3) {
+        static int p_nibble = getenv("AED_NIBBLE") ? atoi(getenv("AED_NIBBLE")) : 14;
+        static int p_minm = getenv("AED_MINM") ? atoi(getenv("AED_MINM")) : 3;
+        static int p_every = getenv("AED_EVERY") ? atoi(getenv("AED_EVERY")) : 1;
+        static int batch_ctr = 0;
+        if (aed_nw >= 2 && u - l + 1 >= p_minm && (batch_ctr++ % p_every) == 0) {
             const int nw = (aed_nw < u - l + 1) ? aed_nw : u - l + 1;
             const int kw = u - nw + 1;
-            aed_window(H.data(), l, u, nw, &S, 0);
-            ++n_aed;
+            aed_window(H.data(), l, u, nw, 0); S = g_aed;
+            ++n_aed; g_stage[u >= 116 ? 0 : u >= 93 ? 1 : u >= 79 ? 2 : 3]++; g_iters += S.iters; if (getenv("AED_TRACE")) fprintf(stderr, "aed u=%d l=%d nw=%d iters=%d ns=%d\n", u, l, nw, S.iters, S.ns);
             const int ok = S.ok, ns = S.ns, nd = nw - ns;
             if (ok && nd > 0) {
                 for (int i = l; i < kw; ++i) {
@@ -108,7 +114,7 @@ static void solve(Packed& H, int n, int aed_nw, int bmax, std::vector<cplx>& eig
                 ns_aed = ns;
             }
             if (ok && nd > 0) {
-                if (u < l + 1 || nd * 100 >= 14 * nw) continue;
+                if (u < l + 1 || (p_nibble > 0 && nd * 100 >= p_nibble * nw)) continue;
             }
         }
         const int m = u - l + 1;
@@ -148,6 +154,7 @@ static void solve(Packed& H, int n, int aed_nw, int bmax, std::vector<cplx>& eig
         }
         for (int b = 0; b < nb; ++b) sweep(H, l, u, s_shift[b]);
         n_macro += (m - 1) + (nb - 1) * MB_D;
+        g_mstage[u >= 116 ? 0 : u >= 93 ? 1 : u >= 79 ? 2 : 3] += (m - 1) + (nb - 1) * MB_D;
         ++n_batch;
     }
     st[0] = n_macro; st[1] = n_batch; st[2] = n_aed; st[3] = n_aed_defl; st[4] = failed;
@@ -172,7 +179,7 @@ int main(int argc, char** argv)
     if (!strcmp(argv[1], "window")) {
         AedScratch S;
         memset(&S, 0, sizeof S);
-        aed_window(H.data(), l, u, nw, &S, 0);
+        aed_window(H.data(), l, u, nw, 0); S = g_aed;
         int o[3] = {S.ns, S.ok, S.iters};
         fwrite(o, sizeof(int), 3, fo);
         for (int i = 0; i < AED_MAX; ++i) fwrite(S.T[i], sizeof(cplx), AED_MAX, fo);
@@ -183,6 +190,7 @@ int main(int argc, char** argv)
         std::vector<cplx> eig(n);
         int st[5];
         solve(H, n, nw, nb, eig, st);
+        if (getenv("AED_STAGES")) fprintf(stderr, "STAGES macro %d %d %d %d aed %d %d %d %d iters %ld\n", g_mstage[0], g_mstage[1], g_mstage[2], g_mstage[3], g_stage[0], g_stage[1], g_stage[2], g_stage[3], g_iters);
         fwrite(st, sizeof(int), 5, fo);
         fwrite(eig.data(), sizeof(cplx), n, fo);
     }
