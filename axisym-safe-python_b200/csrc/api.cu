@@ -49,7 +49,7 @@ static AxsTuning* tuning_mut(void)
         t.hqr_stages = env_int("AXS_HQR_STAGES", 4);
         t.hqr_bulges = env_int("AXS_HQR_BULGES", 8);
         t.hqr_small_direct = env_int("AXS_HQR_SMALL_DIRECT", 1);
-        t.hqr_aed = env_int("AXS_HQR_AED", 8);
+        t.hqr_aed = env_int("AXS_HQR_AED", 0);      // measured on B200: halves the macro steps, but the serial window costs more than it saves
         t.backnorm_wy = env_int("AXS_BACKNORM_WY", 1);
         t.backnorm_wy_modes = env_int("AXS_BACKNORM_WY_MODES", 64);
         t.bpsi_tiled = env_int("AXS_BPSI_TILED", 1);

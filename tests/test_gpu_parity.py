@@ -181,7 +181,7 @@ def test_eigenvalues_vs_reference_zgeev(name, n, kw):
 
 
 VARIANTS = [('reduce_oc', 0), ('reduce_oc', 8), ('backnorm_wy', 0), ('backnorm_wy_modes', 32), ('hqr_stages', 2),
-            ('hqr_bulges', 5), ('hqr_aed', 0), ('hqr_aed', 4), ('hqr_aed', 6)]
+            ('hqr_bulges', 5), ('hqr_aed', 8), ('hqr_aed', 4), ('hqr_aed', 6)]
 
 
 @pytest.mark.parametrize('var,val', VARIANTS, ids=['%s=%s' % v for v in VARIANTS])
