@@ -10,7 +10,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ['api.cu', 'assemble.cu', 'eig_small.cu', 'eig_reduce.cu', 'eig_backx.cu', 'eig_big.cu', 'track.cu']
+SOURCES = ['api.cu', 'assemble.cu', 'eig_small.cu', 'eig_reduce.cu', 'eig_backx.cu', 'eig_big.cu', 'eig_bigred.cu', 'track.cu']
 HEADERS = ['common.cuh', 'aed.cuh', os.path.join('..', '..', 'include', 'axisafe_b200.h')]
 OUT = os.path.join(HERE, 'axisafe_b200', '_lib', 'libaxisafe_b200.so')
 OBJ = os.path.join(HERE, 'build')

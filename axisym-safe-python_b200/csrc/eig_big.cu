@@ -25,6 +25,8 @@
 //   k_norm_big    un-balanced vectors -> psi = v / sqrt(2k u^T K6 u + u^T C u), psi_hat layout.
 #include "common.cuh"
 #include <stdlib.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 // =========================================================================================
 // k_reduce_big
@@ -47,7 +49,7 @@ __device__ __forceinline__ double block_sum_d(double v, double* red, int warp, i
 __global__ void __launch_bounds__(RB_NT, 1)
 k_reduce_big(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict__ Cb,
              const cplx* __restrict__ Mb, const cplx* __restrict__ K1c, const cplx* __restrict__ K6d,
-             const double* __restrict__ omega, const cplx* __restrict__ S_in, AxsWorkBig wk)
+             const double* __restrict__ omega, const cplx* __restrict__ S_in, AxsWorkBig wk, int balance_only)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[2 * RB_NW];
@@ -125,6 +127,7 @@ k_reduce_big(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict
     }
     for (int i = tid; i < n; i += RB_NT) wk.scale[(long long)f * n + i] = d[i];
     __syncthreads();
+    if (balance_only) return;                              // the blocked reduction (eig_bigred.cu) takes over
 
     // ---- phase C: Householder reduction to Hessenberg form -------------------------------
     // One read + one write of the trailing matrix per reflector: the rank-2 update of reflector k
@@ -368,6 +371,11 @@ k_reduce_big(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict
 #define HB_WORKERS (HB_NT - 32)
 #define HB_ITEMS 2                      // ceil(HB_NB * HB_WS / HB_WORKERS)
 
+// A thread-block CLUSTER of CL CTAs (1, 2, 4 or 8; launch attribute) works on one matrix: rank 0 chases
+// the bulge chain through the diagonal window (phase D, serial), then all CL CTAs share the tiles of the
+// off-diagonal strips (phase O, the bulk of the flops for 2N in the thousands); the recorded rotations
+// travel through distributed shared memory, the matrix through L2 with a cluster barrier on either side.
+// With a batch that fills the GPU by itself the launcher uses CL = 1 (one CTA per matrix, as before).
 __global__ void __launch_bounds__(HB_NT, 2)
 k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_all,
           int* __restrict__ info, int* __restrict__ ucur)
@@ -379,7 +387,10 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
     __shared__ cplx s_ra[2][HB_NB], s_rb[2][HB_NB];
     __shared__ cplx s_rr[2][HB_NB];
     __shared__ int s_l;
-    const int f = blockIdx.x, tid = threadIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
+    const int f = blockIdx.x / CL, tid = threadIdx.x;
+    const bool lead = (crank == 0);
     cplx* Hg = H_all + (long long)f * hcol_size(n);
     cplx* eig = eig_all + (long long)f * n;
 #define GH(i, j) Hg[hcol_off(j) + (i)]
@@ -413,16 +424,18 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
         }
         __syncthreads();
         const int l = s_l;
-        if (l > 0 && tid == 0) GH(l, l - 1) = mk(0, 0);
+        // (every CTA of the cluster takes the same decisions from the same global data; only the lead writes.
+        // A subdiagonal entry found negligible stays negligible for the others whether or not they already see the zero.)
+        if (l > 0 && tid == 0 && lead) GH(l, l - 1) = mk(0, 0);
         if (l == u) {
-            if (tid == 0) eig[u] = GH(u, u);
+            if (tid == 0 && lead) eig[u] = GH(u, u);
             --u; its = 0;
             __syncthreads();
             continue;
         }
         ++its;
         if (its > 120) {
-            if (tid == 0) eig[u] = GH(u, u);
+            if (tid == 0 && lead) eig[u] = GH(u, u);
             ++failed; --u; its = 0;
             __syncthreads();
             continue;
@@ -462,7 +475,8 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
             const int wlo = (kmin - 1 > l) ? kmin - 1 : l;
             const int whi = (kmax + 2 < u) ? kmax + 2 : u;
             const int ws = whi - wlo + 1;
-            // ---- phase D: chase the chain through the diagonal window -------------------------
+            // ---- phase D: chase the chain through the diagonal window (lead CTA) ----------------
+            if (lead) {
             for (int idx = tid; idx < ws * ws; idx += HB_NT) {
                 const int j = idx / ws, i = idx - j * ws;
                 buf[j * HB_WLD + i] = (i <= j + 1) ? GH(wlo + i, wlo + j) : mk(0, 0);
@@ -546,9 +560,21 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
                 if (i <= j + 1) GH(wlo + i, wlo + j) = buf[j * HB_WLD + i];
             }
             __syncthreads();
+            }                                              // lead
             const int nt = t1 - t0;
+            if (CL > 1) {
+                // the window is back in global memory and the rotations are recorded: hand both to the cluster
+                __threadfence();
+                cluster.sync();
+                if (!lead) {
+                    const cplx* src = cluster.map_shared_rank(&s_rec[0][0][0], 0);
+                    cplx* dst = &s_rec[0][0][0];
+                    for (int idx = tid; idx < nt * HB_NB * 2; idx += HB_NT) dst[idx] = src[idx];
+                    __syncthreads();
+                }
+            }
             // ---- phase O (right): rows wlo..whi of the columns right of the window ------------
-            for (int c0 = whi + 1; c0 <= u; c0 += HB_TILE) {
+            for (int c0 = whi + 1 + crank * HB_TILE; c0 <= u; c0 += CL * HB_TILE) {
                 const int nc = (u - c0 + 1 < HB_TILE) ? u - c0 + 1 : HB_TILE;
                 for (int idx = tid; idx < nc * ws; idx += HB_NT) {
                     const int cid = idx / ws, rl = idx - cid * ws;
@@ -582,7 +608,7 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
                 __syncthreads();
             }
             // ---- phase O (up): columns wlo..whi of the rows above the window -------------------
-            for (int r0 = l; r0 < wlo; r0 += HB_TILE) {
+            for (int r0 = l + crank * HB_TILE; r0 < wlo; r0 += CL * HB_TILE) {
                 const int nr = (wlo - r0 < HB_TILE) ? wlo - r0 : HB_TILE;
                 for (int idx = tid; idx < nr * ws; idx += HB_NT) {
                     const int cl = idx / nr, rid = idx - cl * nr;
@@ -615,11 +641,15 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
                 }
                 __syncthreads();
             }
+            if (CL > 1) {                                  // strips of all CTAs are in global memory; the lead
+                __threadfence();                           // may overwrite its rotation record
+                cluster.sync();
+            }
         }
 #undef WH
     }
 #undef GH
-    if (tid == 0) { info[f] = failed; ucur[f] = u; }
+    if (tid == 0 && lead) { info[f] = failed; ucur[f] = u; }
 }
 
 static size_t hqr_big_smem() { return (size_t)HB_WS * HB_TLD * sizeof(cplx); }
@@ -1020,14 +1050,34 @@ extern "C" int axs_launch_hqr_stages(int n, int nf, int m_first, cplx* Hp, cplx*
                                      int* stats, cudaStream_t st);
 extern "C" int axs_hqr_stage_capacity(int per_sm);
 
+extern "C" int axs_launch_reduce_blocked(int N, int hb, const cplx* K0s, const cplx* Cb, const cplx* Mb,
+                                         const cplx* K1c, const cplx* K6d, const double* omega, int nf,
+                                         const cplx* S_in, AxsWorkBig wk, cudaStream_t st);
+
+// S(w), |a|^2 tables and the zgebal scaling only (phases A + B of k_reduce_big)
+extern "C" int axs_launch_balance_big(int N, int hb, const cplx* K0s, const cplx* Cb, const cplx* Mb,
+                                      const cplx* K1c, const cplx* K6d, const double* omega, int nf,
+                                      const cplx* S_in, AxsWorkBig wk, cudaStream_t st)
+{
+    const int n = 2 * N;
+    const size_t smem = (size_t)n * sizeof(cplx);
+    AXS_SMEM_ONCE(smem, k_reduce_big);
+    k_reduce_big<<<nf, RB_NT, smem, st>>>(N, hb, K0s, Cb, Mb, K1c, K6d, omega, S_in, wk, 1);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int axs_launch_reduce_big(int N, int hb, const cplx* K0s, const cplx* Cb, const cplx* Mb,
                                      const cplx* K1c, const cplx* K6d, const double* omega, int nf,
                                      const cplx* S_in, AxsWorkBig wk, cudaStream_t st)
 {
     const int n = 2 * N;
+    // default: blocked compact-WY reduction with DMMA trailing updates over the whole GPU (eig_bigred.cu);
+    // tuning big_blocked = 0: one CTA per frequency, unblocked (k_reduce_big)
+    if (axs_tuning()->big_blocked)
+        return axs_launch_reduce_blocked(N, hb, K0s, Cb, Mb, K1c, K6d, omega, nf, S_in, wk, st);
     const size_t smem = (size_t)n * sizeof(cplx);
     AXS_SMEM_ONCE(smem, k_reduce_big);
-    k_reduce_big<<<nf, RB_NT, smem, st>>>(N, hb, K0s, Cb, Mb, K1c, K6d, omega, S_in, wk);
+    k_reduce_big<<<nf, RB_NT, smem, st>>>(N, hb, K0s, Cb, Mb, K1c, K6d, omega, S_in, wk, 0);
     return (int)cudaGetLastError();
 }
 
@@ -1036,8 +1086,29 @@ extern "C" int axs_launch_hqr_big(int n, int nf, cplx* eig, int* info, AxsWorkBi
     const int m2 = axs_hqr_stage_capacity(2);            // what the 2-CTA/SM shared-memory stage can hold
     const size_t smem = hqr_big_smem();
     AXS_SMEM_ONCE(smem, k_hqr_big);
-    k_hqr_big<<<nf, HB_NT, smem, st>>>(n, m2, wk.Hc, eig, info, wk.ucur);
-    cudaError_t e = cudaGetLastError();
+    // cluster size: the CTAs of a cluster share the strip tiles of one matrix; a batch that fills the GPU
+    // (2 CTAs per SM) keeps one CTA per matrix
+    int sms = 148, dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int CL = 1;
+    while (CL < 8 && (long long)nf * CL * 2 <= sms && CL * 2 * HB_TILE <= n) CL *= 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nf * CL), 1, 1);
+    cfg.blockDim = dim3(HB_NT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cplx* Hc = wk.Hc;
+    int* ucur = wk.ucur;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_hqr_big, n, m2, Hc, eig, info, ucur);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     return axs_launch_hqr_stages(n, nf, m2, wk.Hc, eig, info, wk.ucur, nullptr, st);
 }

@@ -105,6 +105,39 @@ def test_coated_pipe_stages_vs_oracle(epl, order):
         assert np.abs(amax[p] - P.max(axis=1)).max() < 1e-9 * max(P.max(), 1.0)
 
 
+def test_blocked_reduction_equals_unblocked():
+    """The blocked compact-WY Hessenberg reduction with DMMA trailing updates (csrc/eig_bigred.cu, the
+    default) and the one-CTA-per-frequency unblocked kernel (tuning big_blocked = 0) are two roundings of
+    the same similarity: identical scaling factors, |H| equal in norm, spectra equal to 1e-10, and the
+    same eigenvectors after the back-transformation (which reads the reflectors either one leaves)."""
+    import torch
+    from axisafe_b200 import _native as nat
+    c, m = _coated(2, 8, 3)
+    ops, N = m._device_ops, m.no_of_dofs
+    n2 = 2 * N
+    om = torch.from_numpy(2 * np.pi * c['f']).cuda()
+    res = {}
+    for blocked in (1, 0):
+        old = nat.set_tuning('big_blocked', blocked)
+        try:
+            k, psi, info, work = nat.eig_sweep(ops, om)
+            scale, H = nat.get_reduction(N, len(om), work)
+            assert not info.cpu().numpy().any()
+            res[blocked] = (k.cpu().numpy().reshape(-1, n2), psi.cpu().numpy().reshape(-1, n2, n2), scale, H)
+        finally:
+            nat.set_tuning('big_blocked', old)
+    (k1, p1, s1, H1), (k0, p0, s0, H0) = res[1], res[0]
+    assert np.array_equal(s1, s0)
+    for j in range(len(om)):
+        assert np.abs(np.tril(H1[j], -2)).max() == 0.0
+        assert abs(np.linalg.norm(H1[j]) - np.linalg.norm(H0[j])) <= 1e-12 * np.linalg.norm(H0[j])
+        perm, err = so.match_eigenvalues(k0[j], k1[j])
+        assert err < 1e-10
+        e = so.mode_shape_error(p0[j][N:], p1[j][N:][:, perm])
+        gap = np.array([np.sort(np.abs(k0[j] - v))[1] / abs(v) for v in k0[j]])
+        assert np.all((e < 1e-6) | (gap < 1e-3))
+
+
 def test_solve_api_large_chunked(monkeypatch):
     """solve() on a 2N = 294 mesh: chunked sweep (forced 3-frequency chunks) == one-shot sweep,
     tracked table and psi_hat consistent, energy_ratio runs on the device-resident shapes."""
