@@ -56,6 +56,7 @@ static AxsTuning* tuning_mut(void)
         t.track_fma = env_int("AXS_TRACK_FMA", 0);
         t.big_blocked = env_int("AXS_BIG_BLOCKED", 1);
         t.big_panel = env_int("AXS_BIG_PANEL", 32);
+        t.big_qr_cluster = env_int("AXS_BIG_QR_CLUSTER", 0);
         init = true;
     }
     return &t;
@@ -78,6 +79,7 @@ static int* tuning_field(const char* name)
     if (!strcmp(name, "track_fma")) return &t->track_fma;
     if (!strcmp(name, "big_blocked")) return &t->big_blocked;
     if (!strcmp(name, "big_panel")) return &t->big_panel;
+    if (!strcmp(name, "big_qr_cluster")) return &t->big_qr_cluster;
     return nullptr;
 }
 extern "C" int axs_set_tuning(const char* name, int value)

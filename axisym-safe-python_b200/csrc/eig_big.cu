@@ -376,6 +376,10 @@ k_reduce_big(int N, int hb, const cplx* __restrict__ K0s, const cplx* __restrict
 // off-diagonal strips (phase O, the bulk of the flops for 2N in the thousands); the recorded rotations
 // travel through distributed shared memory, the matrix through L2 with a cluster barrier on either side.
 // With a batch that fills the GPU by itself the launcher uses CL = 1 (one CTA per matrix, as before).
+// CLUSTER = false is the one-CTA-per-matrix instance (all cluster code folds away).  In the cluster
+// instance every CTA reads matrix entries that other SMs have written, so the reads of the deflation scan
+// and of the shifts go through L2 (__ldcg) and every cluster barrier is followed by a fence.
+template <bool CLUSTER>
 __global__ void __launch_bounds__(HB_NT, 2)
 k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_all,
           int* __restrict__ info, int* __restrict__ ucur)
@@ -388,12 +392,13 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
     __shared__ cplx s_rr[2][HB_NB];
     __shared__ int s_l;
     cg::cluster_group cluster = cg::this_cluster();
-    const int CL = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
-    const int f = blockIdx.x / CL, tid = threadIdx.x;
-    const bool lead = (crank == 0);
+    const int CL = CLUSTER ? (int)cluster.num_blocks() : 1, crank = CLUSTER ? (int)cluster.block_rank() : 0;
+    const int f = CLUSTER ? blockIdx.x / CL : blockIdx.x, tid = threadIdx.x;
+    const bool lead = CLUSTER ? (crank == 0) : true;
     cplx* Hg = H_all + (long long)f * hcol_size(n);
     cplx* eig = eig_all + (long long)f * n;
 #define GH(i, j) Hg[hcol_off(j) + (i)]
+#define GHR(i, j) (CLUSTER ? __ldcg(&Hg[hcol_off(j) + (i)]) : Hg[hcol_off(j) + (i)])   /* read that may see another SM's write */
 
     int u = n - 1, its = 0, failed = 0;
     while (u >= m_stop) {
@@ -401,18 +406,18 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
         if (tid == 0) s_l = 0;
         __syncthreads();
         for (int k = 1 + tid; k <= u; k += HB_NT) {
-            const double sub = cabs1(GH(k, k - 1));
+            const double sub = cabs1(GHR(k, k - 1));
             bool neg = false;
             if (sub <= SMALL_D) neg = true;
             else {
-                const cplx hkk = GH(k, k), hk1k1 = GH(k - 1, k - 1);
+                const cplx hkk = GHR(k, k), hk1k1 = GHR(k - 1, k - 1);
                 double tst = cabs1(hk1k1) + cabs1(hkk);
                 if (tst == 0.0) {
-                    if (k - 2 >= 0) tst += cabs1(GH(k - 1, k - 2));
-                    if (k + 1 <= u) tst += cabs1(GH(k + 1, k));
+                    if (k - 2 >= 0) tst += cabs1(GHR(k - 1, k - 2));
+                    if (k + 1 <= u) tst += cabs1(GHR(k + 1, k));
                 }
                 if (sub <= EPS_D * tst) {
-                    const double up = cabs1(GH(k - 1, k));
+                    const double up = cabs1(GHR(k - 1, k));
                     const double ab = fmax(sub, up), ba = fmin(sub, up);
                     const double dd = cabs1(csub(hk1k1, hkk));
                     const double aa = fmax(cabs1(hkk), dd), bb = fmin(cabs1(hkk), dd);
@@ -428,14 +433,14 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
         // A subdiagonal entry found negligible stays negligible for the others whether or not they already see the zero.)
         if (l > 0 && tid == 0 && lead) GH(l, l - 1) = mk(0, 0);
         if (l == u) {
-            if (tid == 0 && lead) eig[u] = GH(u, u);
+            if (tid == 0 && lead) eig[u] = GHR(u, u);
             --u; its = 0;
             __syncthreads();
             continue;
         }
         ++its;
         if (its > 120) {
-            if (tid == 0 && lead) eig[u] = GH(u, u);
+            if (tid == 0 && lead) eig[u] = GHR(u, u);
             ++failed; --u; its = 0;
             __syncthreads();
             continue;
@@ -446,14 +451,14 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
         // ---- shifts: eigenvalues of the trailing 2x2 diagonal blocks -------------------------
         if (tid < (nb + 1) / 2) {
             const int i = u - 2 * tid;
-            const cplx a11 = GH(i - 1, i - 1), a12 = GH(i - 1, i), a21 = GH(i, i - 1), a22 = GH(i, i);
+            const cplx a11 = GHR(i - 1, i - 1), a12 = GHR(i - 1, i), a21 = GHR(i, i - 1), a22 = GHR(i, i);
             const cplx hd = cscale(csub(a11, a22), 0.5);
             const cplx disc = csqrt_(cadd(cmul(hd, hd), cmul(a12, a21)));
             const cplx mid = cscale(cadd(a11, a22), 0.5);
             cplx e1 = cadd(mid, disc), e2 = csub(mid, disc);
             if (cabs1(csub(e2, a22)) < cabs1(csub(e1, a22))) { const cplx tmp = e1; e1 = e2; e2 = tmp; }
             if (its % 10 == 0) {                         // exceptional shifts against stagnation
-                const double ex = 0.75 * cabs1(GH(u, u - 1));
+                const double ex = 0.75 * cabs1(GHR(u, u - 1));
                 e1 = cadd(e1, mk(ex, 0)); e2 = cadd(e2, mk(0, ex));
             }
             s_shift[2 * tid] = e1;
@@ -462,11 +467,16 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
         __syncthreads();
         if (tid == 0) {                                  // rotation that introduces bulge 0
             cplx a, b, r;
-            make_rot_rc(csub(GH(l, l), s_shift[0]), GH(l + 1, l), a, b, r);
+            make_rot_rc(csub(GHR(l, l), s_shift[0]), GHR(l + 1, l), a, b, r);
             s_ra[0][0] = a; s_rb[0][0] = b; s_rr[0][0] = r;
         }
         __syncthreads();
         const int nsteps = (m - 1) + (nb - 1) * HB_D;
+        if (CLUSTER && CL > 1) {
+            // every CTA of the cluster has taken its decisions (deflation scan, shifts) from the matrix as
+            // the previous batch left it: only now may the lead start to rewrite the diagonal window
+            cluster.sync();
+        }
 
         for (int t0 = 0; t0 < nsteps; t0 += HB_S) {
             const int t1 = (t0 + HB_S < nsteps) ? t0 + HB_S : nsteps;
@@ -479,7 +489,7 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
             if (lead) {
             for (int idx = tid; idx < ws * ws; idx += HB_NT) {
                 const int j = idx / ws, i = idx - j * ws;
-                buf[j * HB_WLD + i] = (i <= j + 1) ? GH(wlo + i, wlo + j) : mk(0, 0);
+                buf[j * HB_WLD + i] = (i <= j + 1) ? GHR(wlo + i, wlo + j) : mk(0, 0);
             }
 #define WH(i, j) buf[((j) - wlo) * HB_WLD + ((i) - wlo)]
             // fixed work items of this window: (bulge, column) for the row rotations,
@@ -562,10 +572,11 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
             __syncthreads();
             }                                              // lead
             const int nt = t1 - t0;
-            if (CL > 1) {
+            if (CLUSTER && CL > 1) {
                 // the window is back in global memory and the rotations are recorded: hand both to the cluster
                 __threadfence();
                 cluster.sync();
+                __threadfence();
                 if (!lead) {
                     const cplx* src = cluster.map_shared_rank(&s_rec[0][0][0], 0);
                     cplx* dst = &s_rec[0][0][0];
@@ -578,7 +589,7 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
                 const int nc = (u - c0 + 1 < HB_TILE) ? u - c0 + 1 : HB_TILE;
                 for (int idx = tid; idx < nc * ws; idx += HB_NT) {
                     const int cid = idx / ws, rl = idx - cid * ws;
-                    buf[rl * HB_TLD + cid] = GH(wlo + rl, c0 + cid);
+                    buf[rl * HB_TLD + cid] = GHR(wlo + rl, c0 + cid);
                 }
                 __syncthreads();
                 if (tid < nc) {
@@ -612,7 +623,7 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
                 const int nr = (wlo - r0 < HB_TILE) ? wlo - r0 : HB_TILE;
                 for (int idx = tid; idx < nr * ws; idx += HB_NT) {
                     const int cl = idx / nr, rid = idx - cl * nr;
-                    buf[cl * HB_TLD + rid] = GH(r0 + rid, wlo + cl);
+                    buf[cl * HB_TLD + rid] = GHR(r0 + rid, wlo + cl);
                 }
                 __syncthreads();
                 if (tid < nr) {
@@ -641,14 +652,16 @@ k_hqr_big(int n, int m_stop, cplx* __restrict__ H_all, cplx* __restrict__ eig_al
                 }
                 __syncthreads();
             }
-            if (CL > 1) {                                  // strips of all CTAs are in global memory; the lead
+            if (CLUSTER && CL > 1) {                       // strips of all CTAs are in global memory; the lead
                 __threadfence();                           // may overwrite its rotation record
                 cluster.sync();
+                __threadfence();
             }
         }
 #undef WH
     }
 #undef GH
+#undef GHR
     if (tid == 0 && lead) { info[f] = failed; ucur[f] = u; }
 }
 
@@ -1085,13 +1098,23 @@ extern "C" int axs_launch_hqr_big(int n, int nf, cplx* eig, int* info, AxsWorkBi
 {
     const int m2 = axs_hqr_stage_capacity(2);            // what the 2-CTA/SM shared-memory stage can hold
     const size_t smem = hqr_big_smem();
-    AXS_SMEM_ONCE(smem, k_hqr_big);
+    AXS_SMEM_ONCE(smem, k_hqr_big<false>);
+    AXS_SMEM_ONCE(smem, k_hqr_big<true>);
     // cluster size: the CTAs of a cluster share the strip tiles of one matrix; a batch that fills the GPU
     // (2 CTAs per SM) keeps one CTA per matrix
     int sms = 148, dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int CL = 1;
     while (CL < 8 && (long long)nf * CL * 2 <= sms && CL * 2 * HB_TILE <= n) CL *= 2;
+    if (axs_tuning()->big_qr_cluster > 0) CL = axs_tuning()->big_qr_cluster;       // A/B: 1, 2, 4, 8
+    cplx* Hc = wk.Hc;
+    int* ucur = wk.ucur;
+    if (CL == 1) {
+        k_hqr_big<false><<<nf, HB_NT, smem, st>>>(n, m2, Hc, eig, info, ucur);
+        cudaError_t e1 = cudaGetLastError();
+        if (e1 != cudaSuccess) return (int)e1;
+        return axs_launch_hqr_stages(n, nf, m2, wk.Hc, eig, info, wk.ucur, nullptr, st);
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(nf * CL), 1, 1);
     cfg.blockDim = dim3(HB_NT, 1, 1);
@@ -1104,9 +1127,7 @@ extern "C" int axs_launch_hqr_big(int n, int nf, cplx* eig, int* info, AxsWorkBi
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cplx* Hc = wk.Hc;
-    int* ucur = wk.ucur;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k_hqr_big, n, m2, Hc, eig, info, ucur);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k_hqr_big<true>, n, m2, Hc, eig, info, ucur);
     if (e != cudaSuccess) return (int)e;
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
