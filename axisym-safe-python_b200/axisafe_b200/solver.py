@@ -979,6 +979,9 @@ def _sweep_large(torch, _native, ops, omega, halo, select=None):
     n2, nloc = 2 * ops.N, len(omega)
     L = _native.lib()
     free, _ = torch.cuda.mem_get_info()
+    # blocks that torch's caching allocator holds but does not use (the workspace of a previous sweep) are
+    # available to this one as well
+    free += max(0, torch.cuda.memory_reserved() - torch.cuda.memory_allocated())
     per_mat = n2 * n2 * 16
     keep = nloc * per_mat <= 0.45 * free
     budget = 0.8 * (free - (nloc * per_mat if keep else 0))
