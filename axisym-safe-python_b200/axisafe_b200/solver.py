@@ -737,7 +737,7 @@ def _shard_plan(nf, world, unit, K=None, first=None):
     of ``unit`` matrices (one halo frequency included) when the sweep is long enough."""
     per = nf // world
     if K is None:
-        K = 4 if per >= 512 else 2
+        K = int(os.environ.get('AXS_SHARD_K', 4 if per >= 512 else 2))     # A/B: more, equal chunks
     if first is None:
         first = float(os.environ.get('AXS_SHARD_FIRST', 0.888 if world <= 2 else (0.77 if world <= 4 else 0.67)))
     if K == 4:
