@@ -736,6 +736,24 @@ def _shard_plan(nf, world, unit, K=None, first=None):
     The second pair is split 2:1 so that the last download is the small one.  Pieces are whole waves
     of ``unit`` matrices (one halo frequency included) when the sweep is long enough."""
     per = nf // world
+    fine = os.environ.get('AXS_SHARD_FINE', '1') != '0'
+    if K is None and first is None and 'AXS_SHARD_K' not in os.environ and 'AXS_SHARD_FIRST' not in os.environ \
+            and world >= 4 and per >= 4 * unit and fine:
+        # Four or more ranks share the host's memory system for their downloads (measured on 8 B200s:
+        # ~19 GB/s per GPU, 27 ms for the 0.5 GB of a 2000-point block against 55 ms of compute), so the
+        # download has to start early and run all the way: chunks of two whole waves of `unit` matrices
+        # (one halo frequency included), the remainder last - at 2000 points per rank 6 x 295 + 230.
+        waves = per / float(unit)
+        K = min(8, max(2, int(round(waves / 2))))
+        kept = 2 * unit - 1
+        while kept * (K - 1) >= per:
+            K -= 1
+        gb = [c * kept * world for c in range(K)] + [nf]
+        pieces = []
+        for c in range(K):
+            L = gb[c + 1] - gb[c]
+            pieces.append([(gb[c] + (L * r) // world, gb[c] + (L * (r + 1)) // world) for r in range(world)])
+        return pieces
     if K is None:
         K = int(os.environ.get('AXS_SHARD_K', 4 if per >= 512 else 2))     # A/B: more, equal chunks
     if first is None:
@@ -838,6 +856,19 @@ def _solve_sharded_pipelined(sol, torch, _native, ops, nf, n2, rank, world, host
                 amax_h[a:b - 1].copy_(amax[a * n2:(b - 1) * n2].view(-1, n2), non_blocking=True)
             ev_small[c].record(ss)
 
+    # index tensors and buffers of the final gather, prepared before the pipeline starts (a pageable H2D
+    # copy issued at the end would make the host wait for every queued kernel and download)
+    keep_slots = torch.from_numpy(np.concatenate([np.arange(so[c] + halo[c], so[c + 1]) for c in range(K)])).to(dev)
+    counts = [sum(pieces[c][r][1] - pieces[c][r][0] for c in range(K)) for r in range(world)]
+    size = max(counts)
+    index = np.concatenate([np.arange(pieces[c][r][0], pieces[c][r][1]) for r in range(world) for c in range(K)])
+    src = np.concatenate([r * size + np.arange(counts[r]) for r in range(world)])
+    back = np.empty(nf, dtype=np.int64)
+    back[index] = src                                    # global frequency -> row of the gathered table
+    back_d = torch.from_numpy(back).to(dev)
+    k_h = pin(nf, n2, dtype=torch.complex128)
+    o_h = pin(nf, n2 + 1, dtype=torch.int32)
+
     carry = [None]                                      # absolute order at the base of the next chunk
 
     def finish(c):
@@ -888,15 +919,7 @@ def _solve_sharded_pipelined(sol, torch, _native, ops, nf, n2, rank, world, host
     main.wait_stream(xs)
     for s_ in cs:
         main.wait_stream(s_)
-    keep_slots = torch.from_numpy(np.concatenate([np.arange(so[c] + halo[c], so[c + 1]) for c in range(K)])).to(dev)
     k_nat_kept = k_nat.view(slots, n2).index_select(0, keep_slots)
-    counts = [sum(pieces[c][r][1] - pieces[c][r][0] for c in range(K)) for r in range(world)]
-    size = max(counts)
-    index = np.concatenate([np.arange(pieces[c][r][0], pieces[c][r][1]) for r in range(world) for c in range(K)])
-    src = np.concatenate([r * size + np.arange(counts[r]) for r in range(world)])
-    back = np.empty(nf, dtype=np.int64)
-    back[index] = src                                    # global frequency -> row of the gathered table
-    back_d = torch.from_numpy(back).to(dev)
     # (the per-frequency counts of unconverged eigenvalues travel as an extra column of the order table)
     order_info = torch.cat([order_d.view(kept, n2), info.index_select(0, keep_slots).view(kept, 1)], dim=1)
     tables = []
@@ -909,8 +932,6 @@ def _solve_sharded_pipelined(sol, torch, _native, ops, nf, n2, rank, world, host
         else:
             dist.all_gather_into_tensor(full, pad)
         tables.append(full.index_select(0, back_d))
-    k_h = pin(nf, n2, dtype=torch.complex128)
-    o_h = pin(nf, n2 + 1, dtype=torch.int32)
     k_h.copy_(tables[0], non_blocking=True)
     o_h.copy_(tables[1], non_blocking=True)
     tl.append(('gather', time.perf_counter()))
