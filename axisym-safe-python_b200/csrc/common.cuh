@@ -248,8 +248,9 @@ static inline long long axs_work_layout(int n2, int nf, void* base, AxsWork* w) 
 #define AXS_BIG_MODE_GRID 592           // persistent CTAs of k_modes_col (4 per SM)
 #define AXS_BIG_RB 64                   // row blocks of 128 rows (2N <= 8192)
 #define AXS_BIG_CG 32                   // column groups
-#define AXS_BIG_YW (4 + AXS_BIG_RB + AXS_BIG_CG + 12)   // y, w (double buffered) + partial sums; the blocked
-                                        // reduction (eig_bigred.cu) keeps Y, W (32 rows each), <= 16 partial rows and T here
+#define AXS_BIG_YW (4 + AXS_BIG_RB + AXS_BIG_CG + 28)   // y, w (double buffered) + partial sums; the blocked
+                                        // reduction (eig_bigred.cu) keeps Y, W (32 rows each), 16 partial rows, T and - from row 88 - the T
+                                        // factors of all panels (32 rows) here
 
 struct AxsWorkBig {
     cplx*   A;      // [nf][n2*n2]  dense column-major work matrix (S -> reflectors below subdiag)

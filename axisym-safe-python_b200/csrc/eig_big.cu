@@ -1063,6 +1063,7 @@ extern "C" int axs_launch_hqr_stages(int n, int nf, int m_first, cplx* Hp, cplx*
                                      int* stats, cudaStream_t st);
 extern "C" int axs_hqr_stage_capacity(int per_sm);
 
+extern "C" int axs_launch_backx_blocked(int n, int nf, cplx* psi, AxsWorkBig wk, cudaStream_t st);
 extern "C" int axs_launch_reduce_blocked(int N, int hb, const cplx* K0s, const cplx* Cb, const cplx* Mb,
                                          const cplx* K1c, const cplx* K6d, const double* omega, int nf,
                                          const cplx* S_in, AxsWorkBig wk, cudaStream_t st);
@@ -1164,6 +1165,15 @@ extern "C" int axs_launch_modes_big(int N, int hb, const cplx* Cb, const cplx* K
     cudaError_t e;
     int Cs = 8;                                          // slab width that fits next to 3 reflector buffers
     while (Cs >= 1 && (size_t)(Cs + 4) * n * sizeof(cplx) > 224 * 1024) Cs >>= 1;
+    if (Cs < 4 && axs_tuning()->big_blocked && axs_tuning()->big_panel >= 32) {
+        // sizes whose slab of mode vectors no longer fits an SM: blocked compact-WY back-transformation on
+        // DMMA tiles with the T factors the blocked reduction kept (eig_bigred.cu) - level 3 instead of
+        // one pass over all reflectors per mode
+        rc = axs_launch_backx_blocked(n, nf, psi, wk, st);
+        if (rc) return rc;
+        k_norm_big<<<dim3((n + 31) / 32, nf), 256, 0, st>>>(N, hb, Cb, K6d, eig, psi);
+        return (int)cudaGetLastError();
+    }
     if (Cs >= 1) {
         const size_t smem = (size_t)(Cs + 4) * n * sizeof(cplx);
         AXS_SMEM_ONCE(smem, k_backx_slab);

@@ -44,13 +44,16 @@ struct BrScratch {
     cplx* W;      // [nb][n]   W = T^H V^H A(:, trailing), row q at W + q n (indexed by absolute column)
     cplx* part;   // [CG][n]   partial sums of the products A v
     cplx* T;      // [nb][nb]  row-major upper triangular
+    cplx* Tall;   // [panels][nb][nb] the T factor of every panel, kept for the back-transformation
 };
+#define BR_TALL_ROW 88                  // Tall starts at row 88 of the yw region (32 rows of n entries)
 __device__ __host__ __forceinline__ BrScratch br_scratch(cplx* ywb, int n, int CG) {
     BrScratch s;
     s.Y = ywb;
     s.W = ywb + (long long)BR_NB_MAX * n;
     s.part = ywb + 2LL * BR_NB_MAX * n;
     s.T = ywb + (2LL * BR_NB_MAX + CG) * n;
+    s.Tall = ywb + (long long)BR_TALL_ROW * n;
     return s;
 }
 
@@ -239,7 +242,11 @@ k_br_gemv(int n, int k0, int c, int CG, AxsWorkBig wk)
 // complex product is four real MMAs).  CTA tile 64 (m) x 32 (n), 8 warps x (one m8 row tile x four n8
 // column tiles), K in chunks of 16 staged in padded shared memory with register prefetch of the next
 // chunk.  The four uses differ in operand addressing and in the epilogue only.
-enum { BR_YTOP = 0, BR_RIGHT = 1, BR_LEFTW = 2, BR_LEFTA = 3 };
+// Two more uses serve the blocked BACK-TRANSFORMATION of the Hessenberg-basis eigenvectors X (psi, row
+// major [row][mode]):  X <- (I - V T V^H) X per panel, panels in reverse order:
+//     BXW   W = V^H X(k0+1:n, :)       (then W <- T W: k_bx_tw)
+//     BXA   X(k0+1:n, :) -= V W
+enum { BR_YTOP = 0, BR_RIGHT = 1, BR_LEFTW = 2, BR_LEFTA = 3, BR_BXW = 4, BR_BXA = 5 };
 #define BR_TM 64
 #define BR_TN 32
 #define BR_KC 16
@@ -255,7 +262,7 @@ __device__ __forceinline__ void br_dmma(double& d0, double& d1, double a, double
 
 template <int MODE>
 __global__ void __launch_bounds__(256)
-k_br_gemm(int n, int k0, int nbc, int CG, AxsWorkBig wk)
+k_br_gemm(int n, int k0, int nbc, int CG, AxsWorkBig wk, cplx* __restrict__ X_all)
 {
     __shared__ __align__(16) cplx sA[BR_KC * BR_SA];
     __shared__ __align__(16) cplx sB[BR_KC * BR_SB];
@@ -263,13 +270,16 @@ k_br_gemm(int n, int k0, int nbc, int CG, AxsWorkBig wk)
     const int gq = lane >> 2, tq = lane & 3;
     cplx* A = wk.A + (long long)f * n * n;
     const BrScratch sc = br_scratch(wk.yw + (long long)f * AXS_BIG_YW * n, n, CG);
+    cplx* X = (MODE == BR_BXW || MODE == BR_BXA) ? X_all + (long long)f * n * n : nullptr;
     const int t0 = k0 + nbc;                                // first trailing column
     // logical index ranges [lo, hi) of m, n, k for this use
     int m_lo, m_hi, n_lo, n_hi, k_lo, k_hi;
     if (MODE == BR_YTOP)       { m_lo = 0;      m_hi = k0 + 1; n_lo = 0;  n_hi = nbc; k_lo = k0 + 1; k_hi = n; }
     else if (MODE == BR_RIGHT) { m_lo = 0;      m_hi = n;      n_lo = t0; n_hi = n;   k_lo = 0;      k_hi = nbc; }
     else if (MODE == BR_LEFTW) { m_lo = t0;     m_hi = n;      n_lo = 0;  n_hi = nbc; k_lo = k0 + 1; k_hi = n; }
-    else                       { m_lo = k0 + 1; m_hi = n;      n_lo = t0; n_hi = n;   k_lo = 0;      k_hi = nbc; }
+    else if (MODE == BR_LEFTA) { m_lo = k0 + 1; m_hi = n;      n_lo = t0; n_hi = n;   k_lo = 0;      k_hi = nbc; }
+    else if (MODE == BR_BXW)   { m_lo = 0;      m_hi = n;      n_lo = 0;  n_hi = nbc; k_lo = k0 + 1; k_hi = n; }
+    else                       { m_lo = k0 + 1; m_hi = n;      n_lo = 0;  n_hi = n;   k_lo = 0;      k_hi = nbc; }
     const int m0 = m_lo + blockIdx.x * BR_TM, n0 = n_lo + blockIdx.y * BR_TN;
     if (m0 >= m_hi || n0 >= n_hi) return;
 
@@ -279,18 +289,19 @@ k_br_gemm(int n, int k0, int nbc, int CG, AxsWorkBig wk)
         if (MODE == BR_YTOP) return A[(long long)k * n + m];                       // A(i, j), m = i, k = j
         if (MODE == BR_RIGHT) return sc.Y[(long long)k * n + m];                   // Y(i, q)
         if (MODE == BR_LEFTW) return A[(long long)m * n + k];                      // A(i, j), m = j, k = i
-        return br_v(A, n, k0, m, k);                                               // V(i, q)
+        if (MODE == BR_BXW) return X[(long long)k * n + m];                        // X(i, mode), m = mode, k = i
+        return br_v(A, n, k0, m, k);                                               // V(i, q)  (LEFTA, BXA)
     };
     auto opB = [&](int k, int nn) -> cplx {
         if (k >= k_hi || nn >= n_hi) return mk(0, 0);
         if (MODE == BR_YTOP) return br_v(A, n, k0, k, nn);                         // V(j, q)
         if (MODE == BR_RIGHT) return cconj(br_v(A, n, k0, nn, k));                 // conj(V(j, q)), nn = j, k = q
-        if (MODE == BR_LEFTW) return cconj(br_v(A, n, k0, k, nn));                 // conj(V(i, q)), k = i, nn = q
-        return sc.W[(long long)k * n + nn];                                        // W(q, j)
+        if (MODE == BR_LEFTW || MODE == BR_BXW) return cconj(br_v(A, n, k0, k, nn));   // conj(V(i, q)), k = i, nn = q
+        return sc.W[(long long)k * n + nn];                                        // W(q, j)  (LEFTA, BXA: j = mode)
     };
     // thread -> staged element: the memory-contiguous index of each operand is the fastest one
     const bool a_kfast = (MODE == BR_LEFTW);
-    const bool b_kfast = (MODE == BR_YTOP || MODE == BR_LEFTW);
+    const bool b_kfast = (MODE == BR_YTOP || MODE == BR_LEFTW || MODE == BR_BXW);
     cplx ra[BR_NLA], rb[BR_NLB];
     auto fetch = [&](int kc) {
 #pragma unroll
@@ -354,8 +365,11 @@ k_br_gemm(int n, int k0, int nbc, int CG, AxsWorkBig wk)
             if (nn >= n_hi) continue;
             const cplx v = mk(cre[t][e], cim[t][e]);
             if (MODE == BR_YTOP) sc.Y[(long long)nn * n + m] = v;                 // Y0(i, q) (x T in k_br_top)
-            else if (MODE == BR_LEFTW) sc.W[(long long)nn * n + m] = v;           // W0(q, j)
-            else {                                                                // A(i, j) -= ...
+            else if (MODE == BR_LEFTW || MODE == BR_BXW) sc.W[(long long)nn * n + m] = v;   // W0(q, j) / W0(q, mode)
+            else if (MODE == BR_BXA) {                                            // X(i, mode) -= ...
+                cplx* p = X + (long long)m * n + nn;
+                *p = csub(*p, v);
+            } else {                                                              // A(i, j) -= ...
                 cplx* p = A + (long long)nn * n + m;
                 *p = csub(*p, v);
             }
@@ -365,7 +379,7 @@ k_br_gemm(int n, int k0, int nbc, int CG, AxsWorkBig wk)
 // k_br_top: rows i = 0 .. k0 (above the panel): Y(i, :) <- Y0(i, :) T, then the right update of the
 // panel's own columns A(i, k0+jj) -= sum_{q < jj} Y(i, q) conj(V(k0+jj, q)).  One thread per row.
 __global__ void __launch_bounds__(256)
-k_br_top(int n, int k0, int nbc, int CG, AxsWorkBig wk)
+k_br_top(int n, int k0, int nbc, int CG, int panel, AxsWorkBig wk)
 {
     __shared__ cplx s_T[BR_NB_MAX * BR_NB_MAX];
     __shared__ cplx s_Vc[BR_NB_MAX * BR_NB_MAX];            // conj(V(k0+jj, q))
@@ -376,6 +390,7 @@ k_br_top(int n, int k0, int nbc, int CG, AxsWorkBig wk)
         const int p = idx / BR_NB_MAX, q = idx - p * BR_NB_MAX;
         s_T[idx] = (p < nbc && q < nbc && p <= q) ? sc.T[idx] : mk(0, 0);
         s_Vc[idx] = (p < nbc && q < nbc) ? cconj(br_v(A, n, k0, k0 + p, q)) : mk(0, 0);   // p = jj
+        if (blockIdx.x == 0 && panel >= 0) sc.Tall[(long long)panel * BR_NB_MAX * BR_NB_MAX + idx] = s_T[idx];   // for the back-transformation
     }
     __syncthreads();
     const int i = blockIdx.x * 256 + tid;
@@ -430,6 +445,46 @@ k_br_tw(int n, int k0, int nbc, int CG, AxsWorkBig wk)
 #pragma unroll
     for (int q = 0; q < BR_NB_MAX; ++q)
         if (q < nbc) sc.W[(long long)q * n + jcol] = wv[q];
+}
+
+// k_bx_tw: W(:, mode) <- T W(:, mode) with the T factor of panel `panel` (blocked back-transformation).
+__global__ void __launch_bounds__(256)
+k_bx_tw(int n, int nbc, int CG, int panel, AxsWorkBig wk)
+{
+    __shared__ cplx s_T[BR_NB_MAX * BR_NB_MAX];
+    const int f = blockIdx.y, tid = threadIdx.x;
+    const BrScratch sc = br_scratch(wk.yw + (long long)f * AXS_BIG_YW * n, n, CG);
+    for (int idx = tid; idx < BR_NB_MAX * BR_NB_MAX; idx += 256) s_T[idx] = sc.Tall[(long long)panel * BR_NB_MAX * BR_NB_MAX + idx];
+    __syncthreads();
+    const int mode = blockIdx.x * 256 + tid;
+    if (mode >= n) return;
+    cplx wv[BR_NB_MAX];
+#pragma unroll
+    for (int q = 0; q < BR_NB_MAX; ++q) wv[q] = (q < nbc) ? sc.W[(long long)q * n + mode] : mk(0, 0);
+#pragma unroll
+    for (int q = 0; q < BR_NB_MAX; ++q) {                   // in place, top to bottom: w'_q = sum_{p >= q} T(q, p) w_p
+        cplx s = mk(0, 0);
+#pragma unroll
+        for (int p = q; p < BR_NB_MAX; ++p) s = cfma(s_T[q * BR_NB_MAX + p], wv[p], s);
+        wv[q] = s;
+    }
+#pragma unroll
+    for (int q = 0; q < BR_NB_MAX; ++q)
+        if (q < nbc) sc.W[(long long)q * n + mode] = wv[q];
+}
+
+// k_bx_scale: undo the balancing, X(i, :) *= D(i)
+__global__ void __launch_bounds__(256)
+k_bx_scale(int n, cplx* __restrict__ X_all, AxsWorkBig wk)
+{
+    const int f = blockIdx.y;
+    cplx* X = X_all + (long long)f * n * n;
+    const double* dsc = wk.scale + (long long)f * n;
+    const long long nn = (long long)n * n;
+    for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < nn; idx += (long long)gridDim.x * 256) {
+        const int i = (int)(idx / n);
+        X[idx] = cscale(X[idx], dsc[i]);
+    }
 }
 
 // k_br_pack: packed copies of H (QR input Hc, inverse-iteration input Hm), contiguous subdiagonal for
@@ -515,14 +570,14 @@ extern "C" int axs_launch_reduce_blocked(int N, int hb, const cplx* K0s, const c
         }
         k_br_col<<<nf, BR_COL_NT, col_smem, st>>>(n, k0, nbc, CG, 1, wk);
         const int t0 = k0 + nbc, ntrail = n - t0;
-        k_br_gemm<BR_YTOP><<<dim3((k0 + 1 + BR_TM - 1) / BR_TM, 1, nf), 256, 0, st>>>(n, k0, nbc, CG, wk);
-        k_br_top<<<dim3((k0 + 1 + 255) / 256, nf), 256, 0, st>>>(n, k0, nbc, CG, wk);
+        k_br_gemm<BR_YTOP><<<dim3((k0 + 1 + BR_TM - 1) / BR_TM, 1, nf), 256, 0, st>>>(n, k0, nbc, CG, wk, nullptr);
+        k_br_top<<<dim3((k0 + 1 + 255) / 256, nf), 256, 0, st>>>(n, k0, nbc, CG, nb == BR_NB_MAX ? k0 / nb : -1, wk);   // (Tall has room for panels of 32)
         if (ntrail > 0) {
             const int ntn = (ntrail + BR_TN - 1) / BR_TN;
-            k_br_gemm<BR_RIGHT><<<dim3((n + BR_TM - 1) / BR_TM, ntn, nf), 256, 0, st>>>(n, k0, nbc, CG, wk);
-            k_br_gemm<BR_LEFTW><<<dim3((ntrail + BR_TM - 1) / BR_TM, 1, nf), 256, 0, st>>>(n, k0, nbc, CG, wk);
+            k_br_gemm<BR_RIGHT><<<dim3((n + BR_TM - 1) / BR_TM, ntn, nf), 256, 0, st>>>(n, k0, nbc, CG, wk, nullptr);
+            k_br_gemm<BR_LEFTW><<<dim3((ntrail + BR_TM - 1) / BR_TM, 1, nf), 256, 0, st>>>(n, k0, nbc, CG, wk, nullptr);
             k_br_tw<<<dim3((ntrail + 255) / 256, nf), 256, 0, st>>>(n, k0, nbc, CG, wk);
-            k_br_gemm<BR_LEFTA><<<dim3((n - k0 - 1 + BR_TM - 1) / BR_TM, ntn, nf), 256, 0, st>>>(n, k0, nbc, CG, wk);
+            k_br_gemm<BR_LEFTA><<<dim3((n - k0 - 1 + BR_TM - 1) / BR_TM, ntn, nf), 256, 0, st>>>(n, k0, nbc, CG, wk, nullptr);
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return (int)e;
@@ -536,5 +591,28 @@ extern "C" int axs_launch_reduce_blocked(int N, int hb, const cplx* K0s, const c
     if (gx > n) gx = n;
     k_br_pack<<<dim3(gx, nf), 256, 0, st>>>(n, wk, hmax);
     k_br_pack_fin<<<dim3((n + 255) / 256 < 64 ? (n + 255) / 256 : 64, nf), 256, 0, st>>>(n, wk, hmax);
+    return (int)cudaGetLastError();
+}
+
+// Blocked back-transformation X <- D Q X, Q = product of the panels' (I - V T V^H) in reduction order, i.e.
+// the panels are applied to X last to first.  Needs the T factors kept by the blocked reduction of the same
+// workspace (k_br_top -> Tall).  psi holds the Hessenberg-basis vectors from k_modes_col.
+extern "C" int axs_launch_backx_blocked(int n, int nf, cplx* psi, AxsWorkBig wk, cudaStream_t st)
+{
+    int nb = axs_tuning()->big_panel;
+    if (nb < 4) nb = 4;
+    if (nb > BR_NB_MAX) nb = BR_NB_MAX;
+    const int CG = 16;
+    int last = 0;
+    while (last + nb < n - 2) last += nb;
+    for (int k0 = last; k0 >= 0; k0 -= nb) {
+        const int nbc = (nb < n - 2 - k0) ? nb : n - 2 - k0;
+        k_br_gemm<BR_BXW><<<dim3((n + BR_TM - 1) / BR_TM, 1, nf), 256, 0, st>>>(n, k0, nbc, CG, wk, psi);
+        k_bx_tw<<<dim3((n + 255) / 256, nf), 256, 0, st>>>(n, nbc, CG, k0 / nb, wk);
+        k_br_gemm<BR_BXA><<<dim3((n - k0 - 1 + BR_TM - 1) / BR_TM, (n + BR_TN - 1) / BR_TN, nf), 256, 0, st>>>(n, k0, nbc, CG, wk, psi);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    k_bx_scale<<<dim3(256, nf), 256, 0, st>>>(n, psi, wk);
     return (int)cudaGetLastError();
 }
