@@ -736,21 +736,37 @@ def _shard_plan(nf, world, unit, K=None, first=None):
     The second pair is split 2:1 so that the last download is the small one.  Pieces are whole waves
     of ``unit`` matrices (one halo frequency included) when the sweep is long enough."""
     per = nf // world
-    fine = os.environ.get('AXS_SHARD_FINE', '1') != '0'
+    plan = os.environ.get('AXS_SHARD_PLAN', 'geometric')
     if K is None and first is None and 'AXS_SHARD_K' not in os.environ and 'AXS_SHARD_FIRST' not in os.environ \
-            and world >= 4 and per >= 4 * unit and fine:
+            and world >= 4 and per >= 8 * unit and plan != 'pairs2':
         # Four or more ranks share the host's memory system for their downloads (measured on 8 B200s:
-        # ~19 GB/s per GPU, 27 ms for the 0.5 GB of a 2000-point block against 55 ms of compute), so the
-        # download has to start early and run all the way: chunks of two whole waves of `unit` matrices
-        # (one halo frequency included), the remainder last - at 2000 points per rank 6 x 295 + 230.
-        waves = per / float(unit)
-        K = min(8, max(2, int(round(waves / 2))))
-        kept = 2 * unit - 1
-        while kept * (K - 1) >= per:
-            K -= 1
-        gb = [c * kept * world for c in range(K)] + [nf]
+        # ~19 GB/s per GPU, 13 us per frequency point against 27 us of compute), so the download of a chunk
+        # pair hides behind a following pair of HALF its size.  Chunks run pairwise on two streams, and a pair
+        # only uses both streams well when its halves are equal, hence three balanced pairs with 4/7, 2/7 and
+        # 1/7 of the block, the large ones rounded to whole waves of `unit` matrices (one halo frequency
+        # included): at 2000 points per rank 591 591 | 295 295 | 114 114.
+        # 'fine' (measured: 192 k points/s end to end on 8 GPUs against 183 k for two pairs): seven chunks of
+        # two waves each - the downloads start early, but small chunks lose 30 % of the compute rate.
+        if plan == 'fine':
+            kept = 2 * unit - 1
+            K = min(8, max(2, int(round(per / float(unit) / 2))))
+            while kept * (K - 1) >= per:
+                K -= 1
+            sizes = [kept] * (K - 1) + [per - kept * (K - 1)]
+        else:
+            align = lambda x: max(1, int(round((x + 1.0) / unit))) * unit - 1
+            c1, c2 = align(per * 4.0 / 7 / 2), align(per * 2.0 / 7 / 2)
+            rem = per - 2 * c1 - 2 * c2
+            if rem < 2:
+                c1, c2 = per * 2 // 7, per // 7
+                rem = per - 2 * c1 - 2 * c2
+            sizes = [c1, c1, c2, c2, rem // 2, rem - rem // 2]
+        gb = [0]
+        for sz in sizes[:-1]:
+            gb.append(gb[-1] + sz * world)
+        gb.append(nf)
         pieces = []
-        for c in range(K):
+        for c in range(len(sizes)):
             L = gb[c + 1] - gb[c]
             pieces.append([(gb[c] + (L * r) // world, gb[c] + (L * (r + 1)) // world) for r in range(world)])
         return pieces
