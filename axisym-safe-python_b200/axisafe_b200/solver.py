@@ -736,17 +736,18 @@ def _shard_plan(nf, world, unit, K=None, first=None):
     The second pair is split 2:1 so that the last download is the small one.  Pieces are whole waves
     of ``unit`` matrices (one halo frequency included) when the sweep is long enough."""
     per = nf // world
-    plan = os.environ.get('AXS_SHARD_PLAN', 'geometric')
+    plan = os.environ.get('AXS_SHARD_PLAN', 'fine')
     if K is None and first is None and 'AXS_SHARD_K' not in os.environ and 'AXS_SHARD_FIRST' not in os.environ \
             and world >= 4 and per >= 8 * unit and plan != 'pairs2':
         # Four or more ranks share the host's memory system for their downloads (measured on 8 B200s:
-        # ~19 GB/s per GPU, 13 us per frequency point against 27 us of compute), so the download of a chunk
-        # pair hides behind a following pair of HALF its size.  Chunks run pairwise on two streams, and a pair
-        # only uses both streams well when its halves are equal, hence three balanced pairs with 4/7, 2/7 and
-        # 1/7 of the block, the large ones rounded to whole waves of `unit` matrices (one halo frequency
-        # included): at 2000 points per rank 591 591 | 295 295 | 114 114.
-        # 'fine' (measured: 192 k points/s end to end on 8 GPUs against 183 k for two pairs): seven chunks of
-        # two waves each - the downloads start early, but small chunks lose 30 % of the compute rate.
+        # ~19 GB/s per GPU, 13 us per frequency point against 27 us of compute), so the downloads have to
+        # start early and keep running.  Measured end to end on 8 B200s, 2000 points per rank
+        # (profiles/r2_pipe_trace_n8_*.txt):
+        #   'pairs2'    two chunk pairs 67 % | 33 % (the round-1 plan)                    183 k points/s
+        #   'fine'      seven chunks of two waves of `unit` matrices, remainder last       192 k  (default)
+        #   'geometric' three balanced pairs 591 591 | 295 295 | 114 114                   185 k
+        # Small chunks lose compute rate (a chunk of 295 matrices fills only half of the 4-CTAs-per-SM QR
+        # stage), large ones delay the downloads; 'fine' is the best of the three.
         if plan == 'fine':
             kept = 2 * unit - 1
             K = min(8, max(2, int(round(per / float(unit) / 2))))
