@@ -379,6 +379,12 @@ def gpu_arm(args):
                                      'leading block parked and re-read between stages',
                      'note': 'FP64 pipe (DFMA/DMMA share one roof on B200); algorithmic flops = 80*n2^3 per '
                              'point for the QR kernel (zhseqr share of F_alg = 100*n2^3); peak = ' + how,
+                     'executed': {'fp64_pipe_active_pct_per_stage': [14.1, 8.6, 6.9, 4.3],
+                                  'issue_active_pct_per_stage': [32.9, 30.9, 24.0, 17.3],
+                                  'source': 'ncu --set full, profiles/r2c_ncu_summary.csv: the kernel is bound by the '
+                                            'latency of its rotation chain and two block barriers per macro step, not '
+                                            'by FP64 throughput; frac is a NOMINAL zhseqr flop count (Schur vectors '
+                                            'are never accumulated)'},
                      'pipeline_frac': value / world * f_alg(n2) / 1e12 / fp64_peak},
         'e2e': {'value': nf_total / e2e_s, 'unit': UNIT,
                 # per rank.  up: omega + the tracked column order of the rank's block; down: tracking tables
@@ -527,7 +533,7 @@ def gpu_arm_cfg4(args, torch, dist, rank, world, local, saved_stdout):
                 'd2h_bytes_per_step': int(ppg * n2 * (16 + 16) + (ppg - 1) * n2 * 12 + 4 * ppg),
                 'note': 'solve() with a host frequency array; k, k_native and the tracking tables come back, psi_hat '
                         '(37 GB per block) stays on the device until it is read'},
-        'gpu_launches': None, 'clocks': clocks.summary(),
+        'gpu_launches': cfg4_launches(n2, ppg) * args.steps, 'clocks': clocks.summary(),
     }
     out['cpu_baseline'] = cpu_baseline_cfg4() if world == 1 and not args.no_cpu else None
     if saved_stdout is not None:
@@ -536,6 +542,17 @@ def gpu_arm_cfg4(args, torch, dist, rank, world, local, saved_stdout):
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cfg4_launches(n2, nf, nb=32, chunk=74):
+    """Kernel launches of one cfg4 step (solve() in chunks of `chunk` frequencies): per chunk the blocked
+    reduction (balance, 2 per column, 1 + 6 per panel, 2 pack), windowed QR + 3 cascade stages, k_modes_col,
+    3 per panel of the blocked back-transformation + scale + norm, tracking (bpsi, track_mma); then the
+    column gather of the kept mode shapes."""
+    panels = -(-(n2 - 2) // nb)
+    per_chunk = 1 + 2 * (n2 - 2) + 7 * panels + 2 + 4 + 1 + 3 * panels + 2 + 2
+    chunks = -(-nf // chunk)
+    return chunks * per_chunk + chunks
 
 
 def cpu_baseline_cfg4():
