@@ -738,8 +738,8 @@ def _shard_plan(nf, world, unit, K=None, first=None):
     per = nf // world
     plan = os.environ.get('AXS_SHARD_PLAN', 'fine')
     if K is None and first is None and 'AXS_SHARD_K' not in os.environ and 'AXS_SHARD_FIRST' not in os.environ \
-            and world >= 4 and per >= 8 * unit and plan != 'pairs2':
-        # Four or more ranks share the host's memory system for their downloads (measured on 8 B200s:
+            and world >= 6 and per >= 8 * unit and plan != 'pairs2':
+        # Many ranks share the host's memory system for their downloads (measured on 8 B200s:
         # ~19 GB/s per GPU, 13 us per frequency point against 27 us of compute), so the downloads have to
         # start early and keep running.  Measured end to end on 8 B200s, 2000 points per rank
         # (profiles/r2_pipe_trace_n8_*.txt):
@@ -747,7 +747,9 @@ def _shard_plan(nf, world, unit, K=None, first=None):
         #   'fine'      seven chunks of two waves of `unit` matrices, remainder last       192 k  (default)
         #   'geometric' three balanced pairs 591 591 | 295 295 | 114 114                   185 k
         # Small chunks lose compute rate (a chunk of 295 matrices fills only half of the 4-CTAs-per-SM QR
-        # stage), large ones delay the downloads; 'fine' is the best of the three.
+        # stage), large ones delay the downloads; 'fine' is the best of the three at eight ranks.  At four
+        # ranks (less contention per download) the two-pair plan measured 109.5 k against 106.7 k for 'fine',
+        # so the fine plan starts at six ranks.
         if plan == 'fine':
             kept = 2 * unit - 1
             K = min(8, max(2, int(round(per / float(unit) / 2))))

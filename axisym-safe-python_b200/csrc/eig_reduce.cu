@@ -501,7 +501,6 @@ extern "C" int axs_launch_reduce_oc(int N, int hb, const cplx* K0s, const cplx* 
     if (e != cudaSuccess) return (int)e;
     if (n <= 128) {
         if (nw == 8) return launch_oc<8, 4, true, false>(n, nf, wk, st);
-        if (nw == 9) return launch_oc<8, 4, true, true>(n, nf, wk, st);     // 8 warps, software-pipelined pass
         return launch_oc<12, 4, true, false>(n, nf, wk, st);
     }
     return launch_oc<8, 6, false, false>(n, nf, wk, st);

@@ -20,8 +20,8 @@ G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), 0
 ref = {i: so.eig_normalised(op, 2 * np.pi * c['f'][i])[0] for i in (0, nf // 2, nf - 1)}
 for bul in sys.argv[2:] or ['0', '2', '4', '6', '8']:
     if ':' in bul:
-        bul, stg = bul.split(':'); os.environ['AXS_HQR_STAGES'] = stg
-    os.environ['AXS_HQR_BULGES'] = bul
+        bul, stg = bul.split(':'); nat.set_tuning('hqr_stages', int(stg))
+    nat.set_tuning('hqr_bulges', int(bul))
     best = 1e9
     for _ in range(3):
         torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -30,7 +30,7 @@ for bul in sys.argv[2:] or ['0', '2', '4', '6', '8']:
     err = max(so.match_eigenvalues(ref[i], kk[i])[1] for i in ref)
     print('bulges=%s  %.2f ms for %d matrices  (%.2f ms per 2000)  max err %.1e  failed %d' % (bul, best, nf, best * 2000 / nf, err, int(info.sum())), flush=True)
 # modes timing
-os.environ['AXS_HQR_BULGES'] = '6'
+nat.set_tuning('hqr_bulges', int('6'))
 k, info = nat.hqr(N, nf, work)
 for _ in range(2):
     torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

@@ -20,7 +20,7 @@ nat.check(L.axs_reduce(N, ops.hb, P(ops.K0s), P(ops.Cb), P(ops.Mb), P(ops.K1c), 
 k, info = nat.hqr(N, nf, work)
 out = {}
 for var in sys.argv[2:] or ['0', '1']:
-    os.environ['AXS_BACKNORM_WY'] = var
+    nat.set_tuning('backnorm_wy', int(var))
     best = 1e9
     for _ in range(4):
         torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

@@ -19,7 +19,7 @@ L = nat.lib(); st = nat._stream(torch); P = nat._ptr
 G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), 0); op = so.operators(G, 0)
 ref = {i: so.eig_normalised(op, 2 * np.pi * c['f'][i])[0] for i in (0, nf // 2, nf - 1)}
 for var in sys.argv[2:] or ['0', '8', '12', '16']:
-    os.environ['AXS_REDUCE_OC'] = var
+    nat.set_tuning('reduce_oc', int(var))
     best = 1e9
     for _ in range(4):
         torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

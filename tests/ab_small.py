@@ -18,7 +18,7 @@ L = nat.lib(); st = nat._stream(torch); P = nat._ptr
 nat.check(L.axs_reduce(N, ops.hb, P(ops.K0s), P(ops.Cb), P(ops.Mb), P(ops.K1c), P(ops.K6d), P(omega), nf, None,
                        P(work.buf), work.bytes, st), 'reduce')
 for var in ('0', '1'):
-    os.environ['AXS_REDUCE_PREBAL'] = var
+    nat.set_tuning('reduce_prebal', int(var))
     best = 1e9
     for _ in range(3):
         torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -29,7 +29,7 @@ for var in ('0', '1'):
     print('%s 2N=%d prebal=%s: reduce %.2f ms per %d points' % (name, 2 * N, var, best, nf), flush=True)
 res = {}
 for var in ('0', '1'):
-    os.environ['AXS_HQR_SMALL_DIRECT'] = var
+    nat.set_tuning('hqr_small_direct', int(var))
     best = 1e9
     for _ in range(3):
         torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
