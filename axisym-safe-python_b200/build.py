@@ -14,7 +14,7 @@ SOURCES = ['api.cu', 'assemble.cu', 'eig_small.cu', 'eig_reduce.cu', 'eig_backx.
 HEADERS = ['common.cuh', 'aed.cuh', os.path.join('..', '..', 'include', 'axisafe_b200.h')]
 OUT = os.path.join(HERE, 'axisafe_b200', '_lib', 'libaxisafe_b200.so')
 OBJ = os.path.join(HERE, 'build')
-FLAGS = (['-DOC_TIMING'] if os.environ.get('AXS_OC_TIMING') else []) + [
+FLAGS = (['-DOC_TIMING'] if os.environ.get('AXS_OC_TIMING') else []) + (['-DAED_PROFILE'] if os.environ.get('AXS_AED_PROFILE') else []) + [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']
 
 

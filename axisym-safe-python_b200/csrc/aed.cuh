@@ -29,6 +29,9 @@ struct AedScratch {
     int ns;                             // number of undeflated eigenvalues (0 .. nw)
     int ok;                             // 0: the window QR did not converge, the window is left alone
     int iters;                          // QR sweeps spent on the window (statistics)
+#ifdef AED_PROFILE
+    long long prof[8];                  // cycles: load, schur, reorder, rehess; steps: schur rotations, swaps, rehess rotations, calls
+#endif
 };
 
 #ifdef AED_HOST
@@ -135,6 +138,14 @@ AED_FN void aed_window(const cplx* H, int l, int u, int nw, int lane)
     }
     const cplx spike = (kw > l) ? H[hcol_off(kw - 1) + kw] : mk(0, 0);
     AED_SYNC();
+#ifdef AED_PROFILE
+    long long pc0 = clock64(), pc1; int pn_rot = 0, pn_swap = 0, pn_reh = 0;
+#define AED_PMARK(i) { pc1 = clock64(); if (lane == 0) S->prof[i] += pc1 - pc0; pc0 = pc1; }
+#define AED_PCNT(v) ++v
+#else
+#define AED_PMARK(i)
+#define AED_PCNT(v)
+#endif
 
     // ---- 1. Schur form of the window (implicit single-shift QR, zlahqr tests) -----------------
     int iu = nw - 1, its = 0, total = 0, ok = 1;
@@ -151,6 +162,7 @@ AED_FN void aed_window(const cplx* H, int l, int u, int nw, int lane)
         }
 #endif
         AED_SYNC();                                       // every lane has read the subdiagonal
+        AED_PMARK(0)
         if (il > 0) { AED_LANES(q, 0, 1) S->T[il][il - 1] = mk(0, 0); }
         if (il == iu) { --iu; its = 0; AED_SYNC(); continue; }
         ++its; ++total;
@@ -158,17 +170,24 @@ AED_FN void aed_window(const cplx* H, int l, int u, int nw, int lane)
         cplx sig = aed_shift2(S->T[iu - 1][iu - 1], S->T[iu - 1][iu], S->T[iu][iu - 1], S->T[iu][iu]);
         if (its == 10 || its == 20) sig = cadd(S->T[iu][iu], mk(0.75 * cabs1(S->T[iu][iu - 1]), 0));
         AED_SYNC();
+        AED_PMARK(1)
         for (int k = il; k < iu; ++k) {
             const cplx x = (k == il) ? csub(S->T[il][il], sig) : S->T[k][k - 1];
             const cplx y = (k == il) ? S->T[il + 1][il] : S->T[k + 1][k - 1];
             double c; cplx s, r;
             aed_rot(x, y, c, s, r);
             AED_SYNC();                                   // x, y read by every lane before they change
+            AED_PMARK(2)
             if (k > il) { AED_LANES(q, 0, 1) { S->T[k][k - 1] = r; S->T[k + 1][k - 1] = mk(0, 0); } }
             aed_apply(S, nw, k, k, (k + 2 < iu) ? k + 2 : iu, c, s, lane);
+            AED_PMARK(3)
+            AED_PCNT(pn_rot);
         }
     }
-    S->ok = ok; S->iters = total;                         // (every lane stores the same value)
+    S->ok = ok; S->iters = total;
+#ifdef AED_PROFILE
+    if (lane == 0) S->prof[5] += total;
+#endif                         // (every lane stores the same value)
     if (!ok) { S->ns = nw; AED_SYNC(); return; }
 
     // ---- 2. spike test from the bottom, undeflatable eigenvalues to the top (zlaqr2, ztrexc) ---
@@ -190,11 +209,15 @@ AED_FN void aed_window(const cplx* H, int l, int u, int nw, int lane)
             }
             AED_LANES(q, 0, 1) { S->T[k][k] = t22; S->T[k + 1][k + 1] = t11; }
             AED_SYNC();
+            AED_PCNT(pn_swap);
         }
         ++ilst;
     }
     AED_LANES(j, 0, ns) S->shift[j] = S->T[j][j];
     S->ns = ns;
+#ifdef AED_PROFILE
+    if (lane == 0) { S->prof[4] += pn_rot; S->prof[7] += 1; }
+#endif
     if (ns == nw) { AED_SYNC(); return; }                 // nothing deflated: the caller leaves H alone
 
     // ---- 3. spike vector and leading ns x ns part back to Hessenberg form ----------------------
@@ -207,6 +230,7 @@ AED_FN void aed_window(const cplx* H, int l, int u, int nw, int lane)
             AED_SYNC();
             AED_LANES(q, 0, 1) { S->sv[j - 1] = r; S->sv[j] = mk(0, 0); }
             aed_apply(S, nw, j - 1, j - 1, (j + 1 < ns - 1) ? j + 1 : ns - 1, c, s, lane);
+            AED_PCNT(pn_reh);
         }
         for (int kk = j; kk + 1 <= ns - 1; ++kk) {         // chase the bulge T(kk+1, kk-1) out of the bottom
             double c; cplx s, r;
@@ -214,8 +238,12 @@ AED_FN void aed_window(const cplx* H, int l, int u, int nw, int lane)
             AED_SYNC();
             AED_LANES(q, 0, 1) { S->T[kk][kk - 1] = r; S->T[kk + 1][kk - 1] = mk(0, 0); }
             aed_apply(S, nw, kk, kk, (kk + 2 < ns - 1) ? kk + 2 : ns - 1, c, s, lane);
+            AED_PCNT(pn_reh);
         }
     }
     AED_LANES(q, 0, 1) S->spike_new = (ns > 0) ? S->sv[0] : mk(0, 0);
     AED_SYNC();
+#ifdef AED_PROFILE
+    if (lane == 0) S->prof[6] += pn_reh;
+#endif
 }

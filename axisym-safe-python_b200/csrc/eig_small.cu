@@ -356,6 +356,9 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
     cplx* eig = eig_all + (long long)f * n;
     __syncthreads();
 
+#ifdef AED_PROFILE
+    if (tid < 8) g_aed.prof[tid] = 0;
+#endif
     int its = 0, failed = 0;
     int n_macro = 0, n_batch = 0, n_aed = 0, n_aed_defl = 0;
     long long clk[4] = {0, 0, 0, 0}, clk0 = 0;            // thread 0: cycles in the AED window / its application / the sweeps
@@ -607,6 +610,11 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
         }
         AED_CLK(3)
     }
+#ifdef AED_PROFILE
+    if (tid == 0 && first_stage && f == 0 && aed_nw >= 2)
+        printf("AED_PROFILE stage1 f0: calls %lld | cycles scan %lld shift %lld rot %lld apply %lld | steps %lld sweeps %lld rehess %lld\n",
+               g_aed.prof[7], g_aed.prof[0], g_aed.prof[1], g_aed.prof[2], g_aed.prof[3], g_aed.prof[4], g_aed.prof[5], g_aed.prof[6]);
+#endif
     if (tid == 0) {
         info[f] = first_stage ? failed : info[f] + failed;
         ucur[f] = u;
