@@ -332,7 +332,9 @@ static size_t reduce_smem(int n) {
 // rejected in round 1 (explicit-shift wavefronts, register carry, leader-owned diagonal block,
 // complex-cosine rotations, the windowed warp-specialised stage 1) are in the git history
 // (commit 3cb38ed) and in DESIGN.md section 4.5; they are no longer compiled into the library.
-template <int NT, int MINB, int NITEMS, bool OPT = false>
+// AED = false instances do not reference the window scratch (2.6 KB of static shared memory), so their
+// stage capacities are the round-1 ones (117 / 95 / 82 instead of 116 / 93 / 79).
+template <int NT, int MINB, int NITEMS, bool OPT = false, bool AED = false>
 __global__ void __launch_bounds__(NT, MINB)
 k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* __restrict__ Hc_all,
          cplx* __restrict__ Hp_all, cplx* __restrict__ eig_all, int* __restrict__ info, int* __restrict__ ucur,
@@ -357,7 +359,7 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
     __syncthreads();
 
 #ifdef AED_PROFILE
-    if (tid < 8) g_aed.prof[tid] = 0;
+    if constexpr (AED) if (tid < 8) g_aed.prof[tid] = 0;
 #endif
     int its = 0, failed = 0;
     int n_macro = 0, n_batch = 0, n_aed = 0, n_aed_defl = 0;
@@ -409,6 +411,7 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
         }
         // ---- aggressive early deflation on the trailing window (zlaqr2 semantics) ------------
         have_shifts = false;
+        if constexpr (AED) {
         if (aed_nw >= 2 && u - l + 1 >= 3) {
             __syncthreads();                              // H(l, l-1) = 0 is visible
             const int nw = (aed_nw < u - l + 1) ? aed_nw : u - l + 1;
@@ -468,6 +471,7 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
                 if (u < l + 1 || nd * 100 >= 14 * nw) continue;
             }
         }
+        }                                                 // if constexpr (AED)
         const int m = u - l + 1;
         if (m < 2) continue;
         int nb = (m - 2) / MB_D + 1;
@@ -611,7 +615,7 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
         AED_CLK(3)
     }
 #ifdef AED_PROFILE
-    if (tid == 0 && first_stage && f == 0 && aed_nw >= 2)
+    if constexpr (AED) if (tid == 0 && first_stage && f == 0 && aed_nw >= 2)
         printf("AED_PROFILE stage1 f0: calls %lld | cycles scan %lld shift %lld rot %lld apply %lld | steps %lld sweeps %lld rehess %lld\n",
                g_aed.prof[7], g_aed.prof[0], g_aed.prof[1], g_aed.prof[2], g_aed.prof[3], g_aed.prof[4], g_aed.prof[5], g_aed.prof[6]);
 #endif
@@ -916,17 +920,23 @@ static int launch_mb(int nf, size_t smem, cudaStream_t st, int n, int bmax, int 
 {
     int aed = axs_tuning()->hqr_aed;
     if (aed > AED_MAX) aed = AED_MAX;
-    AXS_SMEM_ONCE(smem, k_hqr_mb<NT, MINB, NITEMS, OPT>);
-    k_hqr_mb<NT, MINB, NITEMS, OPT><<<nf, NT, smem, st>>>(n, bmax, first, m_stop, aed, Hc, Hp, eig, info, ucur, stats);
+    if (aed >= 2) {
+        AXS_SMEM_ONCE(smem, k_hqr_mb<NT, MINB, NITEMS, OPT, true>);
+        k_hqr_mb<NT, MINB, NITEMS, OPT, true><<<nf, NT, smem, st>>>(n, bmax, first, m_stop, aed, Hc, Hp, eig, info, ucur, stats);
+    } else {
+        AXS_SMEM_ONCE(smem, k_hqr_mb<NT, MINB, NITEMS, OPT, false>);
+        k_hqr_mb<NT, MINB, NITEMS, OPT, false><<<nf, NT, smem, st>>>(n, bmax, first, m_stop, 0, Hc, Hp, eig, info, ucur, stats);
+    }
     return (int)cudaGetLastError();
 }
 
 // Largest active window whose packed storage fits `per_sm` times into the shared memory of an SM
-// (5 KB per CTA: static shared memory of k_hqr_mb incl. the AED scratch + the 1 KB the system reserves).
+// (per CTA 2 KB: static shared memory of k_hqr_mb + the 1 KB the system reserves; 5 KB with the AED scratch).
 extern "C" int axs_hqr_stage_capacity(int per_sm)
 {
+    const size_t slack = (axs_tuning()->hqr_aed >= 2) ? 5120 : 2048;
     int m = 0;
-    while (hqr_mb_smem(m + 1) + 5120 <= (size_t)(227 * 1024 / per_sm)) ++m;
+    while (hqr_mb_smem(m + 1) + slack <= (size_t)(227 * 1024 / per_sm)) ++m;
     return m;
 }
 
