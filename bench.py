@@ -227,6 +227,10 @@ def gpu_arm(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     import axisafe_b200 as ax
     from axisafe_b200 import cases, _native as nat
+    numa_node = None
+    if world > 1 and os.environ.get('AXS_NUMA_BIND', '1') != '0':
+        # one process per GPU: run (and allocate the pinned download buffers) on the GPU's own NUMA node
+        numa_node = nat.bind_host_to_device_numa(local)
 
     if args.config == 'cfg4':
         return gpu_arm_cfg4(args, torch, dist, rank, world, local, saved_stdout)
@@ -396,6 +400,7 @@ def gpu_arm(args):
                 'k_only': {'value': nf_total / e2e_k_s, 'note': 'solve() without reading psi_hat back'}},
         'gpu_launches': ((2 if nloc >= 128 else 1) * 9 + 3) * args.steps,   # per chunk: balance, reduce_oc, hqr x4, modes, wy_tfactor, backnorm_wy; then bpsi, track_mma, apply_order
         'qr_counters': qr_counters(nat, N, nloc, work),
+        'numa_node_rank0': numa_node,
         'clocks': clocks.summary(),
         'hbm_peak_gbs': peaks.get('hbm_gbs'),
     }

@@ -17,6 +17,7 @@
 #define MB_D 3
 static long g_iters = 0;
 static int g_stage[4] = {0, 0, 0, 0}, g_mstage[4] = {0, 0, 0, 0};
+static double g_work = 0.0;   // sum over batches of macro steps x active size (cost model of the windowed large-path QR)
 #define MB_MAX 8
 typedef std::vector<cplx> Packed;
 static inline cplx& HP(Packed& H, int i, int j) { return H[hcol_off(j) + i]; }
@@ -155,6 +156,7 @@ static void solve(Packed& H, int n, int aed_nw, int bmax, std::vector<cplx>& eig
         for (int b = 0; b < nb; ++b) sweep(H, l, u, s_shift[b]);
         n_macro += (m - 1) + (nb - 1) * MB_D;
         g_mstage[u >= 116 ? 0 : u >= 93 ? 1 : u >= 79 ? 2 : 3] += (m - 1) + (nb - 1) * MB_D;
+        g_work += (double)((m - 1) + (nb - 1) * MB_D) * m;
         ++n_batch;
     }
     st[0] = n_macro; st[1] = n_batch; st[2] = n_aed; st[3] = n_aed_defl; st[4] = failed;
@@ -190,6 +192,7 @@ int main(int argc, char** argv)
         std::vector<cplx> eig(n);
         int st[5];
         solve(H, n, nw, nb, eig, st);
+        if (getenv("AED_STAGES")) fprintf(stderr, "WORK %.4g\n", g_work);
         if (getenv("AED_STAGES")) fprintf(stderr, "STAGES macro %d %d %d %d aed %d %d %d %d iters %ld\n", g_mstage[0], g_mstage[1], g_mstage[2], g_mstage[3], g_stage[0], g_stage[1], g_stage[2], g_stage[3], g_iters);
         fwrite(st, sizeof(int), 5, fo);
         fwrite(eig.data(), sizeof(cplx), n, fo);
