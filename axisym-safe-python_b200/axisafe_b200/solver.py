@@ -750,7 +750,13 @@ def _shard_plan(nf, world, unit, K=None, first=None):
         # stage), large ones delay the downloads; 'fine' is the best of the three at eight ranks.  At four
         # ranks (less contention per download) the two-pair plan measured 109.5 k against 106.7 k for 'fine',
         # so the fine plan starts at six ranks.
-        if plan == 'fine':
+        if plan == 'balanced':
+            # two balanced pairs 66 % | 34 %: the last download (34 % of the block) stays exposed, but every
+            # chunk is large enough to compute at the full rate
+            c1 = int(round(0.33 * per))
+            c2 = per // 2 - c1
+            sizes = [c1, c1, c2, per - 2 * c1 - c2]
+        elif plan == 'fine':
             kept = 2 * unit - 1
             K = min(8, max(2, int(round(per / float(unit) / 2))))
             while kept * (K - 1) >= per:
