@@ -42,6 +42,7 @@ _SIGNATURES = {
                         [ctypes.c_void_p] * 3 + [ctypes.c_longlong, ctypes.c_void_p]),
     'axs_track_scan': (ctypes.c_int, [ctypes.c_void_p] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p]),
     'axs_apply_order': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 6),
+    'axs_copy_to_pinned': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p]),
     'axs_select_modes': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 2 + [ctypes.c_int] +
                          [ctypes.c_void_p] * 3),
     'axs_energy_ratio': (ctypes.c_int, [ctypes.c_int] * 2 + [ctypes.c_void_p] * 2 +
@@ -407,6 +408,21 @@ def track_pairs_into(ops, psi, npairs, arg, amax, scratch):
         raise RuntimeError('tracking scratch too small')
     check(lib().axs_track_pairs(ops.N, ops.hb, _ptr(ops.Cb), _ptr(ops.K6d), _ptr(psi), npairs, _ptr(arg),
                                 _ptr(amax), _ptr(scratch), need, _stream(torch)), 'axs_track_pairs')
+
+
+def copy_to_pinned(dst_pinned, src_device):
+    """axs_copy_to_pinned on the current stream: ``dst_pinned`` (contiguous pinned host tensor) <- ``src_device``
+    (contiguous device tensor of the same byte size), stored by a kernel instead of the D2H copy engine."""
+    torch = torch_cuda()
+    nbytes = src_device.numel() * src_device.element_size()
+    if nbytes != dst_pinned.numel() * dst_pinned.element_size() or not dst_pinned.is_pinned():
+        raise ValueError('copy_to_pinned: size mismatch or destination not pinned')
+    if nbytes == 0:
+        return
+    if not (src_device.is_contiguous() and dst_pinned.is_contiguous()):
+        raise ValueError('copy_to_pinned: tensors must be contiguous')
+    check(lib().axs_copy_to_pinned(_ptr(src_device), ctypes.c_void_p(dst_pinned.data_ptr()), nbytes, _stream(torch)),
+          'axs_copy_to_pinned')
 
 
 def fixup_row(prev, a, m, n2):

@@ -559,11 +559,13 @@ def _solve_pipelined(sol, torch, _native, ops, nf, n2, host_work=None):
             ev_track[c].record(st)
         with torch.cuda.stream(ss):                      # small tables on their own stream: waiting for the
             ss.wait_event(ev_track[c])                   # tracking of chunk c must not hold up psi downloads
-            k_h[lo:hi].copy_(k_nat[lo * n2:hi * n2].view(hi - lo, n2), non_blocking=True)
-            info_h[lo:hi].copy_(info[lo:hi], non_blocking=True)
+            # (stored by a kernel through the unified address space: a cudaMemcpyAsync would queue behind the
+            # bulk psi_hat download of the previous chunk on the D2H engine)
+            _native.copy_to_pinned(k_h[lo:hi], k_nat[lo * n2:hi * n2])
+            _native.copy_to_pinned(info_h[lo:hi], info[lo:hi])
             if hi - 1 > p0:
-                arg_h[p0:hi - 1].copy_(arg[p0 * n2:(hi - 1) * n2].view(-1, n2), non_blocking=True)
-                amax_h[p0:hi - 1].copy_(amax[p0 * n2:(hi - 1) * n2].view(-1, n2), non_blocking=True)
+                _native.copy_to_pinned(arg_h[p0:hi - 1], arg[p0 * n2:(hi - 1) * n2])
+                _native.copy_to_pinned(amax_h[p0:hi - 1], amax[p0 * n2:(hi - 1) * n2])
             ev_small[c].record(ss)
 
     def finish(c):
@@ -875,10 +877,12 @@ def _solve_sharded_pipelined(sol, torch, _native, ops, nf, n2, rank, world, host
             ev_track[c].record(st)
         with torch.cuda.stream(ss):
             ss.wait_event(ev_track[c])
-            info_h[a:b].copy_(info[a:b], non_blocking=True)
+            # (kernel stores into the pinned tables: a cudaMemcpyAsync would queue behind the bulk psi_hat
+            # download of the previous chunk on the D2H engine - measured on 8 B200s)
+            _native.copy_to_pinned(info_h[a:b], info[a:b])
             if b - a > 1:
-                arg_h[a:b - 1].copy_(arg[a * n2:(b - 1) * n2].view(-1, n2), non_blocking=True)
-                amax_h[a:b - 1].copy_(amax[a * n2:(b - 1) * n2].view(-1, n2), non_blocking=True)
+                _native.copy_to_pinned(arg_h[a:b - 1], arg[a * n2:(b - 1) * n2])
+                _native.copy_to_pinned(amax_h[a:b - 1], amax[a * n2:(b - 1) * n2])
             ev_small[c].record(ss)
 
     # index tensors and buffers of the final gather, prepared before the pipeline starts (a pageable H2D

@@ -29,6 +29,7 @@ int axs_launch_quad_forms(int, int, const cplx*, const int*, int, const int*, in
 int axs_launch_modal_projection(int, int, const cplx*, const cplx*, cplx*, cudaStream_t);
 int axs_launch_energy_ratio(int, int, const cplx*, const int*, int, const int*, const int*, const cplx*,
                             int, const int*, const int*, const cplx*, double*, cudaStream_t);
+int axs_launch_copy_to_pinned(const void*, void*, long long, cudaStream_t);
 }
 
 #define AXS_ERR_TOO_LARGE 100001
@@ -347,6 +348,14 @@ extern "C" int axs_hqr_stats(int N, int nf, const void* work, int* stats, void* 
     AXS_CUDA_OK(cudaMemcpyAsync(stats, wk.stats, (size_t)nf * AXS_QR_STATS * sizeof(int), cudaMemcpyDeviceToDevice,
                                 (cudaStream_t)stream));
     return 0;
+}
+
+extern "C" int axs_copy_to_pinned(const void* src, void* h_pinned_dst, long long bytes, void* stream)
+{
+    if (!src) return -1;
+    if (!h_pinned_dst) return -2;
+    if (bytes < 0 || (bytes & 3)) return -3;
+    return axs_launch_copy_to_pinned(src, h_pinned_dst, bytes, (cudaStream_t)stream);
 }
 
 extern "C" long long axs_track_worksize(int N, int npairs)

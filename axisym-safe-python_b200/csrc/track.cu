@@ -484,3 +484,26 @@ extern "C" int axs_launch_apply_order(int n, int nf, const int* order, const cpl
     k_apply_order<<<dim3(bx, nf), 256, 0, st>>>(n, order, k_in, psi_in, k_out, psi_out);
     return (int)cudaGetLastError();
 }
+
+// -----------------------------------------------------------------------------------------
+// Small device -> pinned-host copies done by the SMs instead of the copy engine.  The pipelined sweeps
+// download the mode shapes of a chunk (0.1 .. 0.3 GB) with cudaMemcpyAsync while the next chunk
+// computes; the few hundred KB of tracking tables the host is waiting for would queue behind that bulk
+// transfer on the same D2H engine.  Pinned host memory is mapped into the device address space (UVA),
+// so a kernel can store to it directly and the stores interleave with the DMA traffic on the link.
+__global__ void __launch_bounds__(256)
+k_copy_words(const unsigned int* __restrict__ src, unsigned int* __restrict__ dst, long long nwords)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+extern "C" int axs_launch_copy_to_pinned(const void* src, void* dst, long long bytes, cudaStream_t st)
+{
+    const long long nwords = bytes / 4;
+    if (nwords <= 0) return 0;
+    long long blocks = (nwords + 255) / 256;
+    if (blocks > 296) blocks = 296;
+    k_copy_words<<<(int)blocks, 256, 0, st>>>((const unsigned int*)src, (unsigned int*)dst, nwords);
+    return (int)cudaGetLastError();
+}

@@ -152,6 +152,13 @@ int axs_track_pairs(int N, int hb, const axs_cplx* Cb, const axs_cplx* K6d,
 int axs_track_scan(const int* h_arg, const double* h_amax, int nf, int n2, int start,
                    int* h_order);
 
+/* Small device -> PINNED host copy executed by the SMs (a kernel storing through the unified address space)
+ * instead of the copy engine, so that the few hundred KB of tracking tables the host scan waits for
+ * (solver.py:159-182 needs them in order) do not queue behind the bulk download of psi_hat on the same
+ * D2H engine.  h_pinned_dst must be page-locked host memory (cudaHostAlloc / torch pin_memory); bytes a
+ * multiple of 4.  Asynchronous on `stream`. */
+int axs_copy_to_pinned(const void* src, void* h_pinned_dst, long long bytes, void* stream);
+
 /* Column gather after tracking: k_out[f][c] = k[f][order[f][c]],
  * psi_out[f][r][c] = psi[f][r][order[f][c]]  (solver.py:176-182). psi/psi_out may be NULL. */
 int axs_apply_order(int n2, int nf, const int* order, const axs_cplx* k, const axs_cplx* psi,
