@@ -4,24 +4,26 @@
 // together they replace scipy.linalg.eig / LAPACK zgeev, solver.py:136, and solver.py:142),
 // but the matrix of one frequency no longer fits the shared memory of one SM:
 //
-//   k_reduce_big  one CTA per frequency; the work matrix streams from L2/HBM.  The rank-2
-//                 Householder update is a 2-D (row block x column group) decomposition over
-//                 the warps; y = A^H v and w = A v are accumulated with global fp64 reductions.
-//   k_hqr_big     one CTA per frequency; a chain of 8 bulges is chased through a 48 x 48
-//                 DIAGONAL WINDOW held in shared memory for 24 steps ("phase D", the latency
-//                 bound part, identical to k_hqr_mb), the 24 x 8 rotations are recorded, and
-//                 the off-diagonal strips (columns right of the window, rows above it) are
-//                 then updated from 128-wide shared-memory tiles, one thread per column/row,
-//                 bulge-major so that the running element stays in a register ("phase O":
-//                 ~8 rotation updates per element moved, FP64-pipe bound instead of L2 bound).
-//                 Once the active block fits the shared-memory kernels the sweep is handed
-//                 over to the k_hqr_mb stages of eig_small.cu.
-//   k_modes_col   inverse iteration (H - k I) x = 1 as a bottom-up pivoted LU with column
-//                 operations, column-oriented: a CTA sweeps the columns of H from right to
-//                 left, every thread owns rows (cyclic) for M modes in registers, one barrier
-//                 per column.  State that has to survive (multipliers, pivots) is O(n) per mode.
-//   k_backx_big   applies the Householder reflectors to the Hessenberg-basis vectors; T threads
-//                 per mode keep the vector in registers.
+//   k_reduce_big  S(w), |a|^2 tables and the zgebal scaling (one CTA per frequency); with balance_only
+//                 the Hessenberg reduction itself is done by the blocked compact-WY / DMMA kernels of
+//                 eig_bigred.cu (default); otherwise (tuning big_blocked = 0) by the unblocked fused
+//                 rank-2 update below: 2-D (row block x column group) decomposition over the warps,
+//                 y = A^H v and w = A v accumulated with fixed-order reductions.
+//   k_hqr_big     a chain of 8 bulges is chased through a 48 x 48 DIAGONAL WINDOW held in shared memory
+//                 for 24 steps ("phase D", the latency bound part, identical to k_hqr_mb), the 24 x 8
+//                 rotations are recorded, and the off-diagonal strips (columns right of the window, rows
+//                 above it) are then updated from 128-wide shared-memory tiles, one thread per
+//                 column/row, bulge-major so that the running element stays in a register ("phase O").
+//                 One CTA per frequency, or - for batches that do not fill the GPU - a thread-block
+//                 cluster of 2 / 4 / 8 CTAs per frequency that shares the strip tiles.  Once the active
+//                 block fits the shared-memory kernels the sweep is handed over to the k_hqr_mb stages
+//                 of eig_small.cu.
+//   k_modes_col   inverse iteration (H - k I) x = 1 as a bottom-up pivoted LU with column operations,
+//                 column-oriented: a CTA sweeps the columns of H from right to left, every thread owns
+//                 rows (cyclic) for M modes in registers, one barrier per column.  State that has to
+//                 survive (multipliers, pivots) is O(n) per mode.
+//   k_backx_slab / k_backx_big   per-reflector back-transformation (slab of mode vectors in shared memory
+//                 while it fits; registers above that when the blocked form of eig_bigred.cu is off).
 //   k_norm_big    un-balanced vectors -> psi = v / sqrt(2k u^T K6 u + u^T C u), psi_hat layout.
 #include "common.cuh"
 #include <stdlib.h>

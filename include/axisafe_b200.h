@@ -34,9 +34,11 @@ const char* axs_strerror(int code);
 
 /* Largest dense problem size (2N) handled by the shared-memory eigen kernels (one SM holds the
  * whole Hessenberg matrix); above it and up to axs_max_n2() the same entry points run the
- * global-memory instance of the kernels (csrc/eig_big.cu): one CTA per frequency, the matrix
- * streams from L2/HBM, the QR sweep chases its bulge chain through a shared-memory diagonal
- * window and updates the off-diagonal strips from tiles. */
+ * global-memory instance of the kernels: a blocked compact-WY Hessenberg reduction with DMMA trailing
+ * updates that moves the batch through the reduction in lockstep (csrc/eig_bigred.cu), a windowed
+ * multi-bulge QR whose off-diagonal strips are shared by a thread-block cluster per matrix when the
+ * batch is small, column-oriented inverse iteration and a blocked DMMA back-transformation
+ * (csrc/eig_big.cu). */
 int axs_max_small_n2(void);
 int axs_max_n2(void);
 
