@@ -247,3 +247,214 @@ AED_FN void aed_window(const cplx* H, int l, int u, int nw, int lane)
     if (lane == 0) S->prof[6] += pn_reh;
 #endif
 }
+
+// =========================================================================================
+// Register-resident window (aed_window_reg): the same four steps, but T and Z never touch shared
+// memory while the warp works on them.  Lane L = 4 i + p owns the entries (i, 2p) and (i, 2p + 1) of T
+// and of Z in registers:
+//   * a row rotation (k, k+1) is ONE exchange between the lanes of row k and of row k+1 (lane +- 4)
+//     followed by a branch-free update of the own entries,
+//   * a column rotation (k, k+1) needs no exchange for even k (both columns sit in the same lane) and one
+//     exchange between neighbouring lanes for odd k,
+//   * the rotation itself is generated redundantly by every lane from two broadcast entries, so nothing
+//     has to be sent back,
+//   * the deflation scan gathers the three diagonals into lanes 1..iu (one ballot), the shift comes from
+//     four broadcast entries.
+// The dependent chain of a rotation step is two shuffles + the rotation + two 6-instruction updates
+// instead of a shared-memory round trip with three warp barriers; control flow is warp-uniform throughout
+// (every lane derives the same decisions from the same broadcast values), which is what the host build
+// checks by running this very source on an emulated warp (tests/host/warp_emul.h: 32 fibers, collectives
+// as rendezvous; AEDR_SHFL / AEDR_BALLOT / AEDR_CLZ are then supplied by the includer).
+// Results go to the same scratch object (T, Z, shift, spike_new, ns, ok, iters) as aed_window's.
+#ifndef AEDR_SHFL
+__device__ __forceinline__ cplx aedr_shfl_dev(cplx v, int src) {
+    return mk(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+#define AEDR_SHFL(v, src) aedr_shfl_dev((v), (src))
+#define AEDR_BALLOT(p) __ballot_sync(0xffffffffu, (p))
+#define AEDR_CLZ(m) __clz((int)(m))
+#endif
+
+// entry (ii, jj) of T / Z for warp-uniform ii, jj: broadcast from its owner lane
+#define AEDR_GET(ii, jj) AEDR_SHFL((((jj) & 1) ? t1 : t0), 4 * (ii) + ((jj) >> 1))
+#define AEDR_GETZ(ii, jj) AEDR_SHFL((((jj) & 1) ? z1 : z0), 4 * (ii) + ((jj) >> 1))
+#define AEDR_SET(ii, jj, v) do { if (i == (ii) && p == ((jj) >> 1)) { if ((jj) & 1) t1 = (v); else t0 = (v); } } while (0)
+
+// One similarity rotation in the plane (k, k+1): rows k, k+1 of the columns >= jlo, then columns k, k+1
+// of the rows <= ihi of T and of every row of Z (aed_apply for the register layout).  The row exchange
+// does not depend on the rotation, so it is issued BEFORE the rotation is generated (AEDR_ROWX) and its
+// latency hides behind the rsqrt chain; q0 / q1 are the partner row's entries (entries of columns < jlo
+// may be stale by then - they are not used).
+#define AEDR_ROWX(k, q0, q1)                                                                            \
+    const int rowx_src_ = (i == (k)) ? lane + 4 : ((i == (k) + 1) ? lane - 4 : lane);                      \
+    const cplx q0 = AEDR_SHFL(t0, rowx_src_), q1 = AEDR_SHFL(t1, rowx_src_)
+
+AED_INL void aedr_apply(cplx& t0, cplx& t1, cplx& z0, cplx& z1, int lane, int k, int jlo, int ihi, double c, cplx s,
+                        cplx q0, cplx q1)
+{
+    const int i = lane >> 2, p = lane & 3;
+    {
+        const bool top = (i == k), bot = (i == k + 1);
+        // top: c own + s other;  bottom: c own - conj(s) other
+        const cplx se = top ? s : mk(-s.x, s.y);
+        if (top || bot) {
+            if (2 * p >= jlo) t0 = cfma(se, q0, cscale(t0, c));
+            if (2 * p + 1 >= jlo) t1 = cfma(se, q1, cscale(t1, c));
+        }
+    }
+    if ((k & 1) == 0) {
+        if (p == (k >> 1)) {
+            if (i <= ihi) {
+                const cplx n0 = cfmac(t1, s, cscale(t0, c)), n1 = cfms(s, t0, cscale(t1, c));
+                t0 = n0; t1 = n1;
+            }
+            const cplx m0 = cfmac(z1, s, cscale(z0, c)), m1 = cfms(s, z0, cscale(z1, c));
+            z0 = m0; z1 = m1;
+        }
+    } else {
+        // column k is the odd entry of pair (k-1)/2, column k+1 the even entry of pair (k+1)/2
+        const bool isa = (p == (k >> 1)), isb = (p == ((k + 1) >> 1));
+        const int src = isa ? lane + 1 : (isb ? lane - 1 : lane);
+        const cplx rt = AEDR_SHFL(isa ? t1 : t0, src), rz = AEDR_SHFL(isa ? z1 : z0, src);
+        if (isa) {
+            if (i <= ihi) t1 = cfmac(rt, s, cscale(t1, c));
+            z1 = cfmac(rz, s, cscale(z1, c));
+        } else if (isb) {
+            if (i <= ihi) t0 = cfms(s, rt, cscale(t0, c));
+            z0 = cfms(s, rz, cscale(z0, c));
+        }
+    }
+}
+
+AED_FN void aed_window_reg(const cplx* H, int l, int u, int nw, int lane)
+{
+    AedScratch* const S = &g_aed;
+    const int kw = u - nw + 1;
+    const int i = lane >> 2, p = lane & 3, j0 = 2 * p, j1 = 2 * p + 1;
+    cplx t0 = (i < nw && j0 < nw && i <= j0 + 1) ? H[hcol_off(kw + j0) + kw + i] : mk(0, 0);
+    cplx t1 = (i < nw && j1 < nw && i <= j1 + 1) ? H[hcol_off(kw + j1) + kw + i] : mk(0, 0);
+    cplx z0 = mk(i == j0 ? 1.0 : 0.0, 0.0), z1 = mk(i == j1 ? 1.0 : 0.0, 0.0);
+    const cplx spike = (kw > l) ? H[hcol_off(kw - 1) + kw] : mk(0, 0);
+
+    // ---- 1. Schur form of the window ------------------------------------------------------------
+    int iu = nw - 1, its = 0, total = 0, ok = 1;
+    while (iu >= 1) {
+        // lane k (1 <= k <= iu) tests T(k, k-1): the three diagonals are gathered into the lanes
+        int il = 0;
+        {
+            const int k = (lane < nw) ? lane : nw - 1, km = (k > 0) ? k - 1 : 0;
+            const int s_d = 4 * k + (k >> 1), s_sub = 4 * k + (km >> 1), s_sup = 4 * km + (k >> 1);
+            const cplx d_a = AEDR_SHFL(t0, s_d), d_b = AEDR_SHFL(t1, s_d);
+            const cplx b_a = AEDR_SHFL(t0, s_sub), b_b = AEDR_SHFL(t1, s_sub);
+            const cplx p_a = AEDR_SHFL(t0, s_sup), p_b = AEDR_SHFL(t1, s_sup);
+            const cplx hkk = (k & 1) ? d_b : d_a;             // T(k, k)
+            const cplx hsub = (km & 1) ? b_b : b_a;           // T(k, k-1)
+            const cplx hsup = (k & 1) ? p_b : p_a;            // T(k-1, k)
+            const cplx hk1 = AEDR_SHFL(hkk, (lane + 31) & 31);      // T(k-1, k-1)
+            const cplx hsubm = AEDR_SHFL(hsub, (lane + 31) & 31);   // T(k-1, k-2)
+            const cplx hsubp = AEDR_SHFL(hsub, (lane + 1) & 31);    // T(k+1, k)
+            bool neg = false;
+            if (lane >= 1 && lane <= iu) {
+                const double sub = cabs1(hsub);
+                if (sub <= AED_SMALL) neg = true;
+                else {
+                    double tst = cabs1(hk1) + cabs1(hkk);
+                    if (tst == 0.0) {
+                        if (k - 2 >= 0) tst += cabs1(hsubm);
+                        if (k + 1 <= nw - 1) tst += cabs1(hsubp);
+                    }
+                    if (sub <= AED_EPS * tst) {
+                        const double up = cabs1(hsup);
+                        const double ab = fmax(sub, up), ba = fmin(sub, up);
+                        const double dd = cabs1(csub(hk1, hkk));
+                        const double aa = fmax(cabs1(hkk), dd), bb = fmin(cabs1(hkk), dd);
+                        const double sm = aa + ab;
+                        if (ba * (ab / sm) <= fmax(AED_SMALL, AED_EPS * (bb * (aa / sm)))) neg = true;
+                    }
+                }
+            }
+            const unsigned m = AEDR_BALLOT(neg);
+            il = m ? 31 - AEDR_CLZ(m) : 0;
+        }
+        if (il > 0) AEDR_SET(il, il - 1, mk(0, 0));
+        if (il == iu) { --iu; its = 0; continue; }
+        ++its; ++total;
+        if (its > 30) { ok = 0; break; }
+        cplx sig;
+        {
+            const cplx a11 = AEDR_GET(iu - 1, iu - 1), a12 = AEDR_GET(iu - 1, iu);
+            const cplx a21 = AEDR_GET(iu, iu - 1), a22 = AEDR_GET(iu, iu);
+            sig = aed_shift2(a11, a12, a21, a22);
+            if (its == 10 || its == 20) sig = cadd(a22, mk(0.75 * cabs1(a21), 0));
+        }
+        for (int k = il; k < iu; ++k) {
+            cplx x, y;
+            if (k == il) { x = csub(AEDR_GET(il, il), sig); y = AEDR_GET(il + 1, il); }
+            else { x = AEDR_GET(k, k - 1); y = AEDR_GET(k + 1, k - 1); }
+            AEDR_ROWX(k, q0, q1);
+            double c; cplx s, r;
+            aed_rot(x, y, c, s, r);
+            if (k > il) { AEDR_SET(k, k - 1, r); AEDR_SET(k + 1, k - 1, mk(0, 0)); }
+            aedr_apply(t0, t1, z0, z1, lane, k, k, (k + 2 < iu) ? k + 2 : iu, c, s, q0, q1);
+        }
+    }
+    if (!ok) {
+        if (lane == 0) { S->ok = 0; S->iters = total; S->ns = nw; }
+        AED_SYNC();
+        return;
+    }
+
+    // ---- 2. spike test from the bottom, undeflatable eigenvalues to the top -----------------------
+    int ns = nw, ilst = 0;
+    const double sp1 = cabs1(spike);
+    while (ilst < ns) {
+        double foo = cabs1(AEDR_GET(ns - 1, ns - 1));
+        if (foo == 0.0) foo = sp1;
+        if (sp1 * cabs1(AEDR_GETZ(0, ns - 1)) <= fmax(AED_SMALL, AED_EPS * foo)) { --ns; continue; }
+        for (int k = ns - 2; k >= ilst; --k) {
+            const cplx t11 = AEDR_GET(k, k), t22 = AEDR_GET(k + 1, k + 1), t12 = AEDR_GET(k, k + 1);
+            AEDR_ROWX(k, q0, q1);
+            double c; cplx s, r;
+            aed_rot(t12, csub(t22, t11), c, s, r);
+            aedr_apply(t0, t1, z0, z1, lane, k, k + 2, k - 1, c, s, q0, q1);     // rows: columns >= k+2, columns: rows < k
+            AEDR_SET(k, k, t22); AEDR_SET(k + 1, k + 1, t11);
+        }
+        ++ilst;
+    }
+    if (i == j0 && j0 < ns) S->shift[j0] = t0;
+    if (i == j1 && j1 < ns) S->shift[j1] = t1;
+    if (lane == 0) { S->ok = 1; S->iters = total; S->ns = ns; }
+
+    // ---- 3. spike vector (lane j holds entry j) and leading ns x ns part back to Hessenberg form ----
+    cplx sv = mk(0, 0);
+    if (ns < nw) {
+        {
+            const int j = lane & 7;
+            const cplx za = AEDR_SHFL(z0, j >> 1), zb = AEDR_SHFL(z1, j >> 1);      // Z(0, j)
+            if (lane < 8 && lane < ns) sv = cmulc(spike, (j & 1) ? zb : za);
+        }
+        for (int j = ns - 1; j >= 1; --j) {
+            {
+                const cplx x = AEDR_SHFL(sv, j - 1), y = AEDR_SHFL(sv, j);
+                AEDR_ROWX(j - 1, q0, q1);
+                double c; cplx s, r;
+                aed_rot(x, y, c, s, r);
+                if (lane == j - 1) sv = r;
+                if (lane == j) sv = mk(0, 0);
+                aedr_apply(t0, t1, z0, z1, lane, j - 1, j - 1, (j + 1 < ns - 1) ? j + 1 : ns - 1, c, s, q0, q1);
+            }
+            for (int kk = j; kk + 1 <= ns - 1; ++kk) {          // chase the bulge T(kk+1, kk-1) out of the bottom
+                const cplx x = AEDR_GET(kk, kk - 1), y = AEDR_GET(kk + 1, kk - 1);
+                AEDR_ROWX(kk, q0, q1);
+                double c; cplx s, r;
+                aed_rot(x, y, c, s, r);
+                AEDR_SET(kk, kk - 1, r); AEDR_SET(kk + 1, kk - 1, mk(0, 0));
+                aedr_apply(t0, t1, z0, z1, lane, kk, kk, (kk + 2 < ns - 1) ? kk + 2 : ns - 1, c, s, q0, q1);
+            }
+        }
+        if (lane == 0) S->spike_new = (ns > 0) ? sv : mk(0, 0);
+    }
+    S->T[i][j0] = t0; S->T[i][j1] = t1;
+    S->Z[i][j0] = z0; S->Z[i][j1] = z1;
+    AED_SYNC();
+}

@@ -51,6 +51,8 @@ static AxsTuning* tuning_mut(void)
         t.hqr_bulges = env_int("AXS_HQR_BULGES", 8);
         t.hqr_small_direct = env_int("AXS_HQR_SMALL_DIRECT", 1);
         t.hqr_aed = env_int("AXS_HQR_AED", 0);      // measured on B200: halves the macro steps, but the serial window costs more than it saves
+        t.hqr_aed_reg = env_int("AXS_HQR_AED_REG", 1);
+        t.hqr_aed_stages = env_int("AXS_HQR_AED_STAGES", 15);
         t.backnorm_wy = env_int("AXS_BACKNORM_WY", 1);
         t.backnorm_wy_modes = env_int("AXS_BACKNORM_WY_MODES", 64);
         t.bpsi_tiled = env_int("AXS_BPSI_TILED", 1);
@@ -74,6 +76,8 @@ static int* tuning_field(const char* name)
     if (!strcmp(name, "hqr_bulges")) return &t->hqr_bulges;
     if (!strcmp(name, "hqr_small_direct")) return &t->hqr_small_direct;
     if (!strcmp(name, "hqr_aed")) return &t->hqr_aed;
+    if (!strcmp(name, "hqr_aed_reg")) return &t->hqr_aed_reg;
+    if (!strcmp(name, "hqr_aed_stages")) return &t->hqr_aed_stages;
     if (!strcmp(name, "backnorm_wy")) return &t->backnorm_wy;
     if (!strcmp(name, "backnorm_wy_modes")) return &t->backnorm_wy_modes;
     if (!strcmp(name, "bpsi_tiled")) return &t->bpsi_tiled;

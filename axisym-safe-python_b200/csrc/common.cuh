@@ -184,6 +184,8 @@ struct AxsTuning {
     int hqr_bulges;         // AXS_HQR_BULGES: bulges in flight per batch (8)
     int hqr_small_direct;   // AXS_HQR_SMALL_DIRECT: problems that fit an SM twice skip the one-CTA-per-SM stage (1)
     int hqr_aed;            // AXS_HQR_AED: aggressive-early-deflation window (0 = off, the default; 2..8)
+    int hqr_aed_reg;        // AXS_HQR_AED_REG: 1 = register-resident window routine (shuffles), 0 = shared-memory routine
+    int hqr_aed_stages;     // AXS_HQR_AED_STAGES: bit s = AED in the stage with s + 1 CTAs per SM (bit 3: the >= 4 instances); 15 = all
     int backnorm_wy;        // AXS_BACKNORM_WY: blocked compact-WY back-transformation on DMMA tiles (1)
     int backnorm_wy_modes;  // AXS_BACKNORM_WY_MODES: modes per CTA (64 | 32)
     int bpsi_tiled;         // AXS_BPSI_TILED: tiled B psi kernel (1)

@@ -361,6 +361,8 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
 #ifdef AED_PROFILE
     if constexpr (AED) if (tid < 8) g_aed.prof[tid] = 0;
 #endif
+    const bool aed_reg = (aed_nw & 0x100) != 0;           // register-resident window routine (csrc/aed.cuh)
+    aed_nw &= 0xff;
     int its = 0, failed = 0;
     int n_macro = 0, n_batch = 0, n_aed = 0, n_aed_defl = 0;
     long long clk[4] = {0, 0, 0, 0}, clk0 = 0;            // thread 0: cycles in the AED window / its application / the sweeps
@@ -417,7 +419,10 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
             const int nw = (aed_nw < u - l + 1) ? aed_nw : u - l + 1;
             const int kw = u - nw + 1;
             AED_CLK(0)
-            if (tid < 32) aed_window(H, l, u, nw, tid);
+            if (tid < 32) {
+                if (aed_reg) aed_window_reg(H, l, u, nw, tid);
+                else aed_window(H, l, u, nw, tid);
+            }
             __syncthreads();
             AED_CLK(1)
             ++n_aed;
@@ -914,13 +919,24 @@ extern "C" int axs_launch_reduce(int N, int hb, const cplx* K0s, const cplx* Cb,
 }
 
 // launch one k_hqr_mb stage
+// AED window of the stage with `per_sm` co-resident CTAs (1 -> stage 1, 2, 3, >= 4 -> the last instances):
+// tuning hqr_aed, masked per stage by hqr_aed_stages (bit per_sm - 1)
+static int aed_window_of_stage(int per_sm)
+{
+    int aed = axs_tuning()->hqr_aed;
+    if (aed > AED_MAX) aed = AED_MAX;
+    const int bit = (per_sm >= 4) ? 3 : per_sm - 1;
+    if (aed < 2 || !((axs_tuning()->hqr_aed_stages >> bit) & 1)) return 0;
+    return aed;
+}
+
 template <int NT, int MINB, int NITEMS, bool OPT>
 static int launch_mb(int nf, size_t smem, cudaStream_t st, int n, int bmax, int first, int m_stop,
                      const cplx* Hc, cplx* Hp, cplx* eig, int* info, int* ucur, int* stats)
 {
-    int aed = axs_tuning()->hqr_aed;
-    if (aed > AED_MAX) aed = AED_MAX;
+    int aed = aed_window_of_stage(MINB);
     if (aed >= 2) {
+        if (axs_tuning()->hqr_aed_reg) aed |= 0x100;
         AXS_SMEM_ONCE(smem, k_hqr_mb<NT, MINB, NITEMS, OPT, true>);
         k_hqr_mb<NT, MINB, NITEMS, OPT, true><<<nf, NT, smem, st>>>(n, bmax, first, m_stop, aed, Hc, Hp, eig, info, ucur, stats);
     } else {
@@ -934,7 +950,7 @@ static int launch_mb(int nf, size_t smem, cudaStream_t st, int n, int bmax, int 
 // (per CTA 2 KB: static shared memory of k_hqr_mb + the 1 KB the system reserves; 5 KB with the AED scratch).
 extern "C" int axs_hqr_stage_capacity(int per_sm)
 {
-    const size_t slack = (axs_tuning()->hqr_aed >= 2) ? 5120 : 2048;
+    const size_t slack = (aed_window_of_stage(per_sm) >= 2) ? 5120 : 2048;
     int m = 0;
     while (hqr_mb_smem(m + 1) + slack <= (size_t)(227 * 1024 / per_sm)) ++m;
     return m;

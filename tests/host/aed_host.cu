@@ -8,6 +8,14 @@
 //   in : int32 n, l, u, nw, nb ; n*n complex128 column-major (upper Hessenberg)
 //   out (window): int32 ns, ok, iters ; T[AED_MAX*AED_MAX] row-major, Z[...] row-major, shift[AED_MAX], spike_new
 //   out (solve) : int32 macro, batches, aed_calls, aed_defl, failed ; n complex128 eigenvalues
+// AED_REG=1 (environment) runs the register-resident window aed_window_reg on an emulated warp
+// (warp_emul.h: 32 fibers, shuffles / ballots as rendezvous) instead of the shared-memory aed_window.
+#include "../../axisym-safe-python_b200/csrc/common.cuh"
+#include "warp_emul.h"
+static inline cplx wemu_shfl_c(int lane, cplx v, int src, int tag) { wemu::shfl2(lane, v.x, v.y, src, tag); return v; }
+#define AEDR_SHFL(v, src) wemu_shfl_c(lane, (v), (src), __LINE__)
+#define AEDR_BALLOT(p) wemu::ballot(lane, (p), __LINE__)
+#define AEDR_CLZ(m) __builtin_clz((unsigned)(m))
 #include "../../axisym-safe-python_b200/csrc/aed.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -20,6 +28,13 @@ static int g_stage[4] = {0, 0, 0, 0}, g_mstage[4] = {0, 0, 0, 0};
 static double g_work = 0.0;   // sum over batches of macro steps x active size (cost model of the windowed large-path QR)
 #define MB_MAX 8
 typedef std::vector<cplx> Packed;
+static bool use_reg() { static int v = getenv("AED_REG") ? atoi(getenv("AED_REG")) : 0; return v != 0; }
+// one window call: the shared-memory routine as sequential code, or the register routine on the emulated warp
+static void window_call(const cplx* H, int l, int u, int nw)
+{
+    if (use_reg()) wemu::run([=](int lane) { aed_window_reg(H, l, u, nw, lane); });
+    else aed_window(H, l, u, nw, 0);
+}
 static inline cplx& HP(Packed& H, int i, int j) { return H[hcol_off(j) + i]; }
 
 // one implicit single-shift QR sweep on the active block [l, u]: what ONE bulge of k_hqr_mb does
@@ -83,11 +98,12 @@ static void solve(Packed& H, int n, int aed_nw, int bmax, std::vector<cplx>& eig
         static int p_nibble = getenv("AED_NIBBLE") ? atoi(getenv("AED_NIBBLE")) : 14;
         static int p_minm = getenv("AED_MINM") ? atoi(getenv("AED_MINM")) : 3;
         static int p_every = getenv("AED_EVERY") ? atoi(getenv("AED_EVERY")) : 1;
+        static int p_umin = getenv("AED_UMIN") ? atoi(getenv("AED_UMIN")) : 0;   // AED only while u >= p_umin (stage mask of the kernel)
         static int batch_ctr = 0;
-        if (aed_nw >= 2 && u - l + 1 >= p_minm && (batch_ctr++ % p_every) == 0) {
+        if (aed_nw >= 2 && u >= p_umin && u - l + 1 >= p_minm && (batch_ctr++ % p_every) == 0) {
             const int nw = (aed_nw < u - l + 1) ? aed_nw : u - l + 1;
             const int kw = u - nw + 1;
-            aed_window(H.data(), l, u, nw, 0); S = g_aed;
+            window_call(H.data(), l, u, nw); S = g_aed;
             ++n_aed; g_stage[u >= 116 ? 0 : u >= 93 ? 1 : u >= 79 ? 2 : 3]++; g_iters += S.iters; if (getenv("AED_TRACE")) fprintf(stderr, "aed u=%d l=%d nw=%d iters=%d ns=%d\n", u, l, nw, S.iters, S.ns);
             const int ok = S.ok, ns = S.ns, nd = nw - ns;
             if (ok && nd > 0) {
@@ -181,7 +197,7 @@ int main(int argc, char** argv)
     if (!strcmp(argv[1], "window")) {
         AedScratch S;
         memset(&S, 0, sizeof S);
-        aed_window(H.data(), l, u, nw, 0); S = g_aed;
+        window_call(H.data(), l, u, nw); S = g_aed;
         int o[3] = {S.ns, S.ok, S.iters};
         fwrite(o, sizeof(int), 3, fo);
         for (int i = 0; i < AED_MAX; ++i) fwrite(S.T[i], sizeof(cplx), AED_MAX, fo);
@@ -192,7 +208,7 @@ int main(int argc, char** argv)
         std::vector<cplx> eig(n);
         int st[5];
         solve(H, n, nw, nb, eig, st);
-        if (getenv("AED_STAGES")) fprintf(stderr, "WORK %.4g\n", g_work);
+        if (getenv("AED_STAGES")) fprintf(stderr, "WORK %.4g  warp collectives (complex shuffles + ballots) %ld\n", g_work, wemu::g.collectives);
         if (getenv("AED_STAGES")) fprintf(stderr, "STAGES macro %d %d %d %d aed %d %d %d %d iters %ld\n", g_mstage[0], g_mstage[1], g_mstage[2], g_mstage[3], g_stage[0], g_stage[1], g_stage[2], g_stage[3], g_iters);
         fwrite(st, sizeof(int), 5, fo);
         fwrite(eig.data(), sizeof(cplx), n, fo);

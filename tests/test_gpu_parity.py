@@ -180,12 +180,14 @@ def test_eigenvalues_vs_reference_zgeev(name, n, kw):
         assert plain == 0                     # flagship: plain 1e-8 bar, no allowance needed
 
 
-VARIANTS = [('reduce_oc', 0), ('reduce_oc', 8), ('backnorm_wy', 0), ('backnorm_wy_modes', 32), ('hqr_stages', 2),
-            ('hqr_bulges', 5), ('hqr_aed', 8), ('hqr_aed', 4), ('hqr_aed', 6)]
+VARIANTS = [{'reduce_oc': 0}, {'reduce_oc': 8}, {'backnorm_wy': 0}, {'backnorm_wy_modes': 32}, {'hqr_stages': 2},
+            {'hqr_bulges': 5}, {'hqr_aed': 0}, {'hqr_aed': 8}, {'hqr_aed': 4}, {'hqr_aed': 6},
+            {'hqr_aed': 8, 'hqr_aed_reg': 0}, {'hqr_aed': 5, 'hqr_aed_reg': 0}, {'hqr_aed': 8, 'hqr_aed_stages': 5},
+            {'hqr_aed': 7, 'hqr_aed_stages': 10}]
 
 
-@pytest.mark.parametrize('var,val', VARIANTS, ids=['%s=%s' % v for v in VARIANTS])
-def test_kernel_variants_keep_parity(var, val):
+@pytest.mark.parametrize('settings', VARIANTS, ids=['+'.join('%s=%s' % kv for kv in v.items()) for v in VARIANTS])
+def test_kernel_variants_keep_parity(settings):
     """Every kernel-selection switch that is still compiled in (include/axisafe_b200.h, axs_set_tuning)
     meets the same bar as the default kernels on the flagship case: eigenvalues vs zgeev, mode shapes
     vs the default."""
@@ -194,14 +196,15 @@ def test_kernel_variants_keep_parity(var, val):
     k0, psi0, info0, _ = nat.eig_sweep(ops, omega)
     k0 = k0.cpu().numpy().reshape(len(pick), n2)
     psi0 = psi0.cpu().numpy().reshape(len(pick), n2, n2)
-    old = nat.set_tuning(var, val)
+    old = {var: nat.set_tuning(var, val) for var, val in settings.items()}
     try:
         k1, psi1, info1, _ = nat.eig_sweep(ops, omega)
         assert not info1.cpu().numpy().any()
         k1 = k1.cpu().numpy().reshape(len(pick), n2)
         psi1 = psi1.cpu().numpy().reshape(len(pick), n2, n2)
     finally:
-        nat.set_tuning(var, old)
+        for var, val in old.items():
+            nat.set_tuning(var, val)
     for j in range(len(pick)):
         ref = g['eig_untracked'][j]
         perm, _ = so.match_eigenvalues(ref, k1[j])

@@ -228,13 +228,17 @@ def _aed_host_exe():
         pytest.skip('nvcc not available')
     src = os.path.join(ROOT, 'tests', 'host', 'aed_host.cu')
     exe = os.path.join(ROOT, 'tests', 'host', 'aed_host')
-    hdr = os.path.join(ROOT, 'axisym-safe-python_b200', 'csrc', 'aed.cuh')
-    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    deps = [src, os.path.join(ROOT, 'tests', 'host', 'warp_emul.h'),
+            os.path.join(ROOT, 'axisym-safe-python_b200', 'csrc', 'aed.cuh'),
+            os.path.join(ROOT, 'axisym-safe-python_b200', 'csrc', 'common.cuh')]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
         subprocess.run([nvcc, '-x', 'cu', '-DAED_HOST', '-O2', '-Wno-deprecated-gpu-targets', '-o', exe, src], check=True)
     return exe
 
 
-def _aed_run(exe, mode, H, l, u, nw, nb=8):
+def _aed_run(exe, mode, H, l, u, nw, nb=8, reg=0):
+    """reg = 1: the register-resident window routine (aed_window_reg) on the emulated warp of
+    tests/host/warp_emul.h; reg = 0: the shared-memory routine (aed_window) as sequential code."""
     import struct
     import subprocess
     import tempfile
@@ -244,7 +248,7 @@ def _aed_run(exe, mode, H, l, u, nw, nb=8):
         with open(fi, 'wb') as f:
             f.write(struct.pack('5i', n, l, u, nw, nb))
             f.write(np.asarray(H, dtype=complex).tobytes(order='F'))
-        subprocess.run([exe, mode, fi, fo], check=True)
+        subprocess.run([exe, mode, fi, fo], check=True, env=dict(os.environ, AED_REG=str(int(reg))))
         raw = open(fo, 'rb').read()
     if mode == 'solve':
         return struct.unpack('5i', raw[:20]), np.frombuffer(raw[20:], dtype=complex)
@@ -264,7 +268,8 @@ def _safe_hessenberg(i, nf=2000):
     return np.triu(la.hessenberg(Sb), -1), np.linalg.eigvals(S)
 
 
-def test_aed_window_is_a_similarity():
+@pytest.mark.parametrize('reg', [0, 1], ids=['shared', 'registers'])
+def test_aed_window_is_a_similarity(reg):
     """One AED call (zlaqr2 semantics): Z unitary, Z^H W Z = T with T Hessenberg in its leading ns x ns
     part and triangular below, the spike vector reduced to one entry, every deflated eigenvalue
     meeting the spike criterion, spectrum of the window preserved."""
@@ -274,7 +279,6 @@ def test_aed_window_is_a_similarity():
     H, _ = _safe_hessenberg(700)
     n = H.shape[0]
     # a few QR-like iterations so that the trailing window carries converged eigenvalues
-    st, _ = _aed_run(exe, 'solve', H, 0, n - 1, 0)
     cases_ = []
     for nw in (8, 5, 3):
         for u in (n - 1, 60):
@@ -286,7 +290,7 @@ def test_aed_window_is_a_similarity():
     for Hm, l, u, nw in cases_:
         nw = min(nw, u - l + 1)
         kw = u - nw + 1
-        ns, ok, iters, T, Z, shift, spike_new = _aed_run(exe, 'window', Hm, l, u, nw)
+        ns, ok, iters, T, Z, shift, spike_new = _aed_run(exe, 'window', Hm, l, u, nw, reg=reg)
         assert ok == 1 and 0 <= ns <= nw
         T, Z = T[:nw, :nw], Z[:nw, :nw]
         W = Hm[kw:u + 1, kw:u + 1]
@@ -317,8 +321,45 @@ def test_aed_window_is_a_similarity():
     assert deflated_total > 0
 
 
+def test_aed_register_window_matches_shared_window():
+    """The register-resident routine (lane 4 i + p owns T(i, 2p..2p+1), Z likewise; rotations through
+    shuffles) against the shared-memory routine on 60 windows (sizes 2..8, SAFE Hessenberg blocks and
+    random nearly decoupled ones): same number of deflations and QR sweeps, same shifts; T and Z are both
+    valid Schur data of the same window (checked in test_aed_window_is_a_similarity), compared loosely
+    because Schur vectors of close eigenvalues are ill-conditioned."""
+    exe = _aed_host_exe()
+    rng = np.random.default_rng(1)
+    H, _ = _safe_hessenberg(700)
+    n = H.shape[0]
+    tests = [(H, 0, u, nw) for u in (n - 1, 100, 60, 20, 9) for nw in (8, 7, 6, 5, 4, 3, 2)]
+    for t in range(25):
+        m = int(rng.integers(9, 24))
+        R = np.triu(rng.standard_normal([m, m]) + 1j * rng.standard_normal([m, m]), -1)
+        if t % 2:
+            q = int(rng.integers(2, 7))
+            R[np.arange(m - q, m), np.arange(m - q - 1, m - 1)] *= 10.0 ** (-int(rng.integers(6, 16)))
+        tests.append((R, int(rng.integers(0, m - 8)), m - 1, int(rng.integers(2, 9))))
+    deflated = 0
+    for Hm, l, u, nw in tests:
+        nw = min(nw, u - l + 1)
+        a = _aed_run(exe, 'window', Hm, l, u, nw, reg=0)
+        b = _aed_run(exe, 'window', Hm, l, u, nw, reg=1)
+        assert a[:3] == b[:3], (a[:3], b[:3], l, u, nw)
+        ns = a[0]
+        deflated += nw - ns
+        scale = np.abs(Hm[u - nw + 1:u + 1, u - nw + 1:u + 1]).max()
+        if ns:
+            assert np.abs(a[5][:ns] - b[5][:ns]).max() <= 1e-13 * scale
+        assert np.abs(a[3][:nw, :nw] - b[3][:nw, :nw]).max() <= 1e-8 * scale
+        assert np.abs(a[4][:nw, :nw] - b[4][:nw, :nw]).max() <= 1e-8
+        if ns < nw:
+            assert abs(a[6] - b[6]) <= 1e-13 * scale
+    assert deflated > 20
+
+
+@pytest.mark.parametrize('reg', [0, 1], ids=['shared', 'registers'])
 @pytest.mark.parametrize('i', [3, 1400])
-def test_aed_solve_matches_zgeev_and_cuts_the_sweeps(i):
+def test_aed_solve_matches_zgeev_and_cuts_the_sweeps(i, reg):
     """The kernel's batch loop with the AED window in front of every batch (host model): same
     eigenvalues as LAPACK, no failures, less than 70 % of the macro steps of the plain cascade."""
     from oracle import safe_oracle as so
@@ -326,7 +367,7 @@ def test_aed_solve_matches_zgeev_and_cuts_the_sweeps(i):
     H, ref = _safe_hessenberg(i)
     n = H.shape[0]
     plain, ev0 = _aed_run(exe, 'solve', H, 0, n - 1, 0)
-    aed, ev8 = _aed_run(exe, 'solve', H, 0, n - 1, 8)
+    aed, ev8 = _aed_run(exe, 'solve', H, 0, n - 1, 8, reg=reg)
     assert plain[4] == 0 and aed[4] == 0
     assert so.match_eigenvalues(ref, ev0)[1] < 1e-9
     assert so.match_eigenvalues(ref, ev8)[1] < 1e-9
