@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, '_lib', 'libaxisafe_b200.so')
+# AXS_LIBRARY: another build of the same library (A/B builds of tests/run_ab_aed*.sh); default = the in-tree product build
+LIB_PATH = os.environ.get('AXS_LIBRARY') or os.path.join(_HERE, '_lib', 'libaxisafe_b200.so')
 _lib = None
 
 _c_int_p = ctypes.c_void_p

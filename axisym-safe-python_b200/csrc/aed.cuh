@@ -249,6 +249,133 @@ AED_FN void aed_window(const cplx* H, int l, int u, int nw, int lane)
 }
 
 // =========================================================================================
+// aed_window_flat: the shared-memory routine above as ONE loop around ONE rotation step.  A small
+// warp-uniform state machine (the same one as in aed_window_reg below) selects the next rotation of the
+// Schur sweeps (phase 0), of the spike test with its swaps (phase 1) and of the return to Hessenberg form
+// (phase 2); the step itself is aed_window's: generate, overwrite up to two entries, rows, columns + Z, with
+// three warp barriers.  Same arithmetic per entry as aed_window; the point is the code size - a single warp
+// has nobody to hide its instruction fetches behind, and the loop it spins in should fit the 6 KB L0
+// instruction cache of its SM sub-partition.
+// Warp-style macros (identical on the host, where tests/host/warp_emul.h runs the 32 lanes as fibers):
+// (the window has at most 8 x 8 entries: a lane owns at most ONE index of a range of <= 32, which spares the
+// compiler-unrolled strided loops of AED_LANES)
+#define AEDW_ONE(v, lo, hi) for (int v = (lo) + lane, once_ = 1; once_ && v < (hi); once_ = 0)
+#ifndef AEDW_SYNC
+#define AEDW_SYNC() __syncwarp()
+#define AEDW_BALLOT(p) __ballot_sync(0xffffffffu, (p))
+#define AEDW_CLZ(m) __clz((int)(m))
+#endif
+
+AED_FN void aed_window_flat(const cplx* H, int l, int u, int nw, int lane)
+{
+    AedScratch* const S = &g_aed;
+    const int kw = u - nw + 1;
+#pragma unroll 1
+    for (int idx = lane; idx < nw * nw; idx += 32) {
+        const int j = idx / nw, i = idx - j * nw;
+        S->T[i][j] = (i <= j + 1) ? H[hcol_off(kw + j) + kw + i] : mk(0, 0);
+        S->Z[i][j] = mk(i == j ? 1.0 : 0.0, 0.0);
+    }
+    const cplx spike = (kw > l) ? H[hcol_off(kw - 1) + kw] : mk(0, 0);
+    const double sp1 = cabs1(spike);
+    AEDW_SYNC();
+    cplx sig = mk(0, 0);
+    int phase = 0, k = -1;                              // k < 0: the phase has to choose its next group of rotations
+    int iu = nw - 1, il = 0, its = 0, total = 0, ok = 1;     // phase 0
+    int ns = nw, ilst = 0;                              // phase 1
+    int jv = 0;                                         // phase 2: spike entry being annihilated
+
+    for (;;) {
+        // ---- control (warp-uniform; every lane reads the same shared entries) -------------------------
+        int rk, rjlo, rihi, e1i = -1, e1j = 0, e2i = -1, e2j = 0, sva = -1;
+        bool e1_is_r = false;
+        cplx x, y, v1 = mk(0, 0), v2 = mk(0, 0);
+        if (phase == 0) {
+            if (k < 0) {
+                if (iu < 1) { phase = 1; continue; }
+                const bool neg = (lane >= 1 && lane <= iu) ? aed_negligible(S, nw, lane) : false;
+                const unsigned m = AEDW_BALLOT(neg);          // (also: every lane has read the subdiagonal)
+                il = m ? 31 - AEDW_CLZ(m) : 0;
+                if (il > 0 && lane == 0) S->T[il][il - 1] = mk(0, 0);
+                if (il == iu) { --iu; its = 0; AEDW_SYNC(); continue; }
+                ++its; ++total;
+                if (its > 30) { ok = 0; break; }
+                sig = aed_shift2(S->T[iu - 1][iu - 1], S->T[iu - 1][iu], S->T[iu][iu - 1], S->T[iu][iu]);
+                if (its == 10 || its == 20) sig = cadd(S->T[iu][iu], mk(0.75 * cabs1(S->T[iu][iu - 1]), 0));
+                k = il;
+            }
+            const int gc = (k == il) ? il : k - 1;
+            x = S->T[k][gc]; y = S->T[k + 1][gc];
+            if (k == il) x = csub(x, sig);
+            else { e1i = k; e1j = k - 1; e1_is_r = true; e2i = k + 1; e2j = k - 1; }
+            rk = k; rjlo = k; rihi = (k + 2 < iu) ? k + 2 : iu;
+            ++k;
+            if (k >= iu) k = -1;
+        } else if (phase == 1) {
+            if (k < 0) {
+                if (ilst >= ns) {
+                    AEDW_ONE(j, 0, ns) S->shift[j] = S->T[j][j];      // undeflated window eigenvalues = next shifts
+                    if (ns == nw) break;                       // nothing deflated: the caller leaves H alone
+                    AEDW_ONE(j, 0, nw) S->sv[j] = (j < ns) ? cmulc(spike, S->Z[0][j]) : mk(0, 0);
+                    AEDW_SYNC();
+                    phase = 2; jv = ns - 1; k = -1;
+                    continue;
+                }
+                double foo = cabs1(S->T[ns - 1][ns - 1]);
+                if (foo == 0.0) foo = sp1;
+                if (sp1 * cabs1(S->Z[0][ns - 1]) <= fmax(AED_SMALL, AED_EPS * foo)) { --ns; continue; }
+                k = ns - 2;                                    // move T(ns-1, ns-1) up to position ilst by adjacent swaps
+                if (k < ilst) { ++ilst; k = -1; continue; }
+            }
+            {
+                const cplx t11 = S->T[k][k], t22 = S->T[k + 1][k + 1];
+                x = S->T[k][k + 1]; y = csub(t22, t11);
+                e1i = k; e1j = k; v1 = t22; e2i = k + 1; e2j = k + 1; v2 = t11;
+            }
+            rk = k; rjlo = k + 2; rihi = k - 1;                // rows: columns >= k+2, columns: rows < k
+            --k;
+            if (k < ilst) { ++ilst; k = -1; }
+        } else {
+            if (jv < 1) break;
+            if (k < 0) {                                       // annihilate spike entry jv against entry jv-1
+                x = S->sv[jv - 1]; y = S->sv[jv];
+                sva = jv - 1;
+                rk = jv - 1; rjlo = jv - 1; rihi = (jv + 1 < ns - 1) ? jv + 1 : ns - 1;
+                k = jv;
+            } else {                                           // chase the bulge T(k+1, k-1) out of the bottom
+                x = S->T[k][k - 1]; y = S->T[k + 1][k - 1];
+                e1i = k; e1j = k - 1; e1_is_r = true; e2i = k + 1; e2j = k - 1;
+                rk = k; rjlo = k; rihi = (k + 2 < ns - 1) ? k + 2 : ns - 1;
+                ++k;
+            }
+            if (k + 1 > ns - 1) { --jv; k = -1; }
+        }
+        // ---- the rotation step ------------------------------------------------------------------------
+        AEDW_SYNC();                                      // x, y and the control inputs read by every lane before they change
+        double c; cplx s, r;
+        aed_rot(x, y, c, s, r);
+        if (lane == 0) {
+            if (e1_is_r) v1 = r;
+            if (e1i >= 0) S->T[e1i][e1j] = v1;
+            if (e2i >= 0) S->T[e2i][e2j] = v2;
+            if (sva >= 0) { S->sv[sva] = r; S->sv[sva + 1] = mk(0, 0); }
+        }
+        AEDW_ONE(j, rjlo, nw) aed_rows(c, s, S->T[rk][j], S->T[rk + 1][j]);
+        AEDW_SYNC();
+        AEDW_ONE(ii, 0, 2 * nw) {
+            if (ii < nw) { if (ii <= rihi) aed_cols(c, s, S->T[ii][rk], S->T[ii][rk + 1]); }
+            else aed_cols(c, s, S->Z[ii - nw][rk], S->Z[ii - nw][rk + 1]);
+        }
+        AEDW_SYNC();
+    }
+    if (lane == 0) {
+        S->ok = ok; S->iters = total; S->ns = ok ? ns : nw;
+        S->spike_new = (ok && ns > 0 && ns < nw) ? S->sv[0] : mk(0, 0);
+    }
+    AEDW_SYNC();
+}
+
+// =========================================================================================
 // Register-resident window (aed_window_reg): the same four steps, but T and Z never touch shared
 // memory while the warp works on them.  Lane L = 4 i + p owns the entries (i, 2p) and (i, 2p + 1) of T
 // and of Z in registers:
@@ -326,6 +453,12 @@ AED_INL void aedr_apply(cplx& t0, cplx& t1, cplx& z0, cplx& z1, int lane, int k,
     }
 }
 
+// The routine is ONE loop around ONE rotation step (row exchange, rotation, two entry updates, similarity
+// update): a small warp-uniform state machine selects the next rotation of the Schur sweeps (phase 0), of the
+// spike test with its swaps (phase 1) and of the return to Hessenberg form (phase 2).  A single warp has
+// nobody to hide its instruction fetches behind, so the code it loops over has to stay small (the four
+// inlined copies of the step of a straightforward transcription ran 8 x slower on B200 than this form's
+// predecessor in shared memory - DESIGN.md 4.5).
 AED_FN void aed_window_reg(const cplx* H, int l, int u, int nw, int lane)
 {
     AedScratch* const S = &g_aed;
@@ -335,124 +468,136 @@ AED_FN void aed_window_reg(const cplx* H, int l, int u, int nw, int lane)
     cplx t1 = (i < nw && j1 < nw && i <= j1 + 1) ? H[hcol_off(kw + j1) + kw + i] : mk(0, 0);
     cplx z0 = mk(i == j0 ? 1.0 : 0.0, 0.0), z1 = mk(i == j1 ? 1.0 : 0.0, 0.0);
     const cplx spike = (kw > l) ? H[hcol_off(kw - 1) + kw] : mk(0, 0);
-
-    // ---- 1. Schur form of the window ------------------------------------------------------------
-    int iu = nw - 1, its = 0, total = 0, ok = 1;
-    while (iu >= 1) {
-        // lane k (1 <= k <= iu) tests T(k, k-1): the three diagonals are gathered into the lanes
-        int il = 0;
-        {
-            const int k = (lane < nw) ? lane : nw - 1, km = (k > 0) ? k - 1 : 0;
-            const int s_d = 4 * k + (k >> 1), s_sub = 4 * k + (km >> 1), s_sup = 4 * km + (k >> 1);
-            const cplx d_a = AEDR_SHFL(t0, s_d), d_b = AEDR_SHFL(t1, s_d);
-            const cplx b_a = AEDR_SHFL(t0, s_sub), b_b = AEDR_SHFL(t1, s_sub);
-            const cplx p_a = AEDR_SHFL(t0, s_sup), p_b = AEDR_SHFL(t1, s_sup);
-            const cplx hkk = (k & 1) ? d_b : d_a;             // T(k, k)
-            const cplx hsub = (km & 1) ? b_b : b_a;           // T(k, k-1)
-            const cplx hsup = (k & 1) ? p_b : p_a;            // T(k-1, k)
-            const cplx hk1 = AEDR_SHFL(hkk, (lane + 31) & 31);      // T(k-1, k-1)
-            const cplx hsubm = AEDR_SHFL(hsub, (lane + 31) & 31);   // T(k-1, k-2)
-            const cplx hsubp = AEDR_SHFL(hsub, (lane + 1) & 31);    // T(k+1, k)
-            bool neg = false;
-            if (lane >= 1 && lane <= iu) {
-                const double sub = cabs1(hsub);
-                if (sub <= AED_SMALL) neg = true;
-                else {
-                    double tst = cabs1(hk1) + cabs1(hkk);
-                    if (tst == 0.0) {
-                        if (k - 2 >= 0) tst += cabs1(hsubm);
-                        if (k + 1 <= nw - 1) tst += cabs1(hsubp);
-                    }
-                    if (sub <= AED_EPS * tst) {
-                        const double up = cabs1(hsup);
-                        const double ab = fmax(sub, up), ba = fmin(sub, up);
-                        const double dd = cabs1(csub(hk1, hkk));
-                        const double aa = fmax(cabs1(hkk), dd), bb = fmin(cabs1(hkk), dd);
-                        const double sm = aa + ab;
-                        if (ba * (ab / sm) <= fmax(AED_SMALL, AED_EPS * (bb * (aa / sm)))) neg = true;
-                    }
-                }
-            }
-            const unsigned m = AEDR_BALLOT(neg);
-            il = m ? 31 - AEDR_CLZ(m) : 0;
-        }
-        if (il > 0) AEDR_SET(il, il - 1, mk(0, 0));
-        if (il == iu) { --iu; its = 0; continue; }
-        ++its; ++total;
-        if (its > 30) { ok = 0; break; }
-        cplx sig;
-        {
-            const cplx a11 = AEDR_GET(iu - 1, iu - 1), a12 = AEDR_GET(iu - 1, iu);
-            const cplx a21 = AEDR_GET(iu, iu - 1), a22 = AEDR_GET(iu, iu);
-            sig = aed_shift2(a11, a12, a21, a22);
-            if (its == 10 || its == 20) sig = cadd(a22, mk(0.75 * cabs1(a21), 0));
-        }
-        for (int k = il; k < iu; ++k) {
-            cplx x, y;
-            if (k == il) { x = csub(AEDR_GET(il, il), sig); y = AEDR_GET(il + 1, il); }
-            else { x = AEDR_GET(k, k - 1); y = AEDR_GET(k + 1, k - 1); }
-            AEDR_ROWX(k, q0, q1);
-            double c; cplx s, r;
-            aed_rot(x, y, c, s, r);
-            if (k > il) { AEDR_SET(k, k - 1, r); AEDR_SET(k + 1, k - 1, mk(0, 0)); }
-            aedr_apply(t0, t1, z0, z1, lane, k, k, (k + 2 < iu) ? k + 2 : iu, c, s, q0, q1);
-        }
-    }
-    if (!ok) {
-        if (lane == 0) { S->ok = 0; S->iters = total; S->ns = nw; }
-        AED_SYNC();
-        return;
-    }
-
-    // ---- 2. spike test from the bottom, undeflatable eigenvalues to the top -----------------------
-    int ns = nw, ilst = 0;
     const double sp1 = cabs1(spike);
-    while (ilst < ns) {
-        double foo = cabs1(AEDR_GET(ns - 1, ns - 1));
-        if (foo == 0.0) foo = sp1;
-        if (sp1 * cabs1(AEDR_GETZ(0, ns - 1)) <= fmax(AED_SMALL, AED_EPS * foo)) { --ns; continue; }
-        for (int k = ns - 2; k >= ilst; --k) {
-            const cplx t11 = AEDR_GET(k, k), t22 = AEDR_GET(k + 1, k + 1), t12 = AEDR_GET(k, k + 1);
-            AEDR_ROWX(k, q0, q1);
-            double c; cplx s, r;
-            aed_rot(t12, csub(t22, t11), c, s, r);
-            aedr_apply(t0, t1, z0, z1, lane, k, k + 2, k - 1, c, s, q0, q1);     // rows: columns >= k+2, columns: rows < k
-            AEDR_SET(k, k, t22); AEDR_SET(k + 1, k + 1, t11);
-        }
-        ++ilst;
-    }
-    if (i == j0 && j0 < ns) S->shift[j0] = t0;
-    if (i == j1 && j1 < ns) S->shift[j1] = t1;
-    if (lane == 0) { S->ok = 1; S->iters = total; S->ns = ns; }
+    cplx sv = mk(0, 0), sig = mk(0, 0);                 // spike vector entry of lane j (phase 2); shift of the sweep
+    int phase = 0, k = -1;                              // k < 0: the phase has to choose its next group of rotations
+    int iu = nw - 1, il = 0, its = 0, total = 0, ok = 1;     // phase 0
+    int ns = nw, ilst = 0;                              // phase 1
+    int jv = 0;                                         // phase 2: spike entry being annihilated
 
-    // ---- 3. spike vector (lane j holds entry j) and leading ns x ns part back to Hessenberg form ----
-    cplx sv = mk(0, 0);
-    if (ns < nw) {
-        {
-            const int j = lane & 7;
-            const cplx za = AEDR_SHFL(z0, j >> 1), zb = AEDR_SHFL(z1, j >> 1);      // Z(0, j)
-            if (lane < 8 && lane < ns) sv = cmulc(spike, (j & 1) ? zb : za);
-        }
-        for (int j = ns - 1; j >= 1; --j) {
+    for (;;) {
+        // ---- control (warp-uniform): the next rotation = plane rk, rows from column rjlo, columns up to row rihi,
+        //      generated from (x, y); up to two entries (e1, e2) are overwritten before the similarity update
+        int rk, rjlo, rihi, e1i = -1, e1j = 0, e2i = -1, e2j = 0, sva = -1;
+        bool e1_is_r = false;
+        cplx x, y, v1 = mk(0, 0), v2 = mk(0, 0);
+        if (phase == 0) {
+            if (k < 0) {
+                if (iu < 1) { phase = 1; continue; }
+                // lane q (1 <= q <= iu) tests T(q, q-1): the three diagonals are gathered into the lanes
+                {
+                    const int q = (lane < nw) ? lane : nw - 1, qm = (q > 0) ? q - 1 : 0;
+                    const int s_d = 4 * q + (q >> 1), s_sub = 4 * q + (qm >> 1), s_sup = 4 * qm + (q >> 1);
+                    const cplx d_a = AEDR_SHFL(t0, s_d), d_b = AEDR_SHFL(t1, s_d);
+                    const cplx b_a = AEDR_SHFL(t0, s_sub), b_b = AEDR_SHFL(t1, s_sub);
+                    const cplx p_a = AEDR_SHFL(t0, s_sup), p_b = AEDR_SHFL(t1, s_sup);
+                    const cplx hkk = (q & 1) ? d_b : d_a;             // T(q, q)
+                    const cplx hsub = (qm & 1) ? b_b : b_a;           // T(q, q-1)
+                    const cplx hsup = (q & 1) ? p_b : p_a;            // T(q-1, q)
+                    const cplx hk1 = AEDR_SHFL(hkk, (lane + 31) & 31);      // T(q-1, q-1)
+                    const cplx hsubm = AEDR_SHFL(hsub, (lane + 31) & 31);   // T(q-1, q-2)
+                    const cplx hsubp = AEDR_SHFL(hsub, (lane + 1) & 31);    // T(q+1, q)
+                    bool neg = false;
+                    if (lane >= 1 && lane <= iu) {
+                        const double sub = cabs1(hsub);
+                        if (sub <= AED_SMALL) neg = true;
+                        else {
+                            double tst = cabs1(hk1) + cabs1(hkk);
+                            if (tst == 0.0) {
+                                if (q - 2 >= 0) tst += cabs1(hsubm);
+                                if (q + 1 <= nw - 1) tst += cabs1(hsubp);
+                            }
+                            if (sub <= AED_EPS * tst) {
+                                const double up = cabs1(hsup);
+                                const double ab = fmax(sub, up), ba = fmin(sub, up);
+                                const double dd = cabs1(csub(hk1, hkk));
+                                const double aa = fmax(cabs1(hkk), dd), bb = fmin(cabs1(hkk), dd);
+                                const double sm = aa + ab;
+                                if (ba * (ab / sm) <= fmax(AED_SMALL, AED_EPS * (bb * (aa / sm)))) neg = true;
+                            }
+                        }
+                    }
+                    const unsigned m = AEDR_BALLOT(neg);
+                    il = m ? 31 - AEDR_CLZ(m) : 0;
+                }
+                if (il > 0) AEDR_SET(il, il - 1, mk(0, 0));
+                if (il == iu) { --iu; its = 0; continue; }
+                ++its; ++total;
+                if (its > 30) { ok = 0; break; }
+                {
+                    const cplx a11 = AEDR_GET(iu - 1, iu - 1), a12 = AEDR_GET(iu - 1, iu);
+                    const cplx a21 = AEDR_GET(iu, iu - 1), a22 = AEDR_GET(iu, iu);
+                    sig = aed_shift2(a11, a12, a21, a22);
+                    if (its == 10 || its == 20) sig = cadd(a22, mk(0.75 * cabs1(a21), 0));
+                }
+                k = il;
+            }
+            // rotation k of the sweep [il, iu]: the first one introduces the bulge, the others chase it
+            const int gc = (k == il) ? il : k - 1;
+            x = AEDR_GET(k, gc); y = AEDR_GET(k + 1, gc);
+            if (k == il) x = csub(x, sig);
+            else { e1i = k; e1j = k - 1; e1_is_r = true; e2i = k + 1; e2j = k - 1; }
+            rk = k; rjlo = k; rihi = (k + 2 < iu) ? k + 2 : iu;
+            ++k;
+            if (k >= iu) k = -1;
+        } else if (phase == 1) {
+            if (k < 0) {
+                if (ilst >= ns) {
+                    // the undeflated window eigenvalues are the next shifts
+                    if (i == j0 && j0 < ns) S->shift[j0] = t0;
+                    if (i == j1 && j1 < ns) S->shift[j1] = t1;
+                    if (ns == nw) break;                       // nothing deflated: the caller leaves H alone
+                    {
+                        const int j = lane & 7;
+                        const cplx za = AEDR_SHFL(z0, j >> 1), zb = AEDR_SHFL(z1, j >> 1);      // Z(0, j)
+                        if (lane < 8 && lane < ns) sv = cmulc(spike, (j & 1) ? zb : za);
+                    }
+                    phase = 2; jv = ns - 1; k = -1;
+                    continue;
+                }
+                double foo = cabs1(AEDR_GET(ns - 1, ns - 1));
+                if (foo == 0.0) foo = sp1;
+                if (sp1 * cabs1(AEDR_GETZ(0, ns - 1)) <= fmax(AED_SMALL, AED_EPS * foo)) { --ns; continue; }
+                k = ns - 2;                                    // move T(ns-1, ns-1) up to position ilst by adjacent swaps
+                if (k < ilst) { ++ilst; k = -1; continue; }
+            }
             {
-                const cplx x = AEDR_SHFL(sv, j - 1), y = AEDR_SHFL(sv, j);
-                AEDR_ROWX(j - 1, q0, q1);
-                double c; cplx s, r;
-                aed_rot(x, y, c, s, r);
-                if (lane == j - 1) sv = r;
-                if (lane == j) sv = mk(0, 0);
-                aedr_apply(t0, t1, z0, z1, lane, j - 1, j - 1, (j + 1 < ns - 1) ? j + 1 : ns - 1, c, s, q0, q1);
+                const cplx t11 = AEDR_GET(k, k), t22 = AEDR_GET(k + 1, k + 1);
+                x = AEDR_GET(k, k + 1); y = csub(t22, t11);
+                e1i = k; e1j = k; v1 = t22; e2i = k + 1; e2j = k + 1; v2 = t11;
             }
-            for (int kk = j; kk + 1 <= ns - 1; ++kk) {          // chase the bulge T(kk+1, kk-1) out of the bottom
-                const cplx x = AEDR_GET(kk, kk - 1), y = AEDR_GET(kk + 1, kk - 1);
-                AEDR_ROWX(kk, q0, q1);
-                double c; cplx s, r;
-                aed_rot(x, y, c, s, r);
-                AEDR_SET(kk, kk - 1, r); AEDR_SET(kk + 1, kk - 1, mk(0, 0));
-                aedr_apply(t0, t1, z0, z1, lane, kk, kk, (kk + 2 < ns - 1) ? kk + 2 : ns - 1, c, s, q0, q1);
+            rk = k; rjlo = k + 2; rihi = k - 1;                // rows: columns >= k+2, columns: rows < k
+            --k;
+            if (k < ilst) { ++ilst; k = -1; }
+        } else {
+            if (jv < 1) break;
+            if (k < 0) {                                       // annihilate spike entry jv against entry jv-1
+                x = AEDR_SHFL(sv, jv - 1); y = AEDR_SHFL(sv, jv);
+                sva = jv - 1;
+                rk = jv - 1; rjlo = jv - 1; rihi = (jv + 1 < ns - 1) ? jv + 1 : ns - 1;
+                k = jv;
+            } else {                                           // chase the bulge T(k+1, k-1) out of the bottom
+                x = AEDR_GET(k, k - 1); y = AEDR_GET(k + 1, k - 1);
+                e1i = k; e1j = k - 1; e1_is_r = true; e2i = k + 1; e2j = k - 1;
+                rk = k; rjlo = k; rihi = (k + 2 < ns - 1) ? k + 2 : ns - 1;
+                ++k;
             }
+            if (k + 1 > ns - 1) { --jv; k = -1; }
         }
-        if (lane == 0) S->spike_new = (ns > 0) ? sv : mk(0, 0);
+        // ---- the rotation step ------------------------------------------------------------------------
+        AEDR_ROWX(rk, q0, q1);
+        double c; cplx s, r;
+        aed_rot(x, y, c, s, r);
+        if (e1_is_r) v1 = r;
+        AEDR_SET(e1i, e1j, v1);
+        AEDR_SET(e2i, e2j, v2);
+        if (lane == sva) sv = r;
+        if (lane == sva + 1 && sva >= 0) sv = mk(0, 0);
+        aedr_apply(t0, t1, z0, z1, lane, rk, rjlo, rihi, c, s, q0, q1);
+    }
+    if (lane == 0) {
+        S->ok = ok; S->iters = total; S->ns = ok ? ns : nw;
+        S->spike_new = (ok && ns > 0 && ns < nw) ? sv : mk(0, 0);
     }
     S->T[i][j0] = t0; S->T[i][j1] = t1;
     S->Z[i][j0] = z0; S->Z[i][j1] = z1;

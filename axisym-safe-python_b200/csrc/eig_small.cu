@@ -20,6 +20,13 @@
 //              store in the reference psi_hat layout.
 #include "common.cuh"
 #include "aed.cuh"
+// AXS_AED_BUILD: which early-deflation window routine the QR kernels carry: 0 = shared memory (default, the
+// faster one on B200), 1 = registers + shuffles, 2 = both behind the tuning switch hqr_aed_reg.  1 and 2 are
+// A/B builds (tests/run_ab_aed2.sh): a kernel that carries both routines runs EITHER of them 1.7 - 3.6 x
+// slower than a kernel that carries one (measured), so the product build has exactly one.
+#ifndef AXS_AED_BUILD
+#define AXS_AED_BUILD 0
+#endif
 #include <stdlib.h>
 #include <stdio.h>
 
@@ -361,7 +368,8 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
 #ifdef AED_PROFILE
     if constexpr (AED) if (tid < 8) g_aed.prof[tid] = 0;
 #endif
-    const bool aed_reg = (aed_nw & 0x100) != 0;           // register-resident window routine (csrc/aed.cuh)
+    const bool aed_reg = (aed_nw & 0x100) != 0;           // register-resident window routine (AXS_AED_BUILD == 2 only)
+    (void)aed_reg;
     aed_nw &= 0xff;
     int its = 0, failed = 0;
     int n_macro = 0, n_batch = 0, n_aed = 0, n_aed_defl = 0;
@@ -420,8 +428,16 @@ k_hqr_mb(int n, int bmax, int first_stage, int m_stop, int aed_nw, const cplx* _
             const int kw = u - nw + 1;
             AED_CLK(0)
             if (tid < 32) {
+#if AXS_AED_BUILD == 1
+                aed_window_reg(H, l, u, nw, tid);         // register-resident routine only
+#elif AXS_AED_BUILD == 3
+                aed_window_flat(H, l, u, nw, tid);        // shared-memory routine as one loop around one rotation step
+#elif AXS_AED_BUILD == 0
+                aed_window(H, l, u, nw, tid);             // shared-memory routine only (product build)
+#else
                 if (aed_reg) aed_window_reg(H, l, u, nw, tid);
                 else aed_window(H, l, u, nw, tid);
+#endif
             }
             __syncthreads();
             AED_CLK(1)

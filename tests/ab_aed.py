@@ -1,13 +1,14 @@
 """A/B of the aggressive-early-deflation settings of the QR cascade on the flagship matrices (GPU).
 
-    python tests/ab_aed.py [nf] > gpurun_out/ab_aed.log
+    python tests/ab_aed.py [nf] [aed:reg:stages ...] > gpurun_out/ab_aed.log
+    AXS_LIBRARY=<path of another build of the library> python tests/ab_aed.py ...
 
 One process, one reduction of nf cfg1 matrices, then for every setting (hqr_aed window, register /
 shared-memory window routine, per-stage mask): best-of-3 time of axs_hqr, the axs_hqr_stats counters
 (macro steps, window calls, kilo-cycles per stage) and the eigenvalue error of 5 frequencies against
 scipy.linalg.eig (bar 1e-8).  The last line is JSON: the fastest setting that met the bar, for the caller.
 """
-import contextlib, io, json, sys
+import contextlib, io, json, os, sys
 import numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'axisym-safe-python_b200'); sys.path.insert(0, 'tests')
 import torch
@@ -30,8 +31,11 @@ nat.check(L.axs_reduce(N, ops.hb, P(ops.K0s), P(ops.Cb), P(ops.Mb), P(ops.K1c), 
 G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), 0); op = so.operators(G, 0)
 ref = {i: so.eig_normalised(op, 2 * np.pi * c['f'][i])[0] for i in (0, nf // 4, nf // 2, (3 * nf) // 4, nf - 1)}
 
-SETTINGS = [(0, 1, 15), (8, 0, 15), (8, 1, 15), (8, 1, 7), (8, 1, 3), (8, 1, 1), (8, 1, 14), (8, 1, 9), (8, 1, 11), (8, 1, 13),
-            (7, 1, 15), (6, 1, 15), (6, 1, 7), (4, 1, 15)]
+SETTINGS = [(0, 0, 15), (8, 0, 15), (7, 0, 15), (6, 0, 15), (5, 0, 15), (4, 0, 15),
+            (6, 0, 13), (6, 0, 9), (6, 0, 5), (6, 0, 1), (6, 0, 7), (6, 0, 11), (6, 0, 3),
+            (8, 0, 13), (8, 0, 9), (8, 0, 5), (8, 0, 1), (7, 0, 13), (5, 0, 13), (5, 0, 9)]
+if len(sys.argv) > 2:
+    SETTINGS = [tuple(int(x) for x in a.split(':')) for a in sys.argv[2:]]
 rows = []
 for aed, reg, mask in SETTINGS:
     nat.set_tuning('hqr_aed', aed); nat.set_tuning('hqr_aed_reg', reg); nat.set_tuning('hqr_aed_stages', mask)

@@ -16,6 +16,9 @@ static inline cplx wemu_shfl_c(int lane, cplx v, int src, int tag) { wemu::shfl2
 #define AEDR_SHFL(v, src) wemu_shfl_c(lane, (v), (src), __LINE__)
 #define AEDR_BALLOT(p) wemu::ballot(lane, (p), __LINE__)
 #define AEDR_CLZ(m) __builtin_clz((unsigned)(m))
+#define AEDW_SYNC() wemu::syncwarp(lane, __LINE__)
+#define AEDW_BALLOT(p) wemu::ballot(lane, (p), __LINE__)
+#define AEDW_CLZ(m) __builtin_clz((unsigned)(m))
 #include "../../axisym-safe-python_b200/csrc/aed.cuh"
 #include <cstdio>
 #include <cstdlib>
@@ -28,11 +31,13 @@ static int g_stage[4] = {0, 0, 0, 0}, g_mstage[4] = {0, 0, 0, 0};
 static double g_work = 0.0;   // sum over batches of macro steps x active size (cost model of the windowed large-path QR)
 #define MB_MAX 8
 typedef std::vector<cplx> Packed;
-static bool use_reg() { static int v = getenv("AED_REG") ? atoi(getenv("AED_REG")) : 0; return v != 0; }
-// one window call: the shared-memory routine as sequential code, or the register routine on the emulated warp
+static int use_reg() { static int v = getenv("AED_REG") ? atoi(getenv("AED_REG")) : 0; return v; }
+// one window call: AED_REG=0 the shared-memory routine as sequential code; 1 the register routine and
+// 2 the one-loop shared-memory routine (aed_window_flat), both on the emulated warp
 static void window_call(const cplx* H, int l, int u, int nw)
 {
-    if (use_reg()) wemu::run([=](int lane) { aed_window_reg(H, l, u, nw, lane); });
+    if (use_reg() == 1) wemu::run([=](int lane) { aed_window_reg(H, l, u, nw, lane); });
+    else if (use_reg() == 2) wemu::run([=](int lane) { aed_window_flat(H, l, u, nw, lane); });
     else aed_window(H, l, u, nw, 0);
 }
 static inline cplx& HP(Packed& H, int i, int j) { return H[hcol_off(j) + i]; }

@@ -7,6 +7,10 @@
 // run(); a lane that waits in a rendezvous yields to the scheduler.  The emulator checks what the
 // hardware only assumes: every lane must reach the SAME collective (call sites are tagged with their
 // line number) - divergent control flow around a collective aborts with a message instead of hanging.
+// Between two collectives the lanes run one after the other, so a missing barrier (one lane writing what
+// another still has to read) shows as a result that depends on the ORDER of the lanes: WEMU_SEED=<n> in the
+// environment makes the scheduler visit the lanes in a new pseudo-random order every round; race-free code
+// gives bit-identical results for every seed (tests/test_host.py).
 #pragma once
 #include <ucontext.h>
 #include <cstdio>
@@ -102,11 +106,24 @@ static void run(std::function<void(int)> body)
         g.ctx[lane].uc_link = &g.main_ctx;
         makecontext(&g.ctx[lane], (void (*)())trampoline, 1, lane);
     }
+    static const char* seed_env = getenv("WEMU_SEED");
+    static unsigned long long rng = seed_env ? 0x9E3779B97F4A7C15ull * (unsigned long long)(atoll(seed_env) + 1) : 0;
+    int order[W];
+    for (int q = 0; q < W; ++q) order[q] = q;
     for (;;) {
         bool any = false;
         const long before = g.progress;
-        for (int lane = 0; lane < W; ++lane)
+        if (seed_env) {                                   // Fisher-Yates with a 64-bit LCG
+            for (int q = W - 1; q > 0; --q) {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                const int t = (int)((rng >> 33) % (unsigned)(q + 1));
+                const int tmp = order[q]; order[q] = order[t]; order[t] = tmp;
+            }
+        }
+        for (int q = 0; q < W; ++q) {
+            const int lane = order[q];
             if (!g.done[lane]) { any = true; swapcontext(&g.main_ctx, &g.ctx[lane]); }
+        }
         if (!any) break;
         if (g.progress == before) {
             // a whole round without a completed rendezvous: some lanes returned while others wait

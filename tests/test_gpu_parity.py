@@ -182,8 +182,7 @@ def test_eigenvalues_vs_reference_zgeev(name, n, kw):
 
 VARIANTS = [{'reduce_oc': 0}, {'reduce_oc': 8}, {'backnorm_wy': 0}, {'backnorm_wy_modes': 32}, {'hqr_stages': 2},
             {'hqr_bulges': 5}, {'hqr_aed': 0}, {'hqr_aed': 8}, {'hqr_aed': 4}, {'hqr_aed': 6},
-            {'hqr_aed': 8, 'hqr_aed_reg': 0}, {'hqr_aed': 5, 'hqr_aed_reg': 0}, {'hqr_aed': 8, 'hqr_aed_stages': 5},
-            {'hqr_aed': 7, 'hqr_aed_stages': 10}]
+            {'hqr_aed': 5}, {'hqr_aed': 8, 'hqr_aed_stages': 5}, {'hqr_aed': 7, 'hqr_aed_stages': 10}]
 
 
 @pytest.mark.parametrize('settings', VARIANTS, ids=['+'.join('%s=%s' % kv for kv in v.items()) for v in VARIANTS])
