@@ -1,6 +1,7 @@
 #!/bin/bash
-# second A/B session: the three builds of the early-deflation routine (registers only = product build,
-# shared memory only, both behind the runtime switch)
+# A/B session 2 (as run in round 2, when the register routine was the default build): three builds of the
+# early-deflation routine - registers only, shared memory only (aed0), both behind the runtime switch (aed2).
+# Today: tests/build_ab_aed.sh 1 2 builds the variants, the product library is the shared-memory build.
 set -u
 mkdir -p gpurun_out
 AB=axisym-safe-python_b200/axisafe_b200/_lib/ab

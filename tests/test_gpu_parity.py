@@ -230,12 +230,14 @@ def test_aed_cuts_the_qr_sweeps():
     res = {}
     for aed in (0, 8):
         old = nat.set_tuning('hqr_aed', aed)
+        old_mask = nat.set_tuning('hqr_aed_stages', 15)
         try:
             k, _, info, work = nat.eig_sweep(ops, omega, want_modes=False, chunks=1)
             assert not info.cpu().numpy().any()
             res[aed] = (k.cpu().numpy().reshape(64, 2 * N), nat.hqr_stats(N, 64, work))
         finally:
             nat.set_tuning('hqr_aed', old)
+            nat.set_tuning('hqr_aed_stages', old_mask)
     (k0, st0), (k8, st8) = res[0], res[8]
     assert st0[:, 2].sum() == 0 and st0[:, 3].sum() == 0
     assert (st8[:, 3] > 0.8 * 2 * N).all()

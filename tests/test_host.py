@@ -230,15 +230,17 @@ def _aed_host_exe():
     exe = os.path.join(ROOT, 'tests', 'host', 'aed_host')
     deps = [src, os.path.join(ROOT, 'tests', 'host', 'warp_emul.h'),
             os.path.join(ROOT, 'axisym-safe-python_b200', 'csrc', 'aed.cuh'),
+            os.path.join(ROOT, 'axisym-safe-python_b200', 'csrc', 'aed_variants.cuh'),
             os.path.join(ROOT, 'axisym-safe-python_b200', 'csrc', 'common.cuh')]
     if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
         subprocess.run([nvcc, '-x', 'cu', '-DAED_HOST', '-O2', '-Wno-deprecated-gpu-targets', '-o', exe, src], check=True)
     return exe
 
 
-def _aed_run(exe, mode, H, l, u, nw, nb=8, reg=0):
-    """reg = 1: the register-resident window routine (aed_window_reg) on the emulated warp of
-    tests/host/warp_emul.h; reg = 0: the shared-memory routine (aed_window) as sequential code."""
+def _aed_run(exe, mode, H, l, u, nw, nb=8, reg=0, seed=None):
+    """reg = 0: the product routine (aed_window, shared memory) as sequential code; reg = 1 / 2: the A/B
+    formulations of csrc/aed_variants.cuh (aed_window_reg / aed_window_flat) on the emulated warp of
+    tests/host/warp_emul.h; seed: the emulator visits the lanes in a pseudo-random order (race check)."""
     import struct
     import subprocess
     import tempfile
@@ -248,7 +250,11 @@ def _aed_run(exe, mode, H, l, u, nw, nb=8, reg=0):
         with open(fi, 'wb') as f:
             f.write(struct.pack('5i', n, l, u, nw, nb))
             f.write(np.asarray(H, dtype=complex).tobytes(order='F'))
-        subprocess.run([exe, mode, fi, fo], check=True, env=dict(os.environ, AED_REG=str(int(reg))))
+        env = dict(os.environ, AED_REG=str(int(reg)))
+        env.pop('WEMU_SEED', None)
+        if seed is not None:
+            env['WEMU_SEED'] = str(seed)
+        subprocess.run([exe, mode, fi, fo], check=True, env=env)
         raw = open(fo, 'rb').read()
     if mode == 'solve':
         return struct.unpack('5i', raw[:20]), np.frombuffer(raw[20:], dtype=complex)
@@ -268,7 +274,7 @@ def _safe_hessenberg(i, nf=2000):
     return np.triu(la.hessenberg(Sb), -1), np.linalg.eigvals(S)
 
 
-@pytest.mark.parametrize('reg', [0, 1], ids=['shared', 'registers'])
+@pytest.mark.parametrize('reg', [0, 1, 2], ids=['shared', 'registers', 'one-loop'])
 def test_aed_window_is_a_similarity(reg):
     """One AED call (zlaqr2 semantics): Z unitary, Z^H W Z = T with T Hessenberg in its leading ns x ns
     part and triangular below, the spike vector reduced to one entry, every deflated eigenvalue
@@ -321,12 +327,13 @@ def test_aed_window_is_a_similarity(reg):
     assert deflated_total > 0
 
 
-def test_aed_register_window_matches_shared_window():
-    """The register-resident routine (lane 4 i + p owns T(i, 2p..2p+1), Z likewise; rotations through
-    shuffles) against the shared-memory routine on 60 windows (sizes 2..8, SAFE Hessenberg blocks and
-    random nearly decoupled ones): same number of deflations and QR sweeps, same shifts; T and Z are both
-    valid Schur data of the same window (checked in test_aed_window_is_a_similarity), compared loosely
-    because Schur vectors of close eigenvalues are ill-conditioned."""
+def test_aed_variants_match_the_product_window():
+    """The A/B formulations against the product routine on 60 windows (sizes 2..8, SAFE Hessenberg blocks
+    and random nearly decoupled ones).  The register-resident routine (lane 4 i + p owns T(i, 2p..2p+1), Z
+    likewise; rotations through shuffles): same number of deflations and QR sweeps, same shifts; T and Z are
+    both valid Schur data of the same window (test_aed_window_is_a_similarity), compared loosely because
+    Schur vectors of close eigenvalues are ill-conditioned.  The one-loop routine: bit-identical.  Both give
+    bit-identical results whatever order the emulated warp runs its lanes in (no missing warp barrier)."""
     exe = _aed_host_exe()
     rng = np.random.default_rng(1)
     H, _ = _safe_hessenberg(700)
@@ -344,6 +351,11 @@ def test_aed_register_window_matches_shared_window():
         nw = min(nw, u - l + 1)
         a = _aed_run(exe, 'window', Hm, l, u, nw, reg=0)
         b = _aed_run(exe, 'window', Hm, l, u, nw, reg=1)
+        f = _aed_run(exe, 'window', Hm, l, u, nw, reg=2)
+        raw = lambda o: [v if isinstance(v, int) else np.asarray(v).tobytes() for v in o]
+        assert raw(f) == raw(a), (l, u, nw)
+        for variant, first in ((1, b), (2, f)):
+            assert raw(_aed_run(exe, 'window', Hm, l, u, nw, reg=variant, seed=len(tests) + l + u)) == raw(first)
         assert a[:3] == b[:3], (a[:3], b[:3], l, u, nw)
         ns = a[0]
         deflated += nw - ns
@@ -357,7 +369,7 @@ def test_aed_register_window_matches_shared_window():
     assert deflated > 20
 
 
-@pytest.mark.parametrize('reg', [0, 1], ids=['shared', 'registers'])
+@pytest.mark.parametrize('reg', [0, 1, 2], ids=['shared', 'registers', 'one-loop'])
 @pytest.mark.parametrize('i', [3, 1400])
 def test_aed_solve_matches_zgeev_and_cuts_the_sweeps(i, reg):
     """The kernel's batch loop with the AED window in front of every batch (host model): same
