@@ -10,7 +10,7 @@ of solver.py:119-182 replaced by batched sm_100a kernels:
     A(w), S = Binv A          solver.py:121-134           k_reduce (S built in-kernel)
     scipy.linalg.eig (zgeev)  solver.py:136               k_reduce + k_hqr + k_modes
     vec^T B vec normalisation solver.py:142               fused into k_modes
-    biorth = psi^T B psi, argmax   solver.py:157-161      k_bpsi + k_track_gemm
+    biorth = psi^T B psi, argmax   solver.py:157-161      k_bpsi + k_track_mma
     permutation bookkeeping   solver.py:159-182           axs_track_scan (host, integers)
     reorder val / vec         solver.py:176-182           k_apply_order
 

@@ -56,7 +56,6 @@ static AxsTuning* tuning_mut(void)
         t.backnorm_wy = env_int("AXS_BACKNORM_WY", 1);
         t.backnorm_wy_modes = env_int("AXS_BACKNORM_WY_MODES", 64);
         t.bpsi_tiled = env_int("AXS_BPSI_TILED", 1);
-        t.track_fma = env_int("AXS_TRACK_FMA", 0);
         t.big_blocked = env_int("AXS_BIG_BLOCKED", 1);
         t.big_panel = env_int("AXS_BIG_PANEL", 32);
         t.big_qr_cluster = env_int("AXS_BIG_QR_CLUSTER", 0);
@@ -81,7 +80,6 @@ static int* tuning_field(const char* name)
     if (!strcmp(name, "backnorm_wy")) return &t->backnorm_wy;
     if (!strcmp(name, "backnorm_wy_modes")) return &t->backnorm_wy_modes;
     if (!strcmp(name, "bpsi_tiled")) return &t->bpsi_tiled;
-    if (!strcmp(name, "track_fma")) return &t->track_fma;
     if (!strcmp(name, "big_blocked")) return &t->big_blocked;
     if (!strcmp(name, "big_panel")) return &t->big_panel;
     if (!strcmp(name, "big_qr_cluster")) return &t->big_qr_cluster;

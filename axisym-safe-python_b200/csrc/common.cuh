@@ -189,7 +189,6 @@ struct AxsTuning {
     int backnorm_wy;        // AXS_BACKNORM_WY: blocked compact-WY back-transformation on DMMA tiles (1)
     int backnorm_wy_modes;  // AXS_BACKNORM_WY_MODES: modes per CTA (64 | 32)
     int bpsi_tiled;         // AXS_BPSI_TILED: tiled B psi kernel (1)
-    int track_fma;          // AXS_TRACK_FMA: scalar-DFMA tracking GEMM instead of DMMA (0)
     int big_blocked;        // AXS_BIG_BLOCKED: large path, blocked multi-CTA Hessenberg reduction (1); 0 = one CTA per frequency
     int big_panel;          // AXS_BIG_PANEL: panel width of the blocked reduction (32)
     int big_qr_cluster;     // AXS_BIG_QR_CLUSTER: CTAs per matrix in the windowed QR (0 = from the batch size; 1, 2, 4, 8)

@@ -1,10 +1,11 @@
 // Mode tracking (solver.py:151-182) for the SAFE sweep.
 //
 //   k_bpsi        Y = B psi  with  B = [[0, K6], [K6, C]]   (banded C, diagonal K6)
-//   k_track_gemm  P = psi_prev^T Y_cur as a shared-memory tiled complex GEMM with a fused
-//                 row arg-max / row-max epilogue (the reference forms the full biorth matrix
-//                 with two dense n2^3 products, solver.py:157, and then only uses
-//                 argmax_c |P[r,c]| and its value, :159-161).
+//   k_track_mma   P = psi_prev^T Y_cur on FP64 tensor-core tiles (DMMA) with a fused row arg-max /
+//                 row-max epilogue (the reference forms the full biorth matrix with two dense
+//                 n2^3 products, solver.py:157, and then only uses argmax_c |P[r,c]| and its
+//                 value, :159-161).  The scalar-DFMA tile kernel it replaced (5.59 vs 2.7 ms per
+//                 2000 points) is in the git history.
 //   k_apply_order column gather of k and psi once the permutation scan has run.
 //   axs_track_scan (host) the sequential integer scan o_i[r] = a_i[o_{i-1}[r]].
 #include "common.cuh"
@@ -84,84 +85,8 @@ k_bpsi_tiled(int N, int hb, int crows, const cplx* __restrict__ Cb, const cplx* 
     }
 }
 
-// P[a][b] = sum_r psiP[r][a] * Y[r][b];  CTA = 32 rows a x all b (<= 192), 256 threads,
-// thread tile 4 (a) x TB (b) with b strided by 64 so shared reads stay conflict-free.
-#define TR_TA 32
-#define TR_KC 8
-#define TR_BMAX 192
-__global__ void __launch_bounds__(256)
-k_track_gemm(int n, const cplx* __restrict__ psi_all, const cplx* __restrict__ Y_all,
-             int* __restrict__ arg_all, double* __restrict__ amax_all)
-{
-    __shared__ cplx sA[TR_KC][TR_TA];
-    __shared__ cplx sB[TR_KC][TR_BMAX];
-    const int p = blockIdx.y;                 // pair: prev = p, cur = p + 1
-    const int a0 = blockIdx.x * TR_TA;
-    const cplx* psiP = psi_all + (long long)p * n * n;
-    const cplx* Y = Y_all + (long long)(p + 1) * n * n;
-    const int tid = threadIdx.x;
-    const int ta = tid >> 5;                  // 0..7   -> rows a0 + ta*4 .. +3
-    const int tb = tid & 31;                  // 0..31  -> cols tb, tb+32, ... (6 of them)
-    cplx acc[4][6];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) acc[i][j] = mk(0, 0);
-
-    for (int r0 = 0; r0 < n; r0 += TR_KC) {
-        for (int idx = tid; idx < TR_KC * TR_TA; idx += 256) {
-            int rr = idx / TR_TA, aa = idx - rr * TR_TA;
-            int r = r0 + rr, a = a0 + aa;
-            sA[rr][aa] = (r < n && a < n) ? psiP[(long long)r * n + a] : mk(0, 0);
-        }
-        for (int idx = tid; idx < TR_KC * TR_BMAX; idx += 256) {
-            int rr = idx / TR_BMAX, bb = idx - rr * TR_BMAX;
-            int r = r0 + rr;
-            sB[rr][bb] = (r < n && bb < n) ? Y[(long long)r * n + bb] : mk(0, 0);
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int rr = 0; rr < TR_KC; ++rr) {
-            cplx av[4], bv[6];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) av[i] = sA[rr][ta * 4 + i];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) bv[j] = sB[rr][tb + 32 * j];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 6; ++j) acc[i][j] = cfma(av[i], bv[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-    // epilogue: per row a, arg-max over b of |P|^2 (first index wins on ties, like np.argmax)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double best = -1.0;
-        int bi = 0;
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            int b = tb + 32 * j;
-            double m2 = (b < n) ? cabs2(acc[i][j]) : -1.0;
-            if (m2 > best) { best = m2; bi = b; }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-        }
-        if (tb == 0) {
-            int a = a0 + ta * 4 + i;
-            if (a < n) {
-                arg_all[(long long)p * n + a] = bi;
-                amax_all[(long long)p * n + a] = sqrt(best);
-            }
-        }
-    }
-}
-
 // -----------------------------------------------------------------------------------------
-// k_track_mma: the same contraction P = psi_prev^T Y on the FP64 tensor path
+// k_track_mma: the contraction P[a][b] = sum_r psiP[r][a] * Y[r][b] on the FP64 tensor path
 // (mma.sync.aligned.m8n8k4.f64, "DMMA"; tcgen05 has no FP64 kind).  A complex product is four
 // real MMAs per 8x8x4 tile: Pre += Are Bre + (-Aim) Bim,  Pim += Are Bim + Aim Bre.
 // CTA = 32 rows (a) x all columns (b <= 192), 8 warps; warp w owns the n8 column tiles
@@ -406,10 +331,6 @@ extern "C" int axs_launch_track(int N, int hb, const cplx* Cb, const cplx* K6d, 
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    if (axs_tuning()->track_fma && n <= TR_BMAX) {                // scalar-FMA tiles (kept for A/B)
-        k_track_gemm<<<dim3((n + TR_TA - 1) / TR_TA, npairs), 256, 0, st>>>(n, psi, Y, arg, amax);
-        return (int)cudaGetLastError();
-    }
     size_t smem = (size_t)(TM_KC * TM_SA + TM_KC * TM_SB) * sizeof(cplx) + 8 * 32 * (sizeof(double) + sizeof(int));
     AXS_SMEM_ONCE(smem, k_track_mma);
     k_track_mma<<<dim3((n + 31) / 32, npairs), 256, smem, st>>>(n, psi, Y, arg, amax);

@@ -127,7 +127,7 @@ int axs_hqr_stats(int N, int nf, const void* work, int* stats, void* stream);
 /* Kernel-selection switches (A/B measurements and the variant parity tests).  Every switch is read
  * ONCE from the environment variable AXS_<NAME> when the library is first used; afterwards it can be
  * changed with axs_set_tuning.  Names: reduce_oc, reduce_prebal, hqr_stages, hqr_bulges,
- * hqr_small_direct, hqr_aed, hqr_aed_reg, hqr_aed_stages, backnorm_wy, backnorm_wy_modes, bpsi_tiled, track_fma, big_blocked,
+ * hqr_small_direct, hqr_aed, hqr_aed_reg, hqr_aed_stages, backnorm_wy, backnorm_wy_modes, bpsi_tiled, big_blocked,
  * big_panel, big_qr_cluster.  Return 0, or -1 for an unknown name.  Not thread safe against concurrent launches. */
 int axs_set_tuning(const char* name, int value);
 int axs_get_tuning(const char* name, int* value);
