@@ -385,3 +385,94 @@ def test_aed_solve_matches_zgeev_and_cuts_the_sweeps(i, reg):
     assert so.match_eigenvalues(ref, ev8)[1] < 1e-9
     assert aed[2] > 0 and aed[3] > 0.8 * n               # most eigenvalues deflate inside the window
     assert aed[0] < 0.7 * plain[0], (aed, plain)
+
+
+# --------------------------------------------------- the QR kernel itself on an emulated thread block
+def _hqr_emul_exe():
+    """tests/host/hqr_emul: csrc/hqr_mb.cuh (the product's multi-bulge QR kernel) compiled as plain C++
+    against tests/host/shim/cuda_runtime.h and run on the emulated CTA of tests/host/cta_emul.h."""
+    import shutil
+    import subprocess
+    gxx = shutil.which('g++')
+    if gxx is None:
+        pytest.skip('g++ not available')
+    host = os.path.join(ROOT, 'tests', 'host')
+    csrc = os.path.join(ROOT, 'axisym-safe-python_b200', 'csrc')
+    exe = os.path.join(host, 'hqr_emul')
+    deps = [os.path.join(host, 'hqr_emul.cpp'), os.path.join(host, 'cta_emul.h'),
+            os.path.join(host, 'shim', 'cuda_runtime.h')] + \
+           [os.path.join(csrc, h) for h in ('hqr_mb.cuh', 'aed.cuh', 'common.cuh')]
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run([gxx, '-std=c++17', '-O2', '-I', os.path.join(host, 'shim'), '-o', exe,
+                        os.path.join(host, 'hqr_emul.cpp')], check=True)
+    return exe
+
+
+def _hqr_emul_run(exe, H, aed=0, mask=15, bulges=8, seed=None):
+    import struct
+    import subprocess
+    import tempfile
+    n = H.shape[0]
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, 'in'), os.path.join(d, 'out')
+        with open(fi, 'wb') as f:
+            f.write(struct.pack('5i', n, aed, mask, bulges, 0))
+            f.write(np.asarray(H, dtype=complex).tobytes(order='F'))
+        env = dict(os.environ)
+        env.pop('CTA_SEED', None)
+        if seed is not None:
+            env['CTA_SEED'] = str(seed)
+        subprocess.run([exe, fi, fo], check=True, env=env)
+        raw = open(fo, 'rb').read()
+    info, macro, batches, aed_calls, _, launches = struct.unpack('6i', raw[:24])
+    return dict(info=info, macro=macro, batches=batches, aed_calls=aed_calls, launches=launches), \
+        np.frombuffer(raw[24:], dtype=complex)
+
+
+def _case_hessenberg(case, i):
+    import scipy.linalg as la
+    from oracle import safe_oracle as so
+    G = so.assemble(so.build_mesh(case['sets'], case['fmax'], case['PML'], case['PML_props']), case['n'])
+    S = so.S_matrix(so.operators(G, case['n']), 2 * np.pi * case['f'][i])
+    Sb, _ = la.matrix_balance(S, permute=False)
+    return np.triu(la.hessenberg(Sb), -1), np.linalg.eigvals(S)
+
+
+HQR_EMUL_CASES = [('pipe_soil_pml', {'nf': 2000}, 700, 4), ('free_steel_pipe', {}, 100, 1), ('muggleton_submerged', {}, 50, 1),
+                  ('aristegui', {}, 20, 4)]
+
+
+@pytest.mark.parametrize('name,kw,i,launches', HQR_EMUL_CASES, ids=[c[0] for c in HQR_EMUL_CASES])
+def test_hqr_kernel_on_emulated_cta(name, kw, i, launches):
+    """k_hqr_mb - the product kernel source, every instance of the shrinking-window cascade the problem
+    size selects (2N = 126: four launches at 1 / 2 / 3 / 4 CTAs per SM; 2N = 110: four launches from the
+    2-per-SM instance down; 2N = 68: the 5-per-SM instance alone; 2N = 30: the 128-thread instance) -
+    on the emulated thread block: LAPACK's eigenvalues (1e-9 after the unitary Hessenberg reduction of
+    SciPy), no unconverged eigenvalue, the expected number of launches; with the early-deflation window
+    (8 and 6) the same spectrum in fewer macro steps."""
+    from axisafe_b200 import cases
+    from oracle import safe_oracle as so
+    exe = _hqr_emul_exe()
+    H, ref = _case_hessenberg(getattr(cases, name)(**kw), i)
+    st, ev = _hqr_emul_run(exe, H)
+    assert st['info'] == 0 and st['launches'] == launches and st['aed_calls'] == 0
+    assert so.match_eigenvalues(ref, ev)[1] < 1e-9
+    for aed in (8, 6):
+        st_a, ev_a = _hqr_emul_run(exe, H, aed=aed)
+        assert st_a['info'] == 0 and st_a['aed_calls'] > 0
+        assert so.match_eigenvalues(ref, ev_a)[1] < 1e-9
+        assert st_a['macro'] < st['macro']
+
+
+def test_hqr_kernel_has_no_shared_memory_race():
+    """Between two barriers the emulated threads run one after the other; CTA_SEED shuffles that order
+    in every scheduling round.  A kernel without shared-memory races gives bit-identical eigenvalues and
+    counters for every order (512 threads, 2N = 126, ~7800 block barriers; also with the one-warp
+    early-deflation window between the sweeps and with fewer bulges in flight)."""
+    exe = _hqr_emul_exe()
+    H, _ = _safe_hessenberg(1400)
+    for aed, bulges in ((0, 8), (8, 8), (0, 5)):
+        st0, ev0 = _hqr_emul_run(exe, H, aed=aed, bulges=bulges)
+        for seed in (1, 2):
+            st, ev = _hqr_emul_run(exe, H, aed=aed, bulges=bulges, seed=seed)
+            assert st == st0 and np.array_equal(ev, ev0), (aed, bulges, seed)
