@@ -27,7 +27,7 @@ struct State {
     std::vector<ucontext_t> ctx;
     std::vector<std::vector<char>> stack;
     std::vector<char> done;
-    int nthreads = 0, alive = 0, cur = 0, block = 0;
+    int nthreads = 0, alive = 0, cur = 0, block = 0, block_y = 0;
     long progress = 0, barriers = 0;
     Rendezvous block_bar, warp_bar[MAX_THREADS / 32];
     double xb[MAX_THREADS][2];
@@ -38,7 +38,7 @@ struct State {
 static State g;
 
 static inline Uint3 thread_idx() { return Uint3{(unsigned)g.cur, 0, 0}; }
-static inline Uint3 block_idx() { return Uint3{(unsigned)g.block, 0, 0}; }
+static inline Uint3 block_idx() { return Uint3{(unsigned)g.block, (unsigned)g.block_y, 0}; }
 static inline Uint3 block_dim() { return Uint3{(unsigned)g.nthreads, 1, 1}; }
 
 static void yield_() { const int me = g.cur; swapcontext(&g.ctx[me], &g.main_ctx); g.cur = me; }
@@ -85,9 +85,10 @@ static void trampoline(int tid)
     swapcontext(&g.ctx[tid], &g.main_ctx);
 }
 
-// run body() on every thread of a CTA of `nthreads` threads (blockIdx.x = block) to completion
-static void run(int nthreads, int block, std::function<void()> body)
+// run body() on every thread of a CTA of `nthreads` threads (blockIdx = (block, block_y)) to completion
+static void run(int nthreads, int block, std::function<void()> body, int block_y = 0)
 {
+    g.block_y = block_y;
     if (nthreads > MAX_THREADS || nthreads % 32) { fprintf(stderr, "cta: bad block size %d\n", nthreads); abort(); }
     g.body = body; g.nthreads = g.alive = nthreads; g.block = block;
     g.block_bar = Rendezvous();
