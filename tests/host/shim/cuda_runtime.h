@@ -36,3 +36,5 @@ static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int atomicMax(int* p, int v) { const int old = *p; if (v > old) *p = v; return old; }
 static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 static inline long long clock64() { static long long c = 0; return c += 7; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+static inline int min(int a, int b) { return a < b ? a : b; }

@@ -521,3 +521,64 @@ def test_modes_kernel_on_emulated_cta(name, kw, i):
     assert np.array_equal(_modes_emul_run(exe, H, ev, seed=5), X)
     if H.shape[0] <= 68:                                 # two-warp CTAs (16 modes per CTA) give the same vectors
         assert np.array_equal(_modes_emul_run(exe, H, ev, nw=2), X)
+
+
+SWEEP_EMUL_CASES = [('pipe_soil_pml', dict(nf=2000), 700), ('aristegui', {}, 50), ('nguyen', dict(n=1), 40)]
+
+
+@pytest.mark.parametrize('name,kw,i', SWEEP_EMUL_CASES, ids=[c[0] for c in SWEEP_EMUL_CASES])
+def test_frequency_point_on_emulated_gpu(name, kw, i):
+    """One frequency point through the product's own kernel sources on the emulated thread block
+    (tests/host/sweep_emul.cpp): k_balance -> k_reduce_oc -> k_hqr_mb cascade -> k_modes -> k_backnorm, i.e.
+    scipy.linalg.eig + B-normalisation of reference solver.py:136-142, without a GPU.  2N = 126 and 110 take
+    the 12-warp padded reduction and the leader-isolated QR stage 1, 2N = 166 (the largest size of the
+    shared-memory path) the 8-warp unpadded reduction, the plain stage 1 and three-warp k_modes CTAs.
+    Bars as on the GPU: balancing factors identical to LAPACK's zgebal, eigenvalues within the 1e-8
+    bar (conditioning allowance as in the GPU tests), psi^T B psi = I, upper half = k x lower half, mode
+    shapes within 1e-6 of the oracle's B-normalised zgeev vectors."""
+    import struct
+    import subprocess
+    import tempfile
+    import scipy.linalg as la
+    from axisafe_b200 import cases
+    from oracle import safe_oracle as so
+    exe = _emul_exe('sweep_emul', ('reduce_oc.cuh', 'hqr_mb.cuh', 'modes.cuh', 'backnorm.cuh', 'aed.cuh', 'common.cuh'))
+    c = getattr(cases, name)(**kw)
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), c['n'])
+    op = so.operators(G, c['n'])
+    w = 2 * np.pi * c['f'][i]
+    N = op['N']
+    n2 = 2 * N
+    S = so.S_matrix(op, w)
+    C = op['C']
+    r, cc = np.nonzero(C)
+    hb = int(np.abs(r - cc).max())
+    Cb = np.zeros([N, 2 * hb + 1], dtype=complex)                  # banded rows: Cb[r, c - r + hb] = C[r, c]
+    for d in range(-hb, hb + 1):
+        idx = np.arange(max(0, -d), min(N, N - d))
+        Cb[idx, d + hb] = C[idx, idx + d]
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, 'in'), os.path.join(d, 'out')
+        with open(fi, 'wb') as f:
+            f.write(struct.pack('5i', N, hb, 0, 0, 0))
+            f.write(np.asarray(S, dtype=complex).tobytes(order='F'))
+            f.write(Cb.tobytes())
+            f.write(np.diag(op['K6']).astype(complex).tobytes())
+        subprocess.run([exe, fi, fo], check=True)
+        raw = open(fo, 'rb').read()
+    info, launches = struct.unpack('2i', raw[:8])
+    scale = np.frombuffer(raw[8:8 + 8 * n2], dtype=float)
+    k = np.frombuffer(raw[8 + 8 * n2:8 + 24 * n2], dtype=complex)
+    psi = np.frombuffer(raw[8 + 24 * n2:], dtype=complex).reshape(n2, n2)
+    assert info == 0
+    _, (ref_scale, _) = la.matrix_balance(S, permute=False, separate=True)
+    assert np.array_equal(scale, ref_scale)
+    val, vec = so.eig_normalised(op, w)
+    perm, _ = so.match_eigenvalues(val, k)
+    assert np.all(np.abs(val - k[perm]) <= so.eig_tolerance(S, val))
+    if name == 'pipe_soil_pml':
+        assert np.all(np.abs(val - k[perm]) <= 1e-8 * np.abs(val))       # flagship: plain bar
+    assert np.abs(psi[:N] - k * psi[N:]).max() <= 1e-13 * np.abs(psi[:N]).max()
+    assert np.abs(np.diag(psi.T @ op['B'] @ psi) - 1).max() < 1e-9
+    errs = [so.mode_shape_error(vec[N:, [j]], psi[N:, [perm[j]]])[0] for j in range(n2)]
+    assert max(errs) <= 1e-6, max(errs)
