@@ -27,7 +27,7 @@ struct State {
     std::vector<ucontext_t> ctx;
     std::vector<std::vector<char>> stack;
     std::vector<char> done;
-    int nthreads = 0, alive = 0, cur = 0, block = 0, block_y = 0;
+    int nthreads = 0, alive = 0, cur = 0, block = 0, block_y = 0, grid_x = 1, grid_y = 1;
     long progress = 0, barriers = 0;
     Rendezvous block_bar, warp_bar[MAX_THREADS / 32];
     double xb[MAX_THREADS][2];
@@ -40,6 +40,7 @@ static State g;
 static inline Uint3 thread_idx() { return Uint3{(unsigned)g.cur, 0, 0}; }
 static inline Uint3 block_idx() { return Uint3{(unsigned)g.block, (unsigned)g.block_y, 0}; }
 static inline Uint3 block_dim() { return Uint3{(unsigned)g.nthreads, 1, 1}; }
+static inline Uint3 grid_dim() { return Uint3{(unsigned)g.grid_x, (unsigned)g.grid_y, 1}; }
 
 static void yield_() { const int me = g.cur; swapcontext(&g.ctx[me], &g.main_ctx); g.cur = me; }
 
@@ -86,9 +87,9 @@ static void trampoline(int tid)
 }
 
 // run body() on every thread of a CTA of `nthreads` threads (blockIdx = (block, block_y)) to completion
-static void run(int nthreads, int block, std::function<void()> body, int block_y = 0)
+static void run(int nthreads, int block, std::function<void()> body, int block_y = 0, int grid_x = 1, int grid_y = 1)
 {
-    g.block_y = block_y;
+    g.block_y = block_y; g.grid_x = grid_x; g.grid_y = grid_y;
     if (nthreads > MAX_THREADS || nthreads % 32) { fprintf(stderr, "cta: bad block size %d\n", nthreads); abort(); }
     g.body = body; g.nthreads = g.alive = nthreads; g.block = block;
     g.block_bar = Rendezvous();

@@ -24,6 +24,7 @@ typedef int cudaError_t;
 #define threadIdx (cta::thread_idx())
 #define blockIdx (cta::block_idx())
 #define blockDim (cta::block_dim())
+#define gridDim (cta::grid_dim())
 #define AXS_DYNAMIC_SMEM(name) unsigned char* const name = cta::g.dyn_smem
 
 static inline void __syncthreads() { cta::syncthreads(); }
@@ -38,3 +39,7 @@ static inline double rsqrt(double x) { return 1.0 / sqrt(x); }
 static inline long long clock64() { static long long c = 0; return c += 7; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline int min(int a, int b) { return a < b ? a : b; }
+static inline double atomicAdd(double* p, double v) { const double old = *p; *p = old + v; return old; }
+static inline float __double2float_rn(double x) { return (float)x; }
+static inline int __shfl_xor_sync(unsigned, int v, int m) { return (int)cta::shfl((double)v, (int)(cta::g.cur & 31) ^ m); }
+static inline int __shfl_sync(unsigned, int v, int src) { return (int)cta::shfl((double)v, src); }

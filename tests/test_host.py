@@ -5,7 +5,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, CASE_IDS, ROOT, load_golden, make_case
+from conftest import GOLDEN_CASES, CASE_IDS, ROOT, load_golden, golden_dense, make_case
 
 
 def test_quadrature_invariants():
@@ -582,3 +582,254 @@ def test_frequency_point_on_emulated_gpu(name, kw, i):
     assert np.abs(np.diag(psi.T @ op['B'] @ psi) - 1).max() < 1e-9
     errs = [so.mode_shape_error(vec[N:, [j]], psi[N:, [perm[j]]])[0] for j in range(n2)]
     assert max(errs) <= 1e-6, max(errs)
+
+
+# ----------------------------------------------------------- kernel 1 on the emulated thread block
+def _element_arrays(elements):
+    """Descriptor / table / node arrays of a list of element objects, as _native.element_matrices builds them."""
+    from axisafe_b200 import shape_functions as sf
+    tables, table_off, cache = [], {}, 0
+    desc_i, desc_d, nodes, offsets, sizes = [], [], [], [], []
+    node_off = out_off = 0
+    for el in elements:
+        (kind, family, pml, m), dbl = el._descriptor()
+        key = (family, m)
+        if key not in table_off:
+            ksi, w = (sf.build_GLJ_quadrature if family == 1 else sf.build_GLL_quadrature)(m)
+            D = (sf.lagrange_GLJ if family == 1 else sf.lagrange_poly)(ksi)[1]
+            table_off[key] = cache
+            block = np.concatenate([ksi, w, D.ravel()])
+            tables.append(block)
+            cache += len(block)
+        nd = (3 if kind == 0 else 1) * m
+        desc_i.append([kind, family, pml, m, table_off[key], node_off, out_off, 0])
+        desc_d.append(list(dbl) + [0.0] * (12 - len(dbl)))
+        nodes.append(np.asarray(el.nodes_at, dtype=np.float64))
+        offsets.append(out_off)
+        sizes.append(nd)
+        node_off += m
+        out_off += 10 * nd * nd
+    return desc_i, desc_d, tables, nodes, offsets, sizes, out_off
+
+
+def _elements_emulated(elements):
+    """k_element_matrices on the emulated thread block for stand-alone element objects; installs the results."""
+    import struct
+    import subprocess
+    import tempfile
+    exe = _emul_exe('assemble_emul', ('assemble_kernels.cuh', 'common.cuh'))
+    desc_i, desc_d, tables, nodes, offsets, sizes, out_off = _element_arrays(elements)
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, 'in'), os.path.join(d, 'out')
+        with open(fi, 'wb') as f:
+            tab, nod = np.concatenate(tables), np.concatenate(nodes)
+            # no scatter targets: one DOF, every local DOF unmapped (-1)
+            full = sum(el._full_dofs for el in elements)
+            lm_off = np.cumsum([0] + [el._full_dofs for el in elements])[:-1]
+            f.write(struct.pack('10i', len(elements), len(tab), len(nod), out_off, full, 1, 0, 0, 0, 0))
+            for a, t in ((desc_i, np.int32), (desc_d, np.float64), (tab, np.float64), (nod, np.float64),
+                         (-np.ones(full), np.int32), (lm_off, np.int32), (np.zeros(1), np.int32)):
+                f.write(np.ascontiguousarray(np.array(a), dtype=t).tobytes())
+        subprocess.run([exe, fi, fo], check=True)
+        host = np.frombuffer(open(fo, 'rb').read(), dtype=complex)[:out_off]
+    for el, off, nd in zip(elements, offsets, sizes):
+        el._load(host[off:off + 10 * nd * nd].reshape(10, nd, nd).copy())
+
+
+def _assemble_emulated(mesh, n, omega):
+    """Mesh.assemble_matrices(n) with the two library calls (axs_element_matrices, axs_assemble_operators) and
+    axs_build_S replaced by the SAME kernels on the emulated thread block (tests/host/assemble_emul.cpp).  The
+    array preparation mirrors _native.element_matrices / _native.assemble_operators; everything else (element
+    objects, DOF numbering, coupling blocks, COO scatter of the global matrices) is the product's host code.
+    Returns (banded K0s, Cb, Mb [N, W], K6d [N], K1c or None, hb, S [nf, 2N, 2N])."""
+    import struct
+    import subprocess
+    import tempfile
+    from axisafe_b200.mesh import _GLOBAL_NAME
+    exe = _emul_exe('assemble_emul', ('assemble_kernels.cuh', 'common.cuh'))
+    mesh.n = n
+    mesh._instantiate_elements(n)
+    mesh._number_dofs()
+    order = sorted(mesh.IEN)
+    elements = [mesh.elements[el] for el in order]
+    desc_i, desc_d, tables, nodes, offsets, sizes, out_off = _element_arrays(elements)
+    N = mesh.no_of_dofs
+    lm_all, lm_off, hb = [], [], 0
+    for el in order:                                      # as _native.assemble_operators
+        obj = mesh.elements[el]
+        reduced = iter(mesh.LM[el])
+        full = [-1 if i in obj._dropped else next(reduced) for i in range(obj._full_dofs)]
+        live = [g for g in full if g >= 0]
+        if live:
+            hb = max(hb, max(live) - min(live))
+        lm_off.append(len(lm_all))
+        lm_all.extend(full)
+    tclass = np.array([0 if t == 1 else 1 for t in mesh.Tdiag], dtype=np.int32)
+
+    def run(hb, K1c, omega):
+        W = 2 * hb + 1
+        with tempfile.TemporaryDirectory() as d:
+            fi, fo = os.path.join(d, 'in'), os.path.join(d, 'out')
+            with open(fi, 'wb') as f:
+                tab, nod = np.concatenate(tables), np.concatenate(nodes)
+                f.write(struct.pack('10i', len(elements), len(tab), len(nod), out_off, len(lm_all), N, hb, int(n),
+                                    len(omega), 0 if K1c is None else 1))
+                for a, t in ((desc_i, np.int32), (desc_d, np.float64), (tab, np.float64), (nod, np.float64),
+                             (lm_all, np.int32), (lm_off, np.int32), (tclass, np.int32)):
+                    f.write(np.ascontiguousarray(np.array(a), dtype=t).tobytes())
+                if K1c is not None:
+                    f.write(np.ascontiguousarray(K1c, dtype=complex).tobytes())
+                f.write(np.ascontiguousarray(omega, dtype=np.float64).tobytes())
+            subprocess.run([exe, fi, fo], check=True)
+            raw = np.frombuffer(open(fo, 'rb').read(), dtype=complex)
+        o = [0]
+
+        def take(cnt, shape):
+            a = raw[o[0]:o[0] + cnt].reshape(shape)
+            o[0] += cnt
+            return a
+        return (take(out_off, -1), take(N * W, (N, W)), take(N * W, (N, W)), take(N * W, (N, W)), take(N, -1),
+                take(len(omega) * 4 * N * N, (len(omega), 2 * N, 2 * N)))
+    host = run(hb, None, [])[0]                           # element matrices first: the coupling blocks need them
+    for el, off, nd in zip(elements, offsets, sizes):
+        el._load(host[off:off + 10 * nd * nd].reshape(10, nd, nd).copy())
+    mesh._coupling_blocks()
+    for name, matrix in mesh._scatter(list(mesh.LM)).items():
+        setattr(mesh, _GLOBAL_NAME[name], matrix)
+    K1c = None
+    if mesh.is_coupled and mesh.K1_coupling is not None and mesh.K1_coupling.nnz:
+        coo = mesh.K1_coupling.tocoo()
+        hb = max(hb, int(np.max(np.abs(coo.row - coo.col))))
+        K1c = np.zeros([N, 2 * hb + 1], complex)
+        np.add.at(K1c, (coo.row, coo.col - coo.row + hb), coo.data)
+    _, K0s, Cb, Mb, K6d, S = run(hb, K1c, omega)
+    return K0s, Cb, Mb, K6d, K1c, hb, S.transpose(0, 2, 1)        # column-major -> [f, r, c]
+
+
+@pytest.mark.parametrize('name,n,kw', GOLDEN_CASES, ids=CASE_IDS)
+def test_assembly_kernels_on_emulated_gpu(name, n, kw):
+    """Kernel 1 without a GPU: k_element_matrices, k_scatter_operators and k_build_S (the product sources on the
+    emulated thread block) inside the product's own host assembly, against the fixtures written by the
+    unmodified reference - the CPU twin of test_gpu_parity.py::test_global_matrices_vs_reference and
+    ::test_S_batch_vs_reference (same bars: global matrices 2e-12, complex64 mass entries bit-exact, banded
+    operators 2e-12 against the oracle, S(w) 1e-11 against the reference's SuperLU-built S)."""
+    import axisafe_b200 as ax
+    from oracle import safe_oracle as so
+    g = load_golden(name, n)
+    c = make_case(name, n, kw)
+    m = ax.mesh.Mesh()
+    m.create(c['sets'], c['fmax'], PML=c['PML'], PML_props=c['PML_props'])
+    w = 2 * np.pi * c['f'][g['pick']]
+    K0s, Cb, Mb, K6d, K1c, hb, S = _assemble_emulated(m, n, w)
+    for key in ('K1', 'K2', 'K3', 'K4', 'K5', 'K6', 'M', 'KF', 'KFt', 'KFz'):
+        ref = golden_dense(g, key)
+        got = getattr(m, key).toarray()
+        assert np.abs(got - ref).max() <= 2e-12 * max(np.abs(ref).max(), 1e-300), key
+    ref_M = golden_dense(g, 'M')
+    sol = [d for d in g['solid_dofs'] if ref_M[d, d] == np.complex64(ref_M[d, d])]
+    assert np.array_equal(m.M.toarray()[sol, sol], ref_M[sol, sol])       # complex64 quirk, exact
+    if bool(g['is_coupled']):
+        ref = golden_dense(g, 'K1_coupling')
+        assert np.abs(m.K1_coupling.toarray() - ref).max() <= 1e-12 * np.abs(ref).max()
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), n)
+    op = so.operators(G, n)
+    N = m.no_of_dofs
+
+    def dense(band):
+        out = np.zeros([N, N], complex)
+        for r in range(N):
+            for col in range(max(0, r - hb), min(N, r + hb + 1)):
+                out[r, col] = band[r, col - r + hb]
+        return out
+    for band, key in ((K0s, 'K0s'), (Cb, 'C'), (Mb, 'M')):
+        assert np.abs(dense(band) - op[key]).max() <= 2e-12 * max(np.abs(op[key]).max(), 1e-300), key
+    assert np.abs(K6d - np.diag(op['K6'])).max() <= 2e-12 * np.abs(op['K6']).max()
+    for j in range(len(w)):
+        assert np.abs(S[j] - g['S'][j]).max() <= 1e-11 * np.abs(g['S'][j]).max()
+
+
+@pytest.mark.parametrize('n', [0, 1, 2])
+@pytest.mark.parametrize('m', [4, 5, 9, 14, 23])
+def test_element_kernel_on_emulated_gpu(m, n):
+    """Every element class x circumferential order x element order through k_element_matrices on the
+    emulated thread block against the oracle's index-form restatement: the CPU twin of
+    test_gpu_parity.py::test_element_matrices_vs_oracle (2e-12; complex64 mass diagonal bit-exact)."""
+    import axisafe_b200 as ax
+    from oracle import safe_oracle as so
+    E = ax.elements
+    lam, mu = ax.misc.young2lame(156e9, 0.2)
+    solid, water, pml = [lam, mu, 7800, 0.03], [2.25e9, 1000, 0], [0.1, 0.01, 6 + 7j]
+    gll = 0.1 + 0.01 * (so.gll(m)[0] + 1) / 2
+    glj = 0.1 * (so.glj(m)[0] + 1) / 2
+    glj[0] = 0.0
+    cases_ = [('SLAX6', E.SLAX6(gll, n), gll, solid, None), ('ALAX6', E.ALAX6(gll, n), gll, water, None),
+              ('SLAX6_core', E.SLAX6_core(glj, n), glj, solid, None),
+              ('ALAX6_core', E.ALAX6_core(glj, n), glj, water, None),
+              ('SLAX6_PML', E.SLAX6_PML(gll, n, pml), gll, solid, pml),
+              ('ALAX6_PML', E.ALAX6_PML(gll, n, pml), gll, water, pml)]
+    for name, el, nodes, mat, p in cases_:
+        el.add_properties(mat)
+    _elements_emulated([c[1] for c in cases_])
+    for name, el, nodes, mat, p in cases_:
+        ref = so.element_matrices(name, nodes, mat, n, p)
+        for key in ('K_1', 'K_2', 'K_3', 'K_4', 'K_5', 'K_6', 'K_F', 'K_Ft', 'K_Fz', 'M'):
+            a, b = np.asarray(getattr(el, key)), ref[key]
+            assert a.shape == b.shape, (name, key, a.shape, b.shape)
+            assert np.abs(a - b).max() <= 2e-12 * max(np.abs(b).max(), 1e-300), (name, key)
+        if name in ('SLAX6', 'SLAX6_core'):
+            assert el.M.dtype == np.complex64
+            assert np.array_equal(np.diag(el.M), np.diag(ref['M'])), name   # fp32 rounding, bit exact
+        for key in ('Hs0', 'Hs1', 'Hf0', 'Hf1'):
+            if key in ref:
+                assert np.allclose(getattr(el, key), ref[key], rtol=1e-15, atol=0), (name, key)
+
+
+def test_tracking_kernels_on_emulated_gpu():
+    """k_bpsi_tiled / k_bpsi (Y = B psi), k_track_mma (P = psi_prev^T Y on FP64 tensor-core tiles - the one
+    inline-PTX instruction replaced by a lane-collective model of the m8n8k4 fragment layout,
+    tests/host/shim/dmma.h - with the fused row arg-max) and k_apply_order on the emulated thread block, for six
+    consecutive frequencies of the flagship sweep with the oracle's B-normalised zgeev vectors as input: the
+    arg-max table is bit-exact against NumPy's |psi^T B psi|.argmax(axis=1), the row maxima agree to 1e-9 and
+    the column gather equals NumPy's take - the CPU twin of test_gpu_parity.py::test_track_pairs_vs_numpy."""
+    import struct
+    import subprocess
+    import tempfile
+    from axisafe_b200 import cases
+    from oracle import safe_oracle as so
+    exe = _emul_exe('track_emul', ('track_kernels.cuh', 'common.cuh'))
+    c = cases.pipe_soil_pml(nf=2000)
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), c['n'])
+    op = so.operators(G, c['n'])
+    N, n2, nf = op['N'], 2 * op['N'], 6
+    vals, psis = zip(*[so.eig_normalised(op, 2 * np.pi * f) for f in c['f'][700:700 + nf]])
+    k, psi = np.array(vals), np.array(psis)
+    C = op['C']
+    r, cc = np.nonzero(C)
+    hb = int(np.abs(r - cc).max())
+    Cb = np.zeros([N, 2 * hb + 1], dtype=complex)
+    for d in range(-hb, hb + 1):
+        idx = np.arange(max(0, -d), min(N, N - d))
+        Cb[idx, d + hb] = C[idx, idx + d]
+    rng = np.random.default_rng(3)
+    order = np.array([rng.permutation(n2) for _ in range(nf)], dtype=np.int32)
+    for tiled in (1, 0):
+        with tempfile.TemporaryDirectory() as d:
+            fi, fo = os.path.join(d, 'in'), os.path.join(d, 'out')
+            with open(fi, 'wb') as f:
+                f.write(struct.pack('5i', N, hb, nf, tiled, 0))
+                for a in (Cb, np.diag(op['K6']).astype(complex), np.ascontiguousarray(psi), order, np.ascontiguousarray(k)):
+                    f.write(a.tobytes())
+            subprocess.run([exe, fi, fo], check=True)
+            raw = open(fo, 'rb').read()
+        o = (nf - 1) * n2
+        arg = np.frombuffer(raw[:4 * o], dtype=np.int32).reshape(nf - 1, n2)
+        amax = np.frombuffer(raw[4 * o:12 * o], dtype=float).reshape(nf - 1, n2)
+        rest = np.frombuffer(raw[12 * o:], dtype=complex)
+        k_sorted, psi_sorted = rest[:nf * n2].reshape(nf, n2), rest[nf * n2:].reshape(nf, n2, n2)
+        for p in range(nf - 1):
+            P = np.abs(psi[p].T @ op['B'] @ psi[p + 1])
+            assert np.array_equal(arg[p], P.argmax(axis=1)), (tiled, p)
+            assert np.abs(amax[p] - P.max(axis=1)).max() < 1e-9
+        for f in range(nf):
+            assert np.array_equal(k_sorted[f], k[f][order[f]])
+            assert np.array_equal(psi_sorted[f], psi[f][:, order[f]])
