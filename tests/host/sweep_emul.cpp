@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE: the eigen-solve of ONE frequency point through the product's own kernel sources on
 // the emulated thread block of cta_emul.h - what the GPU does for every point of the sweep, without a GPU:
-//   k_balance (S given dense, zgebal scaling)  ->  k_reduce_oc (on-chip Householder Hessenberg reduction)
+//   k_balance (S given dense, zgebal scaling)  ->  k_reduce_oc (on-chip Householder Hessenberg reduction; 2N < 96:
+//   k_reduce, the L2-resident one)
 //   ->  k_hqr_mb cascade (eigenvalues)  ->  k_modes (inverse iteration)  ->  k_backnorm (back-transformation,
 //   un-balancing, B-normalisation, psi_hat layout).
 // 2N <= 128 normally runs the DMMA back-transformation (eig_backx.cu, mma.sync inline PTX - not emulated);
@@ -14,6 +15,7 @@
 #include "shim/cuda_runtime.h"
 #include "shim/cuda_pipeline.h"
 #include "../../axisym-safe-python_b200/csrc/reduce_oc.cuh"
+#include "../../axisym-safe-python_b200/csrc/reduce_l2.cuh"
 #include "../../axisym-safe-python_b200/csrc/hqr_mb.cuh"
 #include "../../axisym-safe-python_b200/csrc/modes.cuh"
 #include "../../axisym-safe-python_b200/csrc/backnorm.cuh"
@@ -81,7 +83,7 @@ int main(int argc, char** argv)
     int hdr[5];
     if (fread(hdr, sizeof(int), 5, fi) != 5) return 4;
     const int N = hdr[0], hb = hdr[1], n = 2 * N, W = 2 * hb + 1;
-    if (n < 96 || n > AXS_MAX_SMALL_N2) { fprintf(stderr, "the on-chip reduction serves 96 <= 2N <= %d\n", AXS_MAX_SMALL_N2); return 8; }
+    if (n < 4 || n > AXS_MAX_SMALL_N2) { fprintf(stderr, "the shared-memory eigen path serves 2N <= %d\n", AXS_MAX_SMALL_N2); return 8; }
     std::vector<cplx> S((size_t)n * n), Cb((size_t)N * W), K6d(N), eig(n), psi((size_t)n * n);
     if (fread(S.data(), sizeof(cplx), S.size(), fi) != S.size()) return 5;
     if (fread(Cb.data(), sizeof(cplx), Cb.size(), fi) != Cb.size()) return 5;
@@ -91,11 +93,15 @@ int main(int argc, char** argv)
     AxsWork wk;
     axs_work_layout(n, 1, (void*)(((uintptr_t)buf.data() + 255) & ~(uintptr_t)255), &wk);
     int info = 0;
-    // ---- axs_launch_reduce_oc ----------------------------------------------------------------------
+    // ---- axs_launch_reduce: k_balance, then the on-chip reduction (2N >= 96) or the L2-resident one ---------
     fits(balance_smem(n));
     ++g_launches;
     cta::run(BAL_THREADS, 0, [&] { k_balance(N, hb, nullptr, Cb.data(), nullptr, nullptr, K6d.data(), nullptr, S.data(), wk); });
-    if (n <= 128) launch_oc<12, 4, true>(n, wk);
+    if (n < 96) {
+        fits(reduce_smem(n));
+        ++g_launches;
+        cta::run(RED_THREADS, 0, [&] { k_reduce(N, hb, nullptr, Cb.data(), nullptr, nullptr, K6d.data(), nullptr, S.data(), wk, 1); });
+    } else if (n <= 128) launch_oc<12, 4, true>(n, wk);
     else launch_oc<8, 6, false>(n, wk);
     // ---- axs_launch_hqr ----------------------------------------------------------------------------
     int m2 = capacity(2);

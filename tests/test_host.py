@@ -523,7 +523,8 @@ def test_modes_kernel_on_emulated_cta(name, kw, i):
         assert np.array_equal(_modes_emul_run(exe, H, ev, nw=2), X)
 
 
-SWEEP_EMUL_CASES = [('pipe_soil_pml', dict(nf=2000), 700), ('aristegui', {}, 50), ('nguyen', dict(n=1), 40)]
+SWEEP_EMUL_CASES = [('pipe_soil_pml', dict(nf=2000), 700), ('aristegui', {}, 50), ('nguyen', dict(n=1), 40),
+                    ('free_steel_pipe', dict(n=1), 250), ('muggleton_submerged', {}, 60), ('gravenkamp', dict(n=1), 30)]
 
 
 @pytest.mark.parametrize('name,kw,i', SWEEP_EMUL_CASES, ids=[c[0] for c in SWEEP_EMUL_CASES])
@@ -532,7 +533,9 @@ def test_frequency_point_on_emulated_gpu(name, kw, i):
     (tests/host/sweep_emul.cpp): k_balance -> k_reduce_oc -> k_hqr_mb cascade -> k_modes -> k_backnorm, i.e.
     scipy.linalg.eig + B-normalisation of reference solver.py:136-142, without a GPU.  2N = 126 and 110 take
     the 12-warp padded reduction and the leader-isolated QR stage 1, 2N = 166 (the largest size of the
-    shared-memory path) the 8-warp unpadded reduction, the plain stage 1 and three-warp k_modes CTAs.
+    shared-memory path) the 8-warp unpadded reduction, the plain stage 1 and three-warp k_modes CTAs; 2N = 30,
+    68 and 68 (BASELINE.json configs[1] and [2]: free pipe, submerged pipe) the L2-resident reduction k_reduce
+    behind k_balance and the QR instance that fits the matrix.
     Bars as on the GPU: balancing factors identical to LAPACK's zgebal, eigenvalues within the 1e-8
     bar (conditioning allowance as in the GPU tests), psi^T B psi = I, upper half = k x lower half, mode
     shapes within 1e-6 of the oracle's B-normalised zgeev vectors."""
@@ -542,7 +545,7 @@ def test_frequency_point_on_emulated_gpu(name, kw, i):
     import scipy.linalg as la
     from axisafe_b200 import cases
     from oracle import safe_oracle as so
-    exe = _emul_exe('sweep_emul', ('reduce_oc.cuh', 'hqr_mb.cuh', 'modes.cuh', 'backnorm.cuh', 'aed.cuh', 'common.cuh'))
+    exe = _emul_exe('sweep_emul', ('reduce_oc.cuh', 'reduce_l2.cuh', 'hqr_mb.cuh', 'modes.cuh', 'backnorm.cuh', 'aed.cuh', 'common.cuh'))
     c = getattr(cases, name)(**kw)
     G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), c['n'])
     op = so.operators(G, c['n'])
