@@ -22,8 +22,16 @@ static inline void __pipeline_wait_prior(int n)
     const long done_below = cta::g_batch[cta::g.cur] - n;
     size_t keep = 0;
     for (size_t i = 0; i < q.size(); ++i) {
-        if (q[i].batch < done_below) memcpy(q[i].dst, q[i].src, q[i].bytes);
-        else q[keep++] = q[i];
+        if (q[i].batch < done_below) {
+            if (q[i].src) memcpy(q[i].dst, q[i].src, q[i].bytes);
+            else memset(q[i].dst, 0, q[i].bytes);          // cp.async with a source size of 0: zero fill
+        } else q[keep++] = q[i];
     }
     q.resize(keep);
 }
+
+// the raw-PTX cp.async of csrc/backx_kernels.cuh (16 bytes, zero fill when the source size is 0)
+#define AXS_CP_ASYNC16(dst, src, bytes) \
+    cta::g_pending[cta::g.cur].push_back(cta::PendingCopy{(void*)(dst), (bytes) ? (const void*)(src) : nullptr, 16, cta::g_batch[cta::g.cur]})
+#define AXS_CP_ASYNC_COMMIT() __pipeline_commit()
+#define AXS_CP_ASYNC_WAIT(n) __pipeline_wait_prior(n)

@@ -20,3 +20,4 @@ static inline void dmma(double& d0, double& d1, double a, double b)
     cta::rendezvous(cta::g.warp_bar[w], 32);
     d0 = s0; d1 = s1;
 }
+static inline void dmma8(double& d0, double& d1, double a, double b) { dmma(d0, d1, a, b); }

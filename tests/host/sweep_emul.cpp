@@ -4,21 +4,26 @@
 //   k_reduce, the L2-resident one)
 //   ->  k_hqr_mb cascade (eigenvalues)  ->  k_modes (inverse iteration)  ->  k_backnorm (back-transformation,
 //   un-balancing, B-normalisation, psi_hat layout).
-// 2N <= 128 normally runs the DMMA back-transformation (eig_backx.cu, mma.sync inline PTX - not emulated);
-// k_backnorm is the instance behind backnorm_wy = 0 and for 128 < 2N <= 166, same result to 2.8e-13.
+// 16 <= 2N <= 128 runs BOTH back-transformations on the same k_modes output: the library's default there, the
+// blocked compact-WY kernels k_wy_tfactor + k_backnorm_wy on FP64 tensor-core tiles (DMMA and cp.async through
+// the models of tests/host/shim), and k_backnorm (the per-reflector instance for 128 < 2N <= 166 and behind
+// backnorm_wy = 0); psi is the default path's, the largest relative difference of the two is reported.
 //   build: g++ -std=c++17 -O2 -I tests/host/shim -o tests/host/sweep_emul tests/host/sweep_emul.cpp
 //   usage: sweep_emul <in> <out>
 //   in : int32 N, hb, 0, 0, 0 ; S[(2N)^2] complex128 column-major ; Cb[N][2hb+1] complex128 ; K6d[N] complex128
-//   out: int32 info, launches ; scale[2N] float64 ; k[2N] complex128 ; psi[2N][2N] complex128 (psi_hat layout)
+//   out: int32 info, launches ; float64 max |psi_wy - psi_slab| / max |psi| (-1: one path only) ; scale[2N] float64 ;
+//        k[2N] complex128 ; psi[2N][2N] complex128 (psi_hat layout)
 // The launch logic mirrors axs_launch_reduce_oc (eig_reduce.cu), axs_launch_hqr / hqr_cascade and
 // axs_launch_modes (eig_small.cu); the kernels are the product source.
 #include "shim/cuda_runtime.h"
 #include "shim/cuda_pipeline.h"
+#include "shim/dmma.h"
 #include "../../axisym-safe-python_b200/csrc/reduce_oc.cuh"
 #include "../../axisym-safe-python_b200/csrc/reduce_l2.cuh"
 #include "../../axisym-safe-python_b200/csrc/hqr_mb.cuh"
 #include "../../axisym-safe-python_b200/csrc/modes.cuh"
 #include "../../axisym-safe-python_b200/csrc/backnorm.cuh"
+#include "../../axisym-safe-python_b200/csrc/backx_kernels.cuh"
 #include <vector>
 
 static int g_launches = 0;
@@ -121,15 +126,40 @@ int main(int argc, char** argv)
         ++g_launches;
         cta::run(32 * nw, b, [&] { k_modes(N, hb, Cb.data(), K6d.data(), eig.data(), psi.data(), wk); });
     }
+    std::vector<cplx> X(psi), psi_slab;
     fits(backnorm_smem(n));
     for (int b = 0; b < (n + BN_COLS - 1) / BN_COLS; ++b) {
         ++g_launches;
         cta::run(256, b, [&] { k_backnorm(N, hb, Cb.data(), K6d.data(), eig.data(), psi.data(), wk); });
     }
+    double wy_diff = -1.0;
+    // ---- axs_launch_backnorm_wy (the default for 16 <= 2N <= 128) --------------------------------------
+    const int nblk = (n - 2 + WY_NB - 1) / WY_NB;
+    if (n <= WY_MAX_N && n >= 16 && (long long)nblk * WY_NB * WY_NB <= (long long)hcol_size(n)) {
+        psi_slab = psi;
+        psi = X;
+        cplx* Tg = wk.Hp;                                  // the QR parking buffer is dead by now
+        for (int b = 0; b < nblk; ++b) {
+            ++g_launches;
+            cta::run(32, b, [&] { k_wy_tfactor(n, wk, Tg, nblk); }, 0, nblk, 1);
+        }
+        fits(backnorm_wy_smem(n, 64));
+        for (int b = 0; b < (n + 63) / 64; ++b) {
+            ++g_launches;
+            cta::run(256, b, [&] { k_backnorm_wy<64>(N, hb, Cb.data(), K6d.data(), eig.data(), psi.data(), wk, Tg, nblk); }, 0, (n + 63) / 64, 1);
+        }
+        double top = 0.0, dif = 0.0;
+        for (size_t q = 0; q < psi.size(); ++q) {
+            top = fmax(top, cabs1(psi[q]));
+            dif = fmax(dif, cabs1(csub(psi[q], psi_slab[q])));
+        }
+        wy_diff = dif / top;
+    }
     FILE* fo = fopen(argv[2], "wb");
     if (!fo) return 6;
     int o[2] = {info, g_launches};
     fwrite(o, sizeof(int), 2, fo);
+    fwrite(&wy_diff, sizeof(double), 1, fo);
     fwrite(wk.scale, sizeof(double), n, fo);
     fwrite(eig.data(), sizeof(cplx), n, fo);
     fwrite(psi.data(), sizeof(cplx), psi.size(), fo);
