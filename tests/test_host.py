@@ -524,6 +524,42 @@ def test_modes_kernel_on_emulated_cta(name, kw, i):
         assert np.array_equal(_modes_emul_run(exe, H, ev, nw=2), X)
 
 
+def _sweep_emul_point(name, kw, i, seed=None):
+    """Input preparation + one run of tests/host/sweep_emul for frequency i of a case; returns (op, w, S, raw output)."""
+    import struct
+    import subprocess
+    import tempfile
+    from axisafe_b200 import cases
+    from oracle import safe_oracle as so
+    exe = _emul_exe('sweep_emul', ('reduce_oc.cuh', 'reduce_l2.cuh', 'hqr_mb.cuh', 'modes.cuh', 'backnorm.cuh', 'backx_kernels.cuh', 'aed.cuh', 'common.cuh'))
+    c = getattr(cases, name)(**kw)
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), c['n'])
+    op = so.operators(G, c['n'])
+    w = 2 * np.pi * c['f'][i]
+    N = op['N']
+    S = so.S_matrix(op, w)
+    C = op['C']
+    r, cc = np.nonzero(C)
+    hb = int(np.abs(r - cc).max())
+    Cb = np.zeros([N, 2 * hb + 1], dtype=complex)                  # banded rows: Cb[r, c - r + hb] = C[r, c]
+    for d in range(-hb, hb + 1):
+        idx = np.arange(max(0, -d), min(N, N - d))
+        Cb[idx, d + hb] = C[idx, idx + d]
+    env = dict(os.environ)
+    env.pop('CTA_SEED', None)
+    if seed is not None:
+        env['CTA_SEED'] = str(seed)
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, 'in'), os.path.join(d, 'out')
+        with open(fi, 'wb') as f:
+            f.write(struct.pack('5i', N, hb, 0, 0, 0))
+            f.write(np.asarray(S, dtype=complex).tobytes(order='F'))
+            f.write(Cb.tobytes())
+            f.write(np.diag(op['K6']).astype(complex).tobytes())
+        subprocess.run([exe, fi, fo], check=True, env=env)
+        return op, w, S, open(fo, 'rb').read()
+
+
 SWEEP_EMUL_CASES = [('pipe_soil_pml', dict(nf=2000), 700), ('aristegui', {}, 50), ('nguyen', dict(n=1), 40),
                     ('free_steel_pipe', dict(n=1), 250), ('muggleton_submerged', {}, 60), ('gravenkamp', dict(n=1), 30)]
 
@@ -541,35 +577,11 @@ def test_frequency_point_on_emulated_gpu(name, kw, i):
     bar (conditioning allowance as in the GPU tests), psi^T B psi = I, upper half = k x lower half, mode
     shapes within 1e-6 of the oracle's B-normalised zgeev vectors."""
     import struct
-    import subprocess
-    import tempfile
     import scipy.linalg as la
-    from axisafe_b200 import cases
     from oracle import safe_oracle as so
-    exe = _emul_exe('sweep_emul', ('reduce_oc.cuh', 'reduce_l2.cuh', 'hqr_mb.cuh', 'modes.cuh', 'backnorm.cuh', 'backx_kernels.cuh', 'aed.cuh', 'common.cuh'))
-    c = getattr(cases, name)(**kw)
-    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), c['n'])
-    op = so.operators(G, c['n'])
-    w = 2 * np.pi * c['f'][i]
+    op, w, S, raw = _sweep_emul_point(name, kw, i)
     N = op['N']
     n2 = 2 * N
-    S = so.S_matrix(op, w)
-    C = op['C']
-    r, cc = np.nonzero(C)
-    hb = int(np.abs(r - cc).max())
-    Cb = np.zeros([N, 2 * hb + 1], dtype=complex)                  # banded rows: Cb[r, c - r + hb] = C[r, c]
-    for d in range(-hb, hb + 1):
-        idx = np.arange(max(0, -d), min(N, N - d))
-        Cb[idx, d + hb] = C[idx, idx + d]
-    with tempfile.TemporaryDirectory() as d:
-        fi, fo = os.path.join(d, 'in'), os.path.join(d, 'out')
-        with open(fi, 'wb') as f:
-            f.write(struct.pack('5i', N, hb, 0, 0, 0))
-            f.write(np.asarray(S, dtype=complex).tobytes(order='F'))
-            f.write(Cb.tobytes())
-            f.write(np.diag(op['K6']).astype(complex).tobytes())
-        subprocess.run([exe, fi, fo], check=True)
-        raw = open(fo, 'rb').read()
     info, launches = struct.unpack('2i', raw[:8])
     wy_diff, = struct.unpack('d', raw[8:16])
     scale = np.frombuffer(raw[16:16 + 8 * n2], dtype=float)
@@ -841,3 +853,12 @@ def test_tracking_kernels_on_emulated_gpu():
         for f in range(nf):
             assert np.array_equal(k_sorted[f], k[f][order[f]])
             assert np.array_equal(psi_sorted[f], psi[f][:, order[f]])
+
+
+@pytest.mark.parametrize('name,kw,i', [SWEEP_EMUL_CASES[0], SWEEP_EMUL_CASES[4]], ids=['pipe_soil_pml', 'muggleton_submerged'])
+def test_frequency_point_has_no_shared_memory_race(name, kw, i):
+    """The whole kernel chain of a frequency point (k_balance, k_reduce_oc / k_reduce, k_hqr_mb, k_modes,
+    k_wy_tfactor, k_backnorm_wy, k_backnorm) with the emulated threads visited in a new pseudo-random order
+    between every two barriers: bit-identical output (balancing factors, eigenvalues, mode shapes)."""
+    base = _sweep_emul_point(name, kw, i)[3]
+    assert _sweep_emul_point(name, kw, i, seed=1)[3] == base
