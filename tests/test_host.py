@@ -886,3 +886,61 @@ def test_hqr_kernel_at_the_instance_boundaries():
         st, ev = _hqr_emul_run(exe, H)
         assert st['info'] == 0, (n, kind, st)
         assert so.match_eigenvalues(np.linalg.eigvals(H), ev)[1] < 1e-9, (n, kind)
+
+
+@pytest.mark.parametrize('N', [8, 47, 48, 64, 65])
+def test_frequency_point_random_pencils_at_the_boundaries(N):
+    """The whole kernel chain on the emulated thread block for RANDOM quadratic pencils (K6 diagonal, C banded
+    symmetric, K0 dense symmetric; S = B^-1 A as in solver.py:115-134) at the sizes where the launchers switch
+    instance: 2N = 16 (smallest size of the blocked back-transformation), 94 / 96 (L2-resident vs on-chip
+    reduction), 128 / 130 (padded 12-warp vs unpadded 8-warp reduction; blocked DMMA vs per-reflector
+    back-transformation).  Same checks as on the reference cases; measured 1e-14 .. 5e-12."""
+    import struct
+    import subprocess
+    import tempfile
+    import scipy.linalg as la
+    from oracle import safe_oracle as so
+    exe = _emul_exe('sweep_emul', ('reduce_oc.cuh', 'reduce_l2.cuh', 'hqr_mb.cuh', 'modes.cuh', 'backnorm.cuh', 'backx_kernels.cuh', 'aed.cuh', 'common.cuh'))
+    rng = np.random.default_rng(100 + N)
+    hb = min(N - 1, int(rng.integers(1, 12)))
+    n2 = 2 * N
+    K6 = np.diag(rng.uniform(0.5, 2, N) * np.exp(1j * rng.uniform(-0.3, 0.3, N)))
+    C = np.zeros([N, N], complex)
+    for d in range(-hb, hb + 1):
+        idx = np.arange(max(0, -d), min(N, N - d))
+        C[idx, idx + d] = rng.standard_normal(len(idx)) + 1j * rng.standard_normal(len(idx))
+    C = C + C.T
+    K0 = rng.standard_normal([N, N]) + 1j * rng.standard_normal([N, N])
+    K0 = (K0 + K0.T) * 10.0 ** rng.uniform(-1, 2)
+    B = np.block([[np.zeros([N, N]), K6], [K6, C]])
+    S = np.linalg.solve(B, np.block([[K6, np.zeros([N, N])], [np.zeros([N, N]), -K0]]))
+    Cb = np.zeros([N, 2 * hb + 1], dtype=complex)
+    for d in range(-hb, hb + 1):
+        idx = np.arange(max(0, -d), min(N, N - d))
+        Cb[idx, d + hb] = C[idx, idx + d]
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, 'in'), os.path.join(d, 'out')
+        with open(fi, 'wb') as f:
+            f.write(struct.pack('5i', N, hb, 0, 0, 0))
+            f.write(np.asarray(S, dtype=complex).tobytes(order='F'))
+            f.write(Cb.tobytes())
+            f.write(np.diag(K6).astype(complex).tobytes())
+        subprocess.run([exe, fi, fo], check=True)
+        raw = open(fo, 'rb').read()
+    info, _ = struct.unpack('2i', raw[:8])
+    wy_diff, = struct.unpack('d', raw[8:16])
+    scale = np.frombuffer(raw[16:16 + 8 * n2], dtype=float)
+    k = np.frombuffer(raw[16 + 8 * n2:16 + 24 * n2], dtype=complex)
+    psi = np.frombuffer(raw[16 + 24 * n2:], dtype=complex).reshape(n2, n2)
+    assert info == 0
+    assert (0 <= wy_diff < 1e-11) if n2 <= 128 else wy_diff == -1.0
+    _, (ref_scale, _) = la.matrix_balance(S, permute=False, separate=True)
+    assert np.array_equal(scale, ref_scale)
+    val, vec = la.eig(S)
+    vec = vec / np.sqrt(np.diag(vec.T @ B @ vec))
+    perm, err = so.match_eigenvalues(val, k)
+    assert err < 1e-10
+    assert np.abs(np.diag(psi.T @ B @ psi) - 1).max() < 1e-9
+    assert np.abs(psi[:N] - k * psi[N:]).max() <= 1e-13 * np.abs(psi[:N]).max()
+    errs = [so.mode_shape_error(vec[N:, [j]], psi[N:, [perm[j]]])[0] for j in range(n2)]
+    assert max(errs) < 1e-8, max(errs)
