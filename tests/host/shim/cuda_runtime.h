@@ -13,7 +13,7 @@
 #define __noinline__ __attribute__((noinline))
 #define __shared__ static
 #define __launch_bounds__(...)
-#define __align__(x) alignas(x)
+#define __align__(x) __attribute__((aligned(x)))
 
 struct alignas(16) double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
@@ -43,3 +43,6 @@ static inline double atomicAdd(double* p, double v) { const double old = *p; *p 
 static inline float __double2float_rn(double x) { return (float)x; }
 static inline int __shfl_xor_sync(unsigned, int v, int m) { return (int)cta::shfl((double)v, (int)(cta::g.cur & 31) ^ m); }
 static inline int __shfl_sync(unsigned, int v, int src) { return (int)cta::shfl((double)v, src); }
+static inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }
+static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x, 8); return r; }
+static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { const unsigned long long old = *p; if (v > old) *p = v; return old; }

@@ -21,3 +21,4 @@ static inline void dmma(double& d0, double& d1, double a, double b)
     d0 = s0; d1 = s1;
 }
 static inline void dmma8(double& d0, double& d1, double a, double b) { dmma(d0, d1, a, b); }
+static inline void br_dmma(double& d0, double& d1, double a, double b) { dmma(d0, d1, a, b); }

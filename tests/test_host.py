@@ -944,3 +944,64 @@ def test_frequency_point_random_pencils_at_the_boundaries(N):
     assert np.abs(psi[:N] - k * psi[N:]).max() <= 1e-13 * np.abs(psi[:N]).max()
     errs = [so.mode_shape_error(vec[N:, [j]], psi[N:, [perm[j]]])[0] for j in range(n2)]
     assert max(errs) < 1e-8, max(errs)
+
+
+def _bigred_emul_run(exe, A, nb=32, seed=None):
+    import struct
+    import subprocess
+    import tempfile
+    n = A.shape[0]
+    env = dict(os.environ)
+    env.pop('CTA_SEED', None)
+    if seed is not None:
+        env['CTA_SEED'] = str(seed)
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, 'in'), os.path.join(d, 'out')
+        with open(fi, 'wb') as f:
+            f.write(struct.pack('5i', n, nb, 0, 0, 0))
+            f.write(np.asarray(A, dtype=complex).tobytes(order='F'))
+        subprocess.run([exe, fi, fo], check=True, env=env)
+        raw = open(fo, 'rb').read()
+    launches, ctas, have_q, _ = struct.unpack('4i', raw[:16])
+    a = np.frombuffer(raw[16:], dtype=complex)
+    return dict(launches=launches, ctas=ctas, have_q=have_q, A=a[:n * n].reshape(n, n).T, tau=a[n * n:n * n + n],
+                Q=a[n * n + n:2 * n * n + n].reshape(n, n), Hc=a[2 * n * n + n:]), raw
+
+
+@pytest.mark.parametrize('n,nb', [(168, 32), (294, 32), (200, 16)], ids=['2N=168', '2N=294', 'panel16'])
+def test_blocked_reduction_on_emulated_gpu(n, nb):
+    """North-star kernel (2) without a GPU: the blocked compact-WY Hessenberg reduction with its trailing
+    updates on FP64 tensor-core tiles (k_br_col, k_br_gemv, k_br_gemm<YTOP / RIGHT / LEFTW / LEFTA>, k_br_top,
+    k_br_tw, k_br_pack*) and the blocked back-transformation (k_br_gemm<BXW / BXA>, k_bx_tw, k_bx_scale) -
+    the product sources, launch by launch and CTA by CTA on the emulated thread block, DMMA through the
+    lane-collective model - for 2N = 168 (the smallest size of the large path) and 294: H is upper Hessenberg,
+    Q = (back-transformation of the identity) is unitary, Q^H A Q = H to 1e-13 ||A||, the spectrum is kept and the
+    packed copy handed to the QR kernel equals H.  Panels of 16 keep no T factors (no Q): spectrum only."""
+    import scipy.linalg as la
+    from oracle import safe_oracle as so
+    exe = _emul_exe('bigred_emul', ('bigred_kernels.cuh', 'common.cuh'))
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal([n, n]) + 1j * rng.standard_normal([n, n])
+    A *= (10.0 ** rng.uniform(-1, 1, size=n))[:, None]
+    A = la.matrix_balance(A, permute=False)[0]
+    out, _ = _bigred_emul_run(exe, A, nb)
+    H = np.triu(out['A'], -1)
+    assert so.match_eigenvalues(np.linalg.eigvals(A), np.linalg.eigvals(H))[1] < 1e-11
+    packed = np.concatenate([H[:min(j + 2, n), j] for j in range(n)])          # column j: rows 0 .. j+1
+    assert np.array_equal(out['Hc'][:len(packed)], packed)
+    if nb == 32:
+        Q = out['Q']
+        assert out['have_q'] == 1
+        assert np.abs(Q.conj().T @ Q - np.eye(n)).max() < 1e-13
+        assert np.abs(Q.conj().T @ A @ Q - H).max() < 1e-13 * np.abs(A).max()
+
+
+def test_blocked_reduction_has_no_shared_memory_race():
+    """Same kernels with the emulated threads of every CTA visited in a pseudo-random order between barriers:
+    bit-identical output (the reductions of the reduction have a fixed summation order by construction)."""
+    import scipy.linalg as la
+    exe = _emul_exe('bigred_emul', ('bigred_kernels.cuh', 'common.cuh'))
+    rng = np.random.default_rng(9)
+    n = 168
+    A = la.matrix_balance(rng.standard_normal([n, n]) + 1j * rng.standard_normal([n, n]), permute=False)[0]
+    assert _bigred_emul_run(exe, A, seed=4)[1] == _bigred_emul_run(exe, A)[1]
