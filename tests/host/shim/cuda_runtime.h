@@ -46,3 +46,6 @@ static inline int __shfl_sync(unsigned, int v, int src) { return (int)cta::shfl(
 static inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }
 static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x, 8); return r; }
 static inline unsigned long long atomicMax(unsigned long long* p, unsigned long long v) { const unsigned long long old = *p; if (v > old) *p = v; return old; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
+static inline void __threadfence() {}
+static inline int atomicAdd(int* p, int v) { const int old = *p; *p = old + v; return old; }

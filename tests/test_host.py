@@ -401,7 +401,7 @@ def _emul_exe(name, headers):
     exe = os.path.join(host, name)
     deps = [os.path.join(host, name + '.cpp'), os.path.join(host, 'cta_emul.h'),
             os.path.join(host, 'shim', 'cuda_runtime.h'), os.path.join(host, 'shim', 'cuda_pipeline.h'),
-            os.path.join(host, 'shim', 'dmma.h')] + \
+            os.path.join(host, 'shim', 'dmma.h'), os.path.join(host, 'shim', 'cooperative_groups.h')] + \
            [os.path.join(csrc, h) for h in headers]
     if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(d) for d in deps):
         subprocess.run([gxx, '-std=c++17', '-O2', '-I', os.path.join(host, 'shim'), '-o', exe,
@@ -1005,3 +1005,58 @@ def test_blocked_reduction_has_no_shared_memory_race():
     n = 168
     A = la.matrix_balance(rng.standard_normal([n, n]) + 1j * rng.standard_normal([n, n]), permute=False)[0]
     assert _bigred_emul_run(exe, A, seed=4)[1] == _bigred_emul_run(exe, A)[1]
+
+
+def test_large_path_frequency_point_on_emulated_gpu():
+    """One frequency point of cfg4's mesh family (coated pipe, 2 elements of order 8 per layer, 2N = 294) through
+    the LARGE path on the emulated thread block, ~700 launches of the product's kernel sources: k_reduce_big
+    (balancing) -> blocked compact-WY reduction on DMMA tiles -> k_hqr_big<false> (windowed multi-bulge QR) ->
+    k_hqr_mb cascade -> k_modes_col -> k_backx_slab + k_norm_big, and the blocked DMMA back-transformation on
+    the same vectors.  The CPU twin of test_gpu_big.py::test_coated_pipe_stages_vs_oracle (same bars); the
+    thread-block-cluster instance of the windowed QR stays GPU-only."""
+    import struct
+    import subprocess
+    import tempfile
+    import scipy.linalg as la
+    from axisafe_b200 import cases
+    from oracle import safe_oracle as so
+    exe = _emul_exe('big_emul', ('big_kernels.cuh', 'bigred_kernels.cuh', 'hqr_mb.cuh', 'aed.cuh', 'common.cuh'))
+    c = cases.coated_pipe(nf=4, n=1, elements_per_layer=2, order=8)
+    G = so.assemble(so.build_mesh(c['sets'], c['fmax'], c['PML'], c['PML_props']), c['n'])
+    op = so.operators(G, c['n'])
+    N, w = op['N'], 2 * np.pi * c['f'][2]
+    n2 = 2 * N
+    assert n2 == 294
+    S = so.S_matrix(op, w)
+    C = op['C']
+    r, cc = np.nonzero(C)
+    hb = int(np.abs(r - cc).max())
+    Cb = np.zeros([N, 2 * hb + 1], dtype=complex)
+    for d in range(-hb, hb + 1):
+        idx = np.arange(max(0, -d), min(N, N - d))
+        Cb[idx, d + hb] = C[idx, idx + d]
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, 'in'), os.path.join(d, 'out')
+        with open(fi, 'wb') as f:
+            f.write(struct.pack('5i', N, hb, 0, 0, 0))
+            f.write(np.asarray(S, dtype=complex).tobytes(order='F'))
+            f.write(Cb.tobytes())
+            f.write(np.diag(op['K6']).astype(complex).tobytes())
+        subprocess.run([exe, fi, fo], check=True)
+        raw = open(fo, 'rb').read()
+    info, launches = struct.unpack('2i', raw[:8])
+    blocked_vs_slab, = struct.unpack('d', raw[8:16])
+    scale = np.frombuffer(raw[16:16 + 8 * n2], dtype=float)
+    k = np.frombuffer(raw[16 + 8 * n2:16 + 24 * n2], dtype=complex)
+    psi = np.frombuffer(raw[16 + 24 * n2:], dtype=complex).reshape(n2, n2)
+    assert info == 0 and launches > 600
+    assert blocked_vs_slab < 1e-11
+    _, (ref_scale, _) = la.matrix_balance(S, permute=False, separate=True)
+    assert np.array_equal(scale, ref_scale)
+    val, vec = so.eig_normalised(op, w)
+    perm, _ = so.match_eigenvalues(val, k)
+    assert np.all(np.abs(val - k[perm]) <= so.eig_tolerance(S, val))
+    assert np.abs(psi[:N] - k * psi[N:]).max() <= 1e-13 * np.abs(psi[:N]).max()
+    assert np.abs(np.einsum('ij,ij->j', psi, op['B'] @ psi) - 1).max() < 1e-9
+    errs = so.mode_shape_error(vec[N:], psi[N:][:, perm])
+    assert errs.max() <= 1e-6, errs.max()
