@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ['api.cu', 'assemble.cu', 'eig_small.cu', 'eig_reduce.cu', 'eig_backx.cu', 'eig_big.cu', 'eig_bigred.cu', 'track.cu']
-HEADERS = ['common.cuh', 'aed.cuh', 'aed_variants.cuh', 'hqr_mb.cuh', 'modes.cuh', 'reduce_oc.cuh', 'backnorm.cuh', 'assemble_kernels.cuh', 'track_kernels.cuh', 'reduce_l2.cuh', 'backx_kernels.cuh', 'bigred_kernels.cuh', 'big_kernels.cuh', os.path.join('..', '..', 'include', 'axisafe_b200.h')]
+HEADERS = ['common.cuh', 'aed.cuh', 'aed_variants.cuh', 'hqr_mb.cuh', 'modes.cuh', 'reduce_oc.cuh', 'backnorm.cuh', 'assemble_kernels.cuh', 'track_kernels.cuh', 'reduce_l2.cuh', 'backx_kernels.cuh', 'bigred_kernels.cuh', 'big_kernels.cuh', 'post_kernels.cuh', os.path.join('..', '..', 'include', 'axisafe_b200.h')]
 OUT = os.path.join(HERE, 'axisafe_b200', '_lib', 'libaxisafe_b200.so')
 OBJ = os.path.join(HERE, 'build')
 FLAGS = (['-DOC_TIMING'] if os.environ.get('AXS_OC_TIMING') else []) + (['-DAED_PROFILE'] if os.environ.get('AXS_AED_PROFILE') else []) + [

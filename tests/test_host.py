@@ -1060,3 +1060,71 @@ def test_large_path_frequency_point_on_emulated_gpu():
     assert np.abs(np.einsum('ij,ij->j', psi, op['B'] @ psi) - 1).max() < 1e-9
     errs = so.mode_shape_error(vec[N:], psi[N:][:, perm])
     assert errs.max() <= 1e-6, errs.max()
+
+
+def test_post_processing_kernels_on_emulated_gpu():
+    """k_energy_ratio, k_quad_forms, k_modal_projection (rows N1 / N3 / N4: the dense batched products of
+    reference solver.py:248-266, :374-408, :428-435) and k_rank_modes + k_zero_unselected (the selection behind
+    solve(no_of_waves=m), solver.py:137-140) on the emulated thread block against NumPy, random data."""
+    import struct
+    import subprocess
+    import tempfile
+    exe = _emul_exe('post_emul', ('post_kernels.cuh', 'common.cuh'))
+    rng = np.random.default_rng(21)
+    N, nf, m = 37, 3, 20
+    n = 2 * N
+    crand = lambda *shape: rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    psi = crand(nf, n, n)
+    tclass = rng.integers(0, 2, N).astype(np.int32)
+
+    def coo(nnz):
+        return (rng.integers(0, N, nnz).astype(np.int32), rng.integers(0, N, nnz).astype(np.int32), crand(nnz))
+    Mt, Mp = coo(150), coo(60)
+    mats = [coo(int(z)) for z in (40, 1, 75)]
+    sel = rng.permutation(n)[:11].astype(np.int32)
+    mat_off = np.cumsum([0] + [len(x[0]) for x in mats]).astype(np.int32)
+    rows, cols, vals = (np.concatenate([x[q] for x in mats]) for q in range(3))
+    fvec = crand(n)
+    fvec[:N] = 0
+    k = crand(nf, n)
+    k[1, 5] = k[1, 9]                                            # a tie: the lower native index ranks first
+    sigma = rng.standard_normal(nf)
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, 'in'), os.path.join(d, 'out')
+        with open(fi, 'wb') as f:
+            f.write(struct.pack('8i', N, nf, len(Mt[0]), len(Mp[0]), len(sel), len(mats), len(rows), m))
+            for a in (psi, tclass, Mt[0], Mt[1], Mt[2], Mp[0], Mp[1], Mp[2], sel, mat_off, rows, cols, vals, fvec, k, sigma):
+                f.write(np.ascontiguousarray(a).tobytes())
+        subprocess.run([exe, fi, fo], check=True)
+        raw = open(fo, 'rb').read()
+    o = [0]
+
+    def take(dtype, *shape):
+        cnt = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        a = np.frombuffer(raw[o[0]:o[0] + cnt], dtype=dtype).reshape(shape)
+        o[0] += cnt
+        return a
+    er, forms, proj = take(float, nf, n), take(complex, nf, len(sel), len(mats)), take(complex, nf, n)
+    rank, psi_sel = take(np.int32, nf, n), take(complex, nf, n, n)
+    q = np.where(tclass[None, :, None] == 1, -1j, 1) * psi[:, N:, :]          # conj(T) psi[N:]
+    form = lambda t, qq: np.einsum('fij,ik,fkj->fj', qq.conj(), _coo_dense(t, N), qq)
+    ref_er = np.abs(form(Mp, q)) / np.abs(form(Mt, q))
+    assert np.abs(er - ref_er).max() <= 1e-12 * np.abs(ref_er).max()
+    for mi, t in enumerate(mats):
+        ref = form(t, q[:, :, sel])
+        assert np.abs(forms[:, :, mi] - ref).max() <= 1e-12 * np.abs(ref).max()
+    ref_proj = np.einsum('frj,r->fj', psi, fvec)
+    assert np.abs(proj - ref_proj).max() <= 1e-12 * np.abs(ref_proj).max()
+    for f in range(nf):
+        d2 = (k[f].real - sigma[f]) ** 2 + k[f].imag ** 2
+        ref_rank = np.empty(n, dtype=np.int32)
+        ref_rank[np.lexsort((np.arange(n), d2))] = np.arange(n)
+        assert np.array_equal(rank[f], ref_rank)
+        keep = ref_rank < m
+        assert np.array_equal(psi_sel[f][:, keep], psi[f][:, keep]) and not psi_sel[f][:, ~keep].any()
+
+
+def _coo_dense(t, N):
+    out = np.zeros([N, N], complex)
+    np.add.at(out, (t[0], t[1]), t[2])
+    return out
